@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — vectors scanned/s of the Quick ADC search path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on; it fits one GPU):
+SIFT1B-shaped synthetic flat database, 1e9 vectors x PQ m=16 x 4 bit (8-byte codes),
+r = 100, keep = 0.05 %, sharded contiguously over the N GPUs of the box (strong scaling).
+A step = one batch of `--queries` queries through the whole hot path (float tables, keep-prefix
+scan, bounds, int8 tables, 4-bit scan, top-r, shard merge).  Codes are a counter-based hash of
+the global vector index, so every sharding sees the same database.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the reference's own AVX2 scan (oracle/_ref, the unmodified sources
+compiled by oracle/Makefile) on the host cores with OpenMP over queries, on a bounded sample
+of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM, M, R, KEEP = 128, 16, 100, 0.0005
+SEED = 1234 + 3
+CODE_BYTES = M // 2
+METRIC = "vectors scanned/s/GPU & HBM roofline % (16x4 PQ); queries/s at 1/2/4/8 GPU"
+
+
+def mix64_np(idx):
+    """splitmix64 finaliser on uint64 (one 8-byte code per vector)."""
+    z = (idx + np.uint64(0x9E3779B97F4A7C15) * np.uint64(SEED)).astype(np.uint64)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def codes_np(lo, hi):
+    with np.errstate(over="ignore"):
+        return mix64_np(np.arange(lo, hi, dtype=np.uint64)).view(np.uint8).reshape(-1, CODE_BYTES)
+
+
+def codes_torch(lo, hi, device):
+    """Same generator on the device (int64 arithmetic wraps like uint64)."""
+    import torch
+
+    def c(v):  # uint64 constant as int64
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def lsr(x, s):  # logical shift right on int64
+        return (x >> s) & ((1 << (64 - s)) - 1)
+
+    z = torch.arange(lo, hi, dtype=torch.int64, device=device) + c((0x9E3779B97F4A7C15 * SEED) & ((1 << 64) - 1))
+    z = (z ^ lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    return z.view(torch.uint8).view(-1, CODE_BYTES)
+
+
+def make_quantizer_and_queries(nq):
+    rng = np.random.default_rng(SEED)
+    cb = rng.standard_normal((M, 16, DIM // M)).astype(np.float32)
+    queries = rng.standard_normal((nq, DIM)).astype(np.float32)
+    return cb, queries
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for rw in rows:
+            if len(rw) < 8:
+                continue
+            try:
+                sm.append(float(rw[1])); mx.append(float(rw[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), rw[4:8]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_cpu, nq, threads, steps, warmup, log=None):
+    """The reference's own CPU path (oracle/_ref) on vectors [0, n_cpu) of the same database."""
+    from oracle.pyoracle import Ref
+    if not Ref.available():
+        return None
+    ref = Ref()
+    cb, queries = make_quantizer_and_queries(nq)
+    h = ref.flat(DIM, M, cb, codes_np(0, n_cpu))
+    h.prepare(KEEP if n_cpu * KEEP >= 2 * R else (2.0 * R) / n_cpu)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        h.search(queries, 1, R, nthreads=threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        if log:
+            log(f"cpu step {it}: {dt:.3f}s")
+    h.close()
+    t = float(np.mean(times))
+    return dict(value=n_cpu * nq / t, seconds_per_step=t)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.pyoracle import Ref
+    threads = os.cpu_count() or 1
+    if not Ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libqadc_ref.so not built"}))
+        return
+    n_cpu = min(args.n_vectors, 1 << 25)
+    nq = max(threads, 32) * 2
+    res = cpu_reference_run(n_cpu, nq, threads, args.steps, args.warmup)
+    sample = (f"first {n_cpu} vectors of the same synthetic database, {nq} queries per step, OpenMP over queries "
+              f"around the reference's scanner_4::query_scan")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "vectors/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": workload_config(args, nq, None),
+        "cpu_baseline": {"value": res["value"], "unit": "vectors/s", "cores": threads, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": res["value"], "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, nq, qb):
+    return {"workload": f"SIFT1B-shaped flat PQ m=16x4bit ({args.n_vectors} vectors x 8 B), top-{R}, keep {KEEP * 100:g}%",
+            "n_vectors": args.n_vectors, "dim": DIM, "m": M, "bits": 4, "r": R, "keep": KEEP, "queries_per_step": nq,
+            "queries_per_pass": qb, "sharding": f"flat contiguous x{args.gpus}",
+            "l2": "database per GPU >> 126 MB L2 (no flush needed)" if args.n_vectors // args.gpus * 8 > 512e6
+                  else "L2 flushed between steps"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import qadc_b200
+    from qadc_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, nq = args.n_vectors, args.queries
+    cb, queries = make_quantizer_and_queries(nq)
+
+    stream = torch.cuda.current_stream(dev)
+    ix = qadc_b200.Index(local, stream.cuda_stream)
+    ix.set_pq(DIM, M, cb)
+    lo, hi = sharding.flat_shard_range(N, rank, world)
+    n_local = hi - lo
+    ix.begin_database([n_local], False)
+    chunk = 1 << 24
+    for c0 in range(lo, hi, chunk):
+        c1 = min(c0 + chunk, hi)
+        t = codes_torch(c0, c1, dev)
+        torch.cuda.synchronize(dev)
+        ix.upload_codes_device(0, c0 - lo, c1 - c0, t.data_ptr())
+        del t
+    n_prefix = sharding.start_size(N, KEEP)
+    if world > 1:
+        ix.set_position_base(0, lo)
+        pre = codes_torch(0, n_prefix, dev)
+        torch.cuda.synchronize(dev)
+        ix.set_prefix_device(0, pre.data_ptr(), n_prefix)
+        del pre
+    ix.finalize(KEEP)
+    if args.qb:
+        ix.set_option("flat_qb", args.qb)
+    ix.set_option("time_scan", 1)
+
+    # device-resident buffers (the `value` leg)
+    d_q = torch.from_numpy(queries).to(dev)
+    d_ids = torch.empty((nq, R), dtype=torch.int32, device=dev)
+    d_d = torch.empty((nq, R), dtype=torch.int8, device=dev)
+    d_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    d_keys = torch.empty((nq, R), dtype=torch.int64, device=dev)
+    o_ids, o_d, o_cnt = torch.empty_like(d_ids), torch.empty_like(d_d), torch.empty_like(d_cnt)
+    flush = None
+    if n_local * CODE_BYTES <= 512e6:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    launches = [0]
+
+    def step_device():
+        if flush is not None:
+            flush.fill_(1)
+        ix.search_device(d_q.data_ptr(), nq, 1, R, d_ids.data_ptr(), d_d.data_ptr(), d_cnt.data_ptr(), d_keys.data_ptr())
+        launches[0] += ix.last_launch_count()
+        if world > 1:
+            gk, gi = sharding.all_gather_topk(d_keys, d_ids)
+            ix.merge_shards_device(gk.data_ptr(), gi.data_ptr(), world, nq, R, o_ids.data_ptr(), o_d.data_ptr(), o_cnt.data_ptr())
+            launches[0] += 1
+
+    # host-buffer leg (`e2e`): pinned queries in, pinned results out, copies inside the timed region
+    h_q = torch.from_numpy(queries).pin_memory()
+    h_ids = torch.empty((nq, R), dtype=torch.int32).pin_memory()
+    h_d = torch.empty((nq, R), dtype=torch.int8).pin_memory()
+    h_cnt = torch.empty(nq, dtype=torch.int32).pin_memory()
+    h_keys = torch.empty((nq, R), dtype=torch.int64).pin_memory()
+
+    def step_e2e():
+        if world == 1:
+            ix.search_host_buffers(h_q.data_ptr(), nq, 1, R, h_ids.data_ptr(), h_d.data_ptr(), h_cnt.data_ptr())
+        else:
+            d_q.copy_(h_q, non_blocking=True)
+            step_device()
+            h_ids.copy_(o_ids, non_blocking=True); h_d.copy_(o_d, non_blocking=True); h_cnt.copy_(o_cnt, non_blocking=True)
+            stream.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    for _ in range(args.warmup):
+        step_device()
+    ix.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches[0] = 0
+    scan_ms = []
+
+    def step_device_timed():
+        step_device()
+        scan_ms.append(ix.last_scan_ms())   # CUDA events on the launching stream around the scan kernel
+
+    ms_step = timed(step_device_timed, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    n_launch = launches[0]
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    ix.synchronize()
+
+    # roofline of the dominant kernel (the 4-bit scan): algorithmic bytes = passes x N_local x 8
+    qb_used = args.qb if args.qb else (4 if nq >= 4 else (2 if nq >= 2 else 1))
+    passes = -(-nq // qb_used)
+    t_scan = float(np.mean(scan_ms)) * 1e-3
+    achieved = passes * n_local * CODE_BYTES / t_scan / 1e9
+    peak, peak_src = measured_peak_hbm()
+
+    if rank == 0:
+        value = N * nq / (ms_step * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "vectors/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": workload_config(args, nq, qb_used),
+            "queries_per_s": nq / (ms_step * 1e-3),
+            "e2e": {"value": N * nq / (ms_e2e * 1e-3), "unit": "vectors/s", "h2d_bytes_per_step": int(queries.nbytes),
+                    "d2h_bytes_per_step": int(nq * R * 5 + nq * 4), "ms_per_step": ms_e2e},
+            "gpu_launches": n_launch,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "scan_flat_kernel",
+                         "kernel_ms": t_scan * 1e3, "kernel_share_of_step": t_scan * 1e3 / ms_step,
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "algorithmic_bytes_per_launch": passes * n_local * CODE_BYTES},
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            n_cpu = min(N, 1 << 24)
+            nq_cpu = max(2 * threads, 32)
+            res = cpu_reference_run(n_cpu, nq_cpu, threads, 2, 1)
+            if res:
+                line["cpu_baseline"] = {"value": res["value"], "unit": "vectors/s", "cores": threads, "kind": "reference",
+                                        "sample": f"reference scanner_4 (AVX2, oracle/_ref) on the first {n_cpu} vectors of "
+                                                  f"the same database, {nq_cpu} queries, OpenMP over queries"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ix.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-vectors", type=int, default=int(os.environ.get("QADC_BENCH_N", 10 ** 9)))
+    ap.add_argument("--queries", type=int, default=16)
+    ap.add_argument("--qb", type=int, default=1, help="queries per pass of the flat scan (0 = library default)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,163 @@
+/* qadc_b200.h — C ABI of the B200-native Quick ADC search path (libqadc_b200.so).
+ *
+ * The reference (technicolor-research/quick-adc) has no FFI: its search path sits behind
+ * two compile-time concepts, the Scanner (scanner_4, db_query_4.cpp:73-310) and the Engine
+ * (nns_engine / nns_engine_batch, query_common.hpp:149-309).  The kept C++ host mirror in
+ * quick-adc_b200/host/ implements those concepts on top of the entry points below, which
+ * are exactly what a maintainer of the reference would bind.
+ *
+ * Conventions: plain C types, caller-allocated outputs, every function returns 0 on
+ * success or a negative QADC_E* code (message via qadc_last_error); the reference's
+ * behaviour on the same conditions is `std::cerr << ...; std::exit(1)`, which the host
+ * mirror reproduces.  One context = one GPU = one host thread at a time.  There is no CPU
+ * fallback: every entry point fails with QADC_ECUDA when no sm_100 device is usable.
+ *
+ * Data formats (all [probe]-verified against the reference):
+ *   codes      row-major, m/2 bytes per vector, code[b] = idx[2b] | idx[2b+1] << 4
+ *              (quantizers.hpp:49-68) — what base_db::get_partition returns
+ *   codebooks  m x 16 x (dim/m) floats, flat (quantizers.hpp:160-168)
+ *   qtables    int8, [query][probe][m][16], entry c at byte c (db_query_4.cpp:65-68)
+ *   tables     float, [query][probe][m][16] (query_common.hpp:235-237)
+ *   ids        flat: position in the database; IVF: labels[partition][position]
+ *
+ * Result rule (the stated deterministic tie-break, SURVEY §8c Stage S): for each query the
+ * r smallest records under the total order (distance, probe_rank, position) among scanned
+ * vectors with distance < 127, sorted by that order, padded with (id 0, distance 127) —
+ * the sentinel the reference seeds its heap with (db_query_4.cpp:276).  Per-vector
+ * distances are min(127, sum_j qtable[j][code_j]), bit-exact with scan_avx_4
+ * (simd_scan.hpp:125-187).
+ */
+#ifndef QADC_B200_H
+#define QADC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QADC_ABI_VERSION 1
+
+enum {
+    QADC_OK = 0,
+    QADC_EINVAL = -1,   /* bad argument / unsupported configuration (reference: exit(1)) */
+    QADC_ECUDA = -2,    /* CUDA error or no sm_100 device */
+    QADC_ESTATE = -3,   /* call order violated (e.g. search before finalize) */
+    QADC_EBOUND = -4,   /* "Max quantization bound too high" (db_query_4.cpp:271-274):
+                           fewer than r vectors in the probed keep-prefixes */
+    QADC_ENOMEM = -5
+};
+
+typedef struct qadc_ctx qadc_ctx;
+
+/* Per-batch phase times in microseconds, the reference's query_metrics fields
+ * (query_common.hpp:21-56), measured with CUDA events on the context's stream. */
+typedef struct qadc_metrics {
+    double index_us;   /* coarse assignment + residuals      (query_common.hpp:284-286) */
+    double rotate_us;  /* OPQ rotation                       (:288-289) */
+    double table_us;   /* float lookup tables                (:291-297) */
+    double scan_us;    /* prefix scan + quantise + scan + top-r (:299-303) */
+    double h2d_us, d2h_us; /* host<->device copies of qadc_search (not in the reference) */
+} qadc_metrics;
+
+int qadc_abi_version(void);
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (e.g. torch's current stream),
+ * or NULL for a context-owned stream. */
+int qadc_create(int device, void* stream, qadc_ctx** out);
+void qadc_destroy(qadc_ctx* ctx);
+/* Message of the last failing call on ctx (ctx == NULL: last qadc_create failure). */
+const char* qadc_last_error(const qadc_ctx* ctx);
+
+/* ---- quantisers ----------------------------------------------------------------------- */
+/* Replaces base_pq / opq state (quantizers.hpp:96-168, :248-301).  bits must be 4 and m in
+ * {16, 32} (get_simd_scan_func_epi8, db_query_4.cpp:23-35).  rotation: dim*dim row-major
+ * (opq::rotation) or NULL for a plain PQ.  Host pointers. */
+int qadc_set_pq(qadc_ctx* ctx, int dim, int m, int bits, const float* codebooks,
+                const float* rotation);
+/* Replaces index_db::centroids (databases.hpp:176-189): K*dim floats. K == 0 / never
+ * called = flat database (flat_db: one partition, assign = 0, residual = query). */
+int qadc_set_coarse(qadc_ctx* ctx, int K, const float* centroids);
+
+/* ---- database upload = scanner_4::prepare_database (db_query_4.cpp:98-228) ------------ */
+/* sizes[p] = vectors of partition p held by THIS context (0 allowed: "Partition is empty",
+ * db_query_4.cpp:113-116).  has_labels: IVF partitions carry labels, flat ones do not
+ * (mixing is an error in the reference too, :118-124). */
+int qadc_begin_database(qadc_ctx* ctx, int partition_count, const uint32_t* sizes,
+                        int has_labels);
+/* Copies vectors [first, first+count) of partition part_i (row-major codes and, if the
+ * database has labels, their labels) and re-lays them out on the device.  `first` must be
+ * a multiple of 256.  on_device != 0: codes/labels are device pointers.  The caller keeps
+ * ownership (the reference's scanner then calls db.free_partition, db_query_4.cpp:190). */
+int qadc_upload_codes(qadc_ctx* ctx, int part_i, uint32_t first, uint32_t count,
+                      const uint8_t* codes, const uint32_t* labels, int on_device);
+/* Sharded databases only: position of this context's first vector inside the full
+ * partition (flat database split across GPUs), default 0. */
+int qadc_set_position_base(qadc_ctx* ctx, int part_i, uint32_t pos_base);
+/* Sharded databases only: explicit keep-prefix of partition part_i (row-major codes of the
+ * first `count` vectors of the FULL partition), replicated on every shard so that all
+ * shards derive identical quantisation bounds.  Overrides the prefix finalize derives. */
+int qadc_set_prefix(qadc_ctx* ctx, int part_i, const uint8_t* codes, uint32_t count,
+                    int on_device);
+/* keep: fraction of each partition scanned in float to bound the quantiser,
+ * starts_sizes[p] = max(1, (unsigned)(size * keep)) in float32 (db_query_4.cpp:125-126). */
+int qadc_finalize(qadc_ctx* ctx, float keep);
+
+/* ---- search: the call engine_gpu makes once per query batch --------------------------- */
+/* Host buffers in, host buffers out (H2D/D2H inside).  queries: nq*dim.  ma: probes per
+ * query (must be 1 for a flat database).  out_ids/out_dists: nq*r; out_counts[q]: number
+ * of real (non-sentinel) entries.  metrics may be NULL.
+ * Replaces nns_engine_batch::batch_process_queries + scanner_4::query_scan per query
+ * (query_common.hpp:194-242, db_query_4.cpp:245-309). */
+int qadc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, uint32_t* out_ids,
+                int8_t* out_dists, int32_t* out_counts, qadc_metrics* metrics);
+/* Same with device-resident buffers, asynchronous on the context's stream.  out_keys
+ * (nq*r uint64, optional) receives the canonical sort keys
+ * (distance << 48 | probe_rank << 32 | position) used to merge shards. */
+int qadc_search_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r,
+                       uint32_t* d_ids, int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys);
+/* Waits for the context's stream and reports deferred device-side conditions of earlier
+ * asynchronous calls (QADC_EBOUND from qadc_search_device). */
+int qadc_synchronize(qadc_ctx* ctx);
+/* Number of kernels launched by the last search call (bench accounting). */
+int qadc_last_launch_count(const qadc_ctx* ctx);
+/* Device time in milliseconds of the scan kernel(s) of the last search call (CUDA events on
+ * the context's stream around the scan launches; synchronises the stream). */
+int qadc_last_scan_ms(qadc_ctx* ctx, float* ms);
+
+/* Merge the local top-r lists of G shards (device buffers laid out [G][nq][r], as an NCCL
+ * all-gather leaves them) into the global top-r under the same total order. */
+int qadc_merge_shards_device(qadc_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_ids,
+                             int G, int nq, int r, uint32_t* d_out_ids, int8_t* d_out_dists,
+                             int32_t* d_out_counts, uint64_t* d_out_keys);
+
+/* ---- parity entry points (host buffers) ------------------------------------------------ */
+/* Stage T: assignment, float tables, bounds and int8 tables for a batch.  assign_in
+ * (nq*ma, optional) injects a coarse assignment instead of computing it.  Any output may
+ * be NULL.  Returns QADC_EBOUND if some query's prefix holds fewer than r vectors. */
+int qadc_build_tables(qadc_ctx* ctx, const float* queries, int nq, int ma, int r,
+                      const int32_t* assign_in, int32_t* out_assign, float* out_tables,
+                      float* out_qmin, float* out_qmax, int8_t* out_qtables);
+/* Stage S with injected int8 tables (the bit-exact stage): assign nq*ma, qtables
+ * nq*ma*m*16 with every entry in [0,127]. */
+int qadc_scan_with_tables(qadc_ctx* ctx, const int32_t* assign, const int8_t* qtables, int nq,
+                          int ma, int r, uint32_t* out_ids, int8_t* out_dists,
+                          int32_t* out_counts);
+/* Stage D: the quantised distance of every vector of partition part_i for one int8 table
+ * (m*16), out[size]. */
+int qadc_dump_distances(qadc_ctx* ctx, int part_i, const int8_t* qtable, int8_t* out);
+/* The device layout read back as row-major codes (layout round-trip test). */
+int qadc_download_codes(qadc_ctx* ctx, int part_i, uint8_t* out_codes);
+
+/* ---- tuning knobs (bench / tests) ------------------------------------------------------ */
+/* key: "flat_qb" (queries per pass of the flat scan: 1,2,4,8), "flat_chunks" (CTAs along
+ * the database, 0 = auto), "time_scan" (1: record CUDA events around the scan kernel for
+ * qadc_last_scan_ms).  Unknown key -> QADC_EINVAL. */
+int qadc_set_option(qadc_ctx* ctx, const char* key, long value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QADC_B200_H */

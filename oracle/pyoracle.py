@@ -240,6 +240,8 @@ class Ref:
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_query_scan.restype = C.c_int
         L.ref_query_scan.argtypes = [C.c_void_p, i32p, C.c_int, f32p, C.c_int, u32p, i8p]
+        L.ref_query_bounds.argtypes = [C.c_void_p, i32p, C.c_int, f32p, C.c_int, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float)]
         L.ref_search.restype = C.c_int
         L.ref_search.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u32p, i8p,
                                  i32p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -313,6 +315,13 @@ class Ref:
             a = np.ascontiguousarray(assign, np.int32)
             n = self.ref.lib.ref_query_scan(self.ptr, a, len(a), t, r, keys, vals)
             return keys, vals, n
+
+        def query_bounds(self, assign, tables, r):
+            t = np.array(tables, np.float32, order="C", copy=True).reshape(-1)
+            a = np.ascontiguousarray(assign, np.int32)
+            qmin, qmax = C.c_float(), C.c_float()
+            self.ref.lib.ref_query_bounds(self.ptr, a, len(a), t, r, C.byref(qmin), C.byref(qmax))
+            return qmin.value, qmax.value
 
         def search(self, queries, ma, r, nthreads=1, blas_tables=False, want_tables=False):
             queries = np.ascontiguousarray(queries, np.float32)

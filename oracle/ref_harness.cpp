@@ -249,6 +249,19 @@ __attribute__((visibility("default"))) int ref_query_scan(
     return bh.size();
 }
 
+// The quantiser bounds exactly as scanner_4::query_scan derives them (db_query_4.cpp:250-259):
+// query_scan_start over the probed prefixes, then min_element over all ma tables (before the
+// negative clamp).
+__attribute__((visibility("default"))) void ref_query_bounds(
+        void* handle, int* assign, int ma, float* tables, int r, float* qmin, float* qmax) {
+    auto h = static_cast<ref_handle*>(handle);
+    const int table_dim = h->db->pq->sq_count * 16;
+    kv_binheap<unsigned, float> tmp_bh(r);
+    h->scanner->query_scan_start(assign, ma, tables, table_dim, tmp_bh);
+    *qmin = *std::min_element(tables, tables + (long)ma * table_dim);
+    *qmax = tmp_bh.max();
+}
+
 // Full per-query path = body of nns_engine::process_query (query_common.hpp:278-307) with
 // thread-local scratch, run for nq queries under OpenMP (nthreads; 1 = the reference's own
 // sequential loop). use_blas_tables: 0 = what `-b1` does (single_simd when ma==1, blas form

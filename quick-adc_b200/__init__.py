@@ -1,0 +1,258 @@
+"""quick-adc_b200 — B200-native Quick ADC search path.
+
+This package is a thin ctypes binding over the C ABI in include/qadc_b200.h
+(libqadc_b200.so, hand-written CUDA for sm_100a).  It is what tests/ and bench.py use; the
+drop-in C++ host mirror of the reference's scanner/engine API lives in host/.
+
+There is NO CPU path: everything here fails loudly when the CUDA library is missing or no
+sm_100 device is present.  Import with ``importlib.import_module("quick-adc_b200")`` (the
+directory name carries the reference's hyphen) or through the ``qadc_b200`` alias module at
+the repository root.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libqadc_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "qadc_b200.h")
+
+QADC_OK, QADC_EINVAL, QADC_ECUDA, QADC_ESTATE, QADC_EBOUND, QADC_ENOMEM = 0, -1, -2, -3, -4, -5
+
+
+class QadcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"qadc error {code}: {msg}")
+        self.code = code
+
+
+class Metrics(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("index_us", "rotate_us", "table_us", "scan_us", "h2d_us", "d2h_us")]
+
+
+_lib = None
+
+
+def load_library(build_if_missing=True):
+    """Loads libqadc_b200.so (building it with nvcc when absent or stale). Never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and os.path.exists("/usr/local/cuda/bin/nvcc"):
+        try:
+            _build.build()
+        except Exception as e:  # a stale .so is still better than none; a missing one is fatal below
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(f"cannot build libqadc_b200.so: {e}")
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, f32 = C.c_void_p, C.c_int, C.c_uint32, C.c_float
+    L.qadc_abi_version.restype = i32
+    L.qadc_create.argtypes = [i32, vp, C.POINTER(vp)]
+    L.qadc_destroy.argtypes = [vp]
+    L.qadc_destroy.restype = None
+    L.qadc_last_error.argtypes = [vp]
+    L.qadc_last_error.restype = C.c_char_p
+    L.qadc_set_pq.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.qadc_set_coarse.argtypes = [vp, i32, vp]
+    L.qadc_begin_database.argtypes = [vp, i32, vp, i32]
+    L.qadc_upload_codes.argtypes = [vp, i32, u32, u32, vp, vp, i32]
+    L.qadc_set_position_base.argtypes = [vp, i32, u32]
+    L.qadc_set_prefix.argtypes = [vp, i32, vp, u32, i32]
+    L.qadc_finalize.argtypes = [vp, f32]
+    L.qadc_search.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.qadc_search_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.qadc_synchronize.argtypes = [vp]
+    L.qadc_last_launch_count.argtypes = [vp]
+    L.qadc_last_scan_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.qadc_merge_shards_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.qadc_build_tables.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.qadc_scan_with_tables.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    L.qadc_dump_distances.argtypes = [vp, i32, vp, vp]
+    L.qadc_download_codes.argtypes = [vp, i32, vp]
+    L.qadc_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    for name in ("qadc_create", "qadc_set_pq", "qadc_set_coarse", "qadc_begin_database", "qadc_upload_codes",
+                 "qadc_set_position_base", "qadc_set_prefix", "qadc_finalize", "qadc_search", "qadc_search_device",
+                 "qadc_synchronize", "qadc_last_launch_count", "qadc_last_scan_ms", "qadc_merge_shards_device",
+                 "qadc_build_tables", "qadc_scan_with_tables", "qadc_dump_distances", "qadc_download_codes",
+                 "qadc_set_option"):
+        getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """numpy array / int device pointer / None -> void*."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Index:
+    """One GPU-resident Quick ADC database = scanner_4 + engine state (db_query_4.cpp:73-310,
+    query_common.hpp:149-309) behind the C ABI."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.qadc_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc:
+            raise QadcError(rc, self.lib.qadc_last_error(None).decode())
+        self.h = h
+        self.dim = self.m = 0
+        self.K = 0
+
+    def _ck(self, rc):
+        if rc:
+            raise QadcError(rc, self.lib.qadc_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.qadc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- quantisers ---------------------------------------------------------------------
+    def set_pq(self, dim, m, codebooks, rotation=None, bits=4):
+        cb = np.ascontiguousarray(codebooks, np.float32).reshape(-1)
+        rot = None if rotation is None else np.ascontiguousarray(rotation, np.float32).reshape(-1)
+        self._ck(self.lib.qadc_set_pq(self.h, dim, m, bits, _ptr(cb), _ptr(rot)))
+        self.dim, self.m = dim, m
+
+    def set_coarse(self, centroids):
+        c = np.ascontiguousarray(centroids, np.float32)
+        self._ck(self.lib.qadc_set_coarse(self.h, c.shape[0], _ptr(c)))
+        self.K = c.shape[0]
+
+    # ---- database -----------------------------------------------------------------------
+    def begin_database(self, sizes, has_labels):
+        s = np.ascontiguousarray(sizes, np.uint32)
+        self._ck(self.lib.qadc_begin_database(self.h, len(s), _ptr(s), int(has_labels)))
+        self.sizes = s
+
+    def upload_codes(self, part_i, first, codes, labels=None):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        lab = None if labels is None else np.ascontiguousarray(labels, np.uint32)
+        self._ck(self.lib.qadc_upload_codes(self.h, part_i, first, codes.shape[0], _ptr(codes), _ptr(lab), 0))
+
+    def upload_codes_device(self, part_i, first, count, d_codes, d_labels=None):
+        self._ck(self.lib.qadc_upload_codes(self.h, part_i, first, count, _ptr(int(d_codes)),
+                                            _ptr(None if d_labels is None else int(d_labels)), 1))
+
+    def set_position_base(self, part_i, base):
+        self._ck(self.lib.qadc_set_position_base(self.h, part_i, base))
+
+    def set_prefix(self, part_i, codes):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        self._ck(self.lib.qadc_set_prefix(self.h, part_i, _ptr(codes), codes.shape[0], 0))
+
+    def set_prefix_device(self, part_i, d_codes, count):
+        self._ck(self.lib.qadc_set_prefix(self.h, part_i, _ptr(int(d_codes)), count, 1))
+
+    def finalize(self, keep):
+        self._ck(self.lib.qadc_finalize(self.h, np.float32(keep)))
+
+    def load_flat(self, codes, keep):
+        """flat_db: one partition, no labels (databases.hpp:77-134)."""
+        codes = np.ascontiguousarray(codes, np.uint8)
+        self.begin_database([codes.shape[0]], False)
+        self.upload_codes(0, 0, codes)
+        self.finalize(keep)
+
+    def load_ivf(self, codes, labels, offsets, keep):
+        """index_db: partition p = rows offsets[p]:offsets[p+1] of codes/labels (databases.hpp:176-250)."""
+        offsets = np.asarray(offsets, np.int64)
+        sizes = np.diff(offsets).astype(np.uint32)
+        self.begin_database(sizes, True)
+        for p in range(len(sizes)):
+            if sizes[p]:
+                self.upload_codes(p, 0, codes[offsets[p]:offsets[p + 1]], labels[offsets[p]:offsets[p + 1]])
+        self.finalize(keep)
+
+    # ---- search -------------------------------------------------------------------------
+    def search(self, queries, ma, r, want_metrics=False):
+        q = np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        ids = np.empty((nq, r), np.uint32)
+        d = np.empty((nq, r), np.int8)
+        cnt = np.empty(nq, np.int32)
+        met = Metrics()
+        self._ck(self.lib.qadc_search(self.h, _ptr(q), nq, ma, r, _ptr(ids), _ptr(d), _ptr(cnt), C.byref(met)))
+        return (ids, d, cnt, met) if want_metrics else (ids, d, cnt)
+
+    def search_host_buffers(self, q_ptr, nq, ma, r, ids_ptr, d_ptr, cnt_ptr):
+        """qadc_search on raw host pointers (pinned buffers owned by the caller)."""
+        self._ck(self.lib.qadc_search(self.h, _ptr(int(q_ptr)), nq, ma, r, _ptr(int(ids_ptr)), _ptr(int(d_ptr)),
+                                      _ptr(int(cnt_ptr)), None))
+
+    def search_device(self, d_queries, nq, ma, r, d_ids, d_dists, d_counts, d_keys=None):
+        self._ck(self.lib.qadc_search_device(self.h, _ptr(int(d_queries)), nq, ma, r, _ptr(int(d_ids)),
+                                             _ptr(int(d_dists)), _ptr(int(d_counts)),
+                                             _ptr(None if d_keys is None else int(d_keys))))
+
+    def synchronize(self):
+        self._ck(self.lib.qadc_synchronize(self.h))
+
+    def merge_shards_device(self, d_keys, d_ids, G, nq, r, d_out_ids, d_out_dists, d_out_counts, d_out_keys=None):
+        self._ck(self.lib.qadc_merge_shards_device(self.h, _ptr(int(d_keys)), _ptr(None if d_ids is None else int(d_ids)),
+                                                   G, nq, r, _ptr(int(d_out_ids)), _ptr(int(d_out_dists)),
+                                                   _ptr(int(d_out_counts)),
+                                                   _ptr(None if d_out_keys is None else int(d_out_keys))))
+
+    def last_launch_count(self):
+        return self.lib.qadc_last_launch_count(self.h)
+
+    def last_scan_ms(self):
+        ms = C.c_float()
+        self._ck(self.lib.qadc_last_scan_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_option(self, key, value):
+        self._ck(self.lib.qadc_set_option(self.h, key.encode(), int(value)))
+
+    # ---- parity entry points ------------------------------------------------------------
+    def build_tables(self, queries, ma, r, assign_in=None):
+        q = np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        out = dict(assign=np.empty((nq, ma), np.int32), tables=np.empty((nq, ma, self.m, 16), np.float32),
+                   qmin=np.empty(nq, np.float32), qmax=np.empty(nq, np.float32),
+                   qtables=np.empty((nq, ma, self.m, 16), np.int8))
+        ai = None if assign_in is None else np.ascontiguousarray(assign_in, np.int32)
+        rc = self.lib.qadc_build_tables(self.h, _ptr(q), nq, ma, r, _ptr(ai), _ptr(out["assign"]), _ptr(out["tables"]),
+                                        _ptr(out["qmin"]), _ptr(out["qmax"]), _ptr(out["qtables"]))
+        out["rc"] = rc
+        if rc and rc != QADC_EBOUND:
+            self._ck(rc)
+        return out
+
+    def scan_with_tables(self, assign, qtables, r):
+        a = np.ascontiguousarray(assign, np.int32)
+        nq, ma = a.shape
+        t = np.ascontiguousarray(qtables, np.int8)
+        ids = np.empty((nq, r), np.uint32)
+        d = np.empty((nq, r), np.int8)
+        cnt = np.empty(nq, np.int32)
+        self._ck(self.lib.qadc_scan_with_tables(self.h, _ptr(a), _ptr(t), nq, ma, r, _ptr(ids), _ptr(d), _ptr(cnt)))
+        return ids, d, cnt
+
+    def dump_distances(self, part_i, qtable):
+        t = np.ascontiguousarray(qtable, np.int8).reshape(-1)
+        out = np.empty(int(self.sizes[part_i]), np.int8)
+        self._ck(self.lib.qadc_dump_distances(self.h, part_i, _ptr(t), _ptr(out)))
+        return out
+
+    def download_codes(self, part_i):
+        out = np.empty((int(self.sizes[part_i]), self.m // 2), np.uint8)
+        self._ck(self.lib.qadc_download_codes(self.h, part_i, _ptr(out)))
+        return out

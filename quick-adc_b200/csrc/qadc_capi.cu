@@ -1,0 +1,754 @@
+// qadc_capi.cu — context, orchestration and the C ABI of libqadc_b200.so (include/qadc_b200.h).
+// Host-side mirror of what scanner_4 (db_query_4.cpp:73-310) and the engines
+// (query_common.hpp:149-309) do around the kernels; no CPU compute path exists here.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qadc_b200.h"
+#include "qadc_scan.cuh"
+#include "qadc_tables.cuh"
+
+using namespace qadc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+constexpr int kMaxSmem = 227 * 1024;
+constexpr int kNW = 8;
+
+}  // namespace
+
+struct qadc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    // quantisers
+    int dim = 0, m = 0;
+    float* d_codebooks = nullptr;
+    float* d_rotation = nullptr;
+    int K = 0;
+    float* d_centroids = nullptr;
+    // database
+    int parts = 0;
+    bool has_labels = false, begun = false, finalized = false;
+    std::vector<uint32_t> h_size, h_pos_base, h_start_size, h_explicit_count;
+    std::vector<uint64_t> h_sb_off, h_label_off, h_start_off;
+    std::vector<uint8_t*> h_explicit_prefix;   // device pointers (owned) or null
+    uint64_t total_sb = 0, total_vec = 0;
+    uint8_t* d_codes = nullptr;
+    uint32_t* d_labels = nullptr;
+    uint64_t *d_sb_off = nullptr, *d_label_off = nullptr, *d_start_off = nullptr;
+    uint32_t *d_size = nullptr, *d_pos_base = nullptr, *d_start_size = nullptr;
+    uint8_t* d_starts = nullptr;
+    uint32_t max_start = 0;
+    // scratch
+    DevBuf staging, b_queries, b_assign, b_tables, b_tmin, b_qmax, b_qmin, b_qtables, b_lists, b_plists, b_ids,
+        b_dists, b_counts, b_keys, b_dump;
+    int* d_err = nullptr;
+    int* h_err = nullptr;   // pinned
+    // options / accounting
+    long opt_flat_qb = 0, opt_flat_chunks = 0;
+    int launches = 0;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;
+    bool scan_timed = false;
+};
+
+namespace {
+
+int fail(qadc_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define QCK(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(ctx, QADC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+int ensure(qadc_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return QADC_OK;
+    if (b.p) QCK(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    QCK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return QADC_OK;
+}
+#define ENSURE(buf, bytes)                                   \
+    do {                                                     \
+        int rc__ = ensure(ctx, buf, bytes);                  \
+        if (rc__) return rc__;                               \
+    } while (0)
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+void free_db(qadc_ctx* c) {
+    cudaFree(c->d_codes); cudaFree(c->d_labels); cudaFree(c->d_sb_off); cudaFree(c->d_label_off);
+    cudaFree(c->d_start_off); cudaFree(c->d_size); cudaFree(c->d_pos_base); cudaFree(c->d_start_size);
+    cudaFree(c->d_starts);
+    for (auto p : c->h_explicit_prefix) cudaFree(p);
+    c->d_codes = nullptr; c->d_labels = nullptr; c->d_sb_off = c->d_label_off = c->d_start_off = nullptr;
+    c->d_size = c->d_pos_base = c->d_start_size = nullptr; c->d_starts = nullptr;
+    c->h_explicit_prefix.clear(); c->h_explicit_count.clear();
+    c->begun = c->finalized = false;
+}
+
+// ---- kernels that only the capi needs ------------------------------------------------------
+// Row-major keep-prefix of every partition out of the native layout (scanner_4 keeps the same
+// row-major copy in starts_flat, db_query_4.cpp:153-168).  grid = (K, y).
+template <int M>
+__global__ void extract_prefix_kernel(const uint8_t* __restrict__ native, const uint64_t* __restrict__ sb_off,
+                                      const uint32_t* __restrict__ start_size, const uint64_t* __restrict__ start_off,
+                                      const uint8_t* __restrict__ has_explicit, uint8_t* __restrict__ starts) {
+    constexpr int CS = M / 2;
+    const int p = blockIdx.x;
+    if (has_explicit[p]) return;
+    const uint32_t n = start_size[p];
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(native + sb_off[p] * sb_bytes(M));
+    for (uint32_t v = blockIdx.y * blockDim.x + threadIdx.x; v < n; v += gridDim.y * blockDim.x) {
+        const uint32_t sb = v / kSbVec, lane = (v % kSbVec) / 8, k = v % 8;
+        const uint32_t* w = base + static_cast<size_t>(sb) * (sb_bytes(M) / 4);
+        for (int b = 0; b < CS; ++b) {
+            const int j0 = 2 * b, j1 = 2 * b + 1;
+            const uint32_t lo = (w[((j0 / 4) * 32 + lane) * 4 + (j0 % 4)] >> (4 * k)) & 15u;
+            const uint32_t hi = (w[((j1 / 4) * 32 + lane) * 4 + (j1 % 4)] >> (4 * k)) & 15u;
+            starts[(start_off[p] + v) * CS + b] = static_cast<uint8_t>(lo | (hi << 4));
+        }
+    }
+}
+
+// ---- flat scan dispatch ---------------------------------------------------------------------
+template <int M, int QB, int G, int NW, int NS>
+int launch_flat(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
+    using Cfg = FlatCfg<M, QB, G, NW, NS>;
+    const size_t smem = Cfg::smem_bytes(a.cap);
+    if (smem > kMaxSmem) return QADC_ENOMEM;
+    auto kern = scan_flat_kernel<M, QB, G, NW, NS>;
+    QCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid(chunks, (a.nq + QB - 1) / QB);
+    kern<<<grid, Cfg::kThreads, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    return QADC_OK;
+}
+
+struct FlatPlan { int qb, g, chunks, cap; uint32_t sb_per_chunk; };
+
+// Chooses queries-per-pass, tile shape and chunk count for the flat scan.
+int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
+    const int M = ctx->m;
+    int qb = static_cast<int>(ctx->opt_flat_qb);
+    if (qb <= 0) qb = (nq >= 4) ? ((M == 16) ? 4 : 2) : ((nq >= 2) ? 2 : 1);
+    if (M == 32 && qb > 2) qb = 2;
+    if (qb > 4) qb = 4;
+    while (qb > nq && qb > 1) qb >>= 1;
+    bool found = false;
+    for (; qb >= 1 && !found; qb >>= 1) {
+        for (int g = (M == 16 && qb == 1) ? 2 : 1; g >= 1 && !found; --g) {
+            const int cap = next_pow2(r + g * kSbVec);
+            size_t smem;
+            if (M == 16)
+                smem = qb == 1 ? (g == 2 ? FlatCfg<16, 1, 2, kNW, 4>::smem_bytes(cap) : FlatCfg<16, 1, 1, kNW, 4>::smem_bytes(cap))
+                               : (qb == 2 ? FlatCfg<16, 2, 1, kNW, 4>::smem_bytes(cap) : FlatCfg<16, 4, 1, kNW, 4>::smem_bytes(cap));
+            else
+                smem = qb == 1 ? FlatCfg<32, 1, 1, kNW, 4>::smem_bytes(cap) : FlatCfg<32, 2, 1, kNW, 4>::smem_bytes(cap);
+            if (smem <= kMaxSmem) { pl.qb = qb; pl.g = g; pl.cap = cap; found = true; }
+        }
+    }
+    if (!found) return fail(ctx, QADC_EINVAL, "r too large for the scan kernel's shared-memory lists");
+    const uint32_t n_sb = static_cast<uint32_t>(ctx->total_sb);
+    const int tile_sb = kNW * pl.g;
+    const int qgroups = (nq + pl.qb - 1) / pl.qb;
+    long chunks = ctx->opt_flat_chunks;
+    if (chunks <= 0) chunks = std::max(1, (2 * ctx->sm_count + qgroups - 1) / qgroups);
+    const long max_chunks = std::max<long>(1, (n_sb + tile_sb - 1) / tile_sb);
+    chunks = std::min(chunks, max_chunks);
+    uint32_t spc = static_cast<uint32_t>((n_sb + chunks - 1) / chunks);
+    spc = ((spc + tile_sb - 1) / tile_sb) * tile_sb;   // whole tiles per chunk
+    pl.sb_per_chunk = std::max<uint32_t>(spc, tile_sb);
+    pl.chunks = static_cast<int>((n_sb + pl.sb_per_chunk - 1) / pl.sb_per_chunk);
+    if (pl.chunks < 1) pl.chunks = 1;
+    return QADC_OK;
+}
+
+int run_merge(qadc_ctx* ctx, MergeArgs ma) {
+    merge_lists_kernel<<<ma.nq, kMergeThreads, 0, ctx->stream>>>(ma);
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    return QADC_OK;
+}
+
+// Stage S on device buffers: assign [nq][ma], qtables [nq][ma][M*16] -> ids/dists/counts/keys.
+int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables, int nq, int ma, int r,
+                uint32_t* d_ids, int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys) {
+    const int M = ctx->m;
+    const bool flat = (ctx->K == 0);
+    int n_lists = 0;
+    if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0, ctx->stream));
+    if (flat) {
+        FlatPlan pl;
+        int rc = plan_flat(ctx, nq, r, pl);
+        if (rc) return rc;
+        n_lists = pl.chunks * kNW;
+        ENSURE(ctx->b_lists, static_cast<size_t>(nq) * n_lists * r * 8);
+        FlatScanArgs a;
+        a.codes = ctx->d_codes; a.n_sb = static_cast<uint32_t>(ctx->total_sb); a.size = ctx->h_size[0];
+        a.pos_base = ctx->h_pos_base[0]; a.sb_per_chunk = pl.sb_per_chunk; a.qtabs = d_qtables; a.nq = nq;
+        a.r = r; a.cap = pl.cap; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
+        if (M == 16) {
+            if (pl.qb == 1 && pl.g == 2) rc = launch_flat<16, 1, 2, kNW, 4>(ctx, a, pl.chunks);
+            else if (pl.qb == 1) rc = launch_flat<16, 1, 1, kNW, 4>(ctx, a, pl.chunks);
+            else if (pl.qb == 2) rc = launch_flat<16, 2, 1, kNW, 4>(ctx, a, pl.chunks);
+            else rc = launch_flat<16, 4, 1, kNW, 4>(ctx, a, pl.chunks);
+        } else {
+            if (pl.qb == 1) rc = launch_flat<32, 1, 1, kNW, 4>(ctx, a, pl.chunks);
+            else rc = launch_flat<32, 2, 1, kNW, 4>(ctx, a, pl.chunks);
+        }
+        if (rc) return rc == QADC_ENOMEM ? fail(ctx, rc, "scan kernel shared memory exceeds 227 KB") : rc;
+    } else {
+        const int cap = next_pow2(r + kSbVec);
+        const size_t smem = static_cast<size_t>(kNW) * cap * 8 + kNW * 8;
+        if (smem > kMaxSmem) return fail(ctx, QADC_EINVAL, "r too large for the IVF scan kernel");
+        int chunks = std::max(1, std::min((ma + kNW - 1) / kNW, (2 * ctx->sm_count + nq - 1) / nq));
+        const int ppc = (ma + chunks - 1) / chunks;
+        chunks = (ma + ppc - 1) / ppc;
+        n_lists = chunks * kNW;
+        ENSURE(ctx->b_lists, static_cast<size_t>(nq) * n_lists * r * 8);
+        IvfScanArgs a;
+        a.codes = ctx->d_codes; a.part_sb_off = ctx->d_sb_off; a.part_size = ctx->d_size;
+        a.part_pos_base = ctx->d_pos_base; a.assign = d_assign; a.qtabs = d_qtables; a.nq = nq; a.ma = ma;
+        a.r = r; a.cap = cap; a.probes_per_chunk = ppc; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
+        dim3 grid(chunks, nq);
+        if (M == 16) {
+            QCK(cudaFuncSetAttribute(scan_ivf_kernel<16, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+            scan_ivf_kernel<16, kNW><<<grid, kNW * 32, smem, ctx->stream>>>(a);
+        } else {
+            QCK(cudaFuncSetAttribute(scan_ivf_kernel<32, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+            scan_ivf_kernel<32, kNW><<<grid, kNW * 32, smem, ctx->stream>>>(a);
+        }
+        ctx->launches++;
+        QCK(cudaGetLastError());
+    }
+    if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan1, ctx->stream));
+    MergeArgs mg{};
+    mg.in_keys = ctx->b_lists.as<uint64_t>(); mg.in_ids = nullptr; mg.L = n_lists; mg.r = r; mg.nq = nq;
+    mg.shard_major = 0; mg.out_keys = d_keys; mg.out_ids = d_ids; mg.out_dists = d_dists; mg.out_counts = d_counts;
+    mg.out_rth_value = nullptr;
+    if (ctx->has_labels) {
+        mg.labels = ctx->d_labels; mg.label_off = ctx->d_label_off; mg.part_pos_base = ctx->d_pos_base;
+        mg.assign = d_assign; mg.ma = ma;
+    }
+    return run_merge(ctx, mg);
+}
+
+// Stage T on device buffers. d_assign_in may be null (then assignment is computed).
+int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, const int32_t* d_assign_in,
+                  bool record_events) {
+    const int M = ctx->m, dim = ctx->dim;
+    const bool flat = (ctx->K == 0);
+    const size_t nqa = static_cast<size_t>(nq) * ma;
+    ENSURE(ctx->b_assign, nqa * 4);
+    ENSURE(ctx->b_tables, nqa * M * 16 * 4);
+    ENSURE(ctx->b_tmin, nqa * 4);
+    ENSURE(ctx->b_qmax, static_cast<size_t>(nq) * 4);
+    ENSURE(ctx->b_qmin, static_cast<size_t>(nq) * 4);
+    ENSURE(ctx->b_qtables, nqa * M * 16);
+    int32_t* d_assign = ctx->b_assign.as<int32_t>();
+    if (record_events) QCK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // 1. assignment (flat_db: assign = 0, databases.hpp:93-101; index_db: :201-211)
+    if (d_assign_in) {
+        QCK(cudaMemcpyAsync(d_assign, d_assign_in, nqa * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else if (flat) {
+        QCK(cudaMemsetAsync(d_assign, 0, nqa * 4, ctx->stream));
+    } else {
+        const size_t smem = kSelCap * 8 + static_cast<size_t>(dim) * 4;
+        coarse_assign_kernel<<<nq, kSelThreads, smem, ctx->stream>>>(d_queries, dim, ctx->d_centroids, ctx->K, ma,
+                                                                   d_assign);
+        ctx->launches++;
+        QCK(cudaGetLastError());
+    }
+    if (record_events) QCK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    // 2+3. residual, rotation, float tables
+    tables_kernel<<<static_cast<unsigned>(nqa), 256, static_cast<size_t>(dim) * 8, ctx->stream>>>(
+        d_queries, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
+        ctx->b_tables.as<float>(), ctx->b_tmin.as<float>());
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    if (record_events) QCK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    // 4. keep-prefix float scan -> qmax
+    int nsplit = 1;
+    if (flat) nsplit = static_cast<int>(std::min<uint32_t>(128, std::max<uint32_t>(1, ctx->max_start / 4096)));
+    ENSURE(ctx->b_plists, static_cast<size_t>(nq) * nsplit * r * 8);
+    PrefixArgs pa;
+    pa.starts = ctx->d_starts; pa.start_off = ctx->d_start_off; pa.start_size = ctx->d_start_size;
+    pa.assign = d_assign; pa.tables = ctx->b_tables.as<float>(); pa.ma = ma; pa.r = r; pa.M = M; pa.nsplit = nsplit;
+    pa.lists = ctx->b_plists.as<uint64_t>();
+    dim3 pgrid(nsplit, nq);
+    if (M == 16) prefix_scan_kernel<16><<<pgrid, kSelThreads, 0, ctx->stream>>>(pa);
+    else prefix_scan_kernel<32><<<pgrid, kSelThreads, 0, ctx->stream>>>(pa);
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    MergeArgs mg{};
+    mg.in_keys = pa.lists; mg.L = nsplit; mg.r = r; mg.nq = nq; mg.out_rth_value = ctx->b_qmax.as<float>();
+    int rc = run_merge(ctx, mg);
+    if (rc) return rc;
+    // 5. bounds + int8 tables
+    quantize_kernel<<<static_cast<unsigned>(nqa), 256, 0, ctx->stream>>>(
+        ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), ctx->b_qmax.as<float>(), ma, M,
+        ctx->b_qtables.as<int8_t>(), ctx->b_qmin.as<float>(), ctx->d_err);
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    return QADC_OK;
+}
+
+int check_search_args(qadc_ctx* ctx, int nq, int ma, int r) {
+    if (!ctx) return QADC_EINVAL;
+    if (!ctx->finalized) return fail(ctx, QADC_ESTATE, "database not finalized");
+    if (nq <= 0 || ma <= 0 || r <= 0) return fail(ctx, QADC_EINVAL, "nq, ma and r must be positive");
+    if (r > kMergeCap / 2) return fail(ctx, QADC_EINVAL, "r > 1024 is not supported");
+    if (ctx->K == 0 && ma != 1)
+        return fail(ctx, QADC_EINVAL, "a flat database must be queried with ma = 1 (SURVEY App. B)");
+    if (ctx->K > 0 && (ma > ctx->K || ma > kSelCap / 2))
+        return fail(ctx, QADC_EINVAL, "ma exceeds the partition count (or 1024)");
+    return QADC_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int qadc_abi_version(void) { return QADC_ABI_VERSION; }
+
+int qadc_create(int device, void* stream, qadc_ctx** out) {
+    qadc_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, QADC_EINVAL, "out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, QADC_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, QADC_EINVAL, "bad device ordinal");
+    cudaDeviceProp prop;
+    QCK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, QADC_ECUDA, "device is not sm_100 (libqadc_b200 has no other code path)");
+    QCK(cudaSetDevice(device));
+    qadc_ctx* c = new qadc_ctx;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    ctx = c;
+    if (stream) c->stream = static_cast<cudaStream_t>(stream);
+    else { QCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    for (auto& ev : c->ev) QCK(cudaEventCreate(&ev));
+    QCK(cudaEventCreate(&c->ev_scan0));
+    QCK(cudaEventCreate(&c->ev_scan1));
+    QCK(cudaMalloc(&c->d_err, sizeof(int)));
+    QCK(cudaMemset(c->d_err, 0, sizeof(int)));
+    QCK(cudaMallocHost(&c->h_err, sizeof(int)));
+    *c->h_err = 0;
+    *out = c;
+    return QADC_OK;
+}
+
+void qadc_destroy(qadc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_db(c);
+    cudaFree(c->d_codebooks); cudaFree(c->d_rotation); cudaFree(c->d_centroids);
+    for (DevBuf* b : {&c->staging, &c->b_queries, &c->b_assign, &c->b_tables, &c->b_tmin, &c->b_qmax, &c->b_qmin,
+                      &c->b_qtables, &c->b_lists, &c->b_plists, &c->b_ids, &c->b_dists, &c->b_counts, &c->b_keys,
+                      &c->b_dump})
+        cudaFree(b->p);
+    cudaFree(c->d_err);
+    cudaFreeHost(c->h_err);
+    for (auto& ev : c->ev) cudaEventDestroy(ev);
+    cudaEventDestroy(c->ev_scan0); cudaEventDestroy(c->ev_scan1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* qadc_last_error(const qadc_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int qadc_set_pq(qadc_ctx* ctx, int dim, int m, int bits, const float* codebooks, const float* rotation) {
+    if (!ctx || !codebooks) return fail(ctx, QADC_EINVAL, "null argument");
+    // get_simd_scan_func_epi8 (db_query_4.cpp:23-35), load_database_check (:393-402)
+    if (bits != 4) return fail(ctx, QADC_EINVAL, "Quantizer must have sq_bits=4");
+    if (m != 16 && m != 32)
+        return fail(ctx, QADC_EINVAL, "Unsupported (nsq,nsq_bits) configuration. Supported: (16,4) (32,4).");
+    if (dim <= 0 || dim % m != 0) return fail(ctx, QADC_EINVAL, "dim must be a positive multiple of m");
+    QCK(cudaSetDevice(ctx->device));
+    cudaFree(ctx->d_codebooks); cudaFree(ctx->d_rotation);
+    ctx->d_codebooks = nullptr; ctx->d_rotation = nullptr;
+    const size_t cb = static_cast<size_t>(dim) * 16 * sizeof(float);
+    QCK(cudaMalloc(&ctx->d_codebooks, cb));
+    QCK(cudaMemcpy(ctx->d_codebooks, codebooks, cb, cudaMemcpyHostToDevice));
+    if (rotation) {
+        const size_t rb = static_cast<size_t>(dim) * dim * sizeof(float);
+        QCK(cudaMalloc(&ctx->d_rotation, rb));
+        QCK(cudaMemcpy(ctx->d_rotation, rotation, rb, cudaMemcpyHostToDevice));
+    }
+    ctx->dim = dim; ctx->m = m;
+    return QADC_OK;
+}
+
+int qadc_set_coarse(qadc_ctx* ctx, int K, const float* centroids) {
+    if (!ctx) return QADC_EINVAL;
+    if (ctx->dim == 0) return fail(ctx, QADC_ESTATE, "qadc_set_pq must be called first");
+    QCK(cudaSetDevice(ctx->device));
+    cudaFree(ctx->d_centroids); ctx->d_centroids = nullptr; ctx->K = 0;
+    if (K <= 0) return QADC_OK;
+    if (!centroids) return fail(ctx, QADC_EINVAL, "centroids is null");
+    const size_t bytes = static_cast<size_t>(K) * ctx->dim * sizeof(float);
+    QCK(cudaMalloc(&ctx->d_centroids, bytes));
+    QCK(cudaMemcpy(ctx->d_centroids, centroids, bytes, cudaMemcpyHostToDevice));
+    ctx->K = K;
+    return QADC_OK;
+}
+
+int qadc_begin_database(qadc_ctx* ctx, int partition_count, const uint32_t* sizes, int has_labels) {
+    if (!ctx || !sizes || partition_count <= 0) return fail(ctx, QADC_EINVAL, "bad database description");
+    if (ctx->m == 0) return fail(ctx, QADC_ESTATE, "qadc_set_pq must be called first");
+    if (ctx->K == 0 && partition_count != 1) return fail(ctx, QADC_EINVAL, "a flat database has exactly one partition");
+    if (ctx->K > 0 && partition_count != ctx->K) return fail(ctx, QADC_EINVAL, "partition_count != coarse centroid count");
+    QCK(cudaSetDevice(ctx->device));
+    free_db(ctx);
+    const int P = partition_count;
+    ctx->parts = P; ctx->has_labels = has_labels != 0;
+    ctx->h_size.assign(sizes, sizes + P);
+    ctx->h_pos_base.assign(P, 0);
+    ctx->h_sb_off.assign(P, 0); ctx->h_label_off.assign(P, 0);
+    ctx->h_explicit_prefix.assign(P, nullptr); ctx->h_explicit_count.assign(P, 0);
+    uint64_t sb = 0, vec = 0;
+    for (int p = 0; p < P; ++p) {
+        ctx->h_sb_off[p] = sb; ctx->h_label_off[p] = vec;
+        sb += (static_cast<uint64_t>(sizes[p]) + kSbVec - 1) / kSbVec;
+        vec += sizes[p];
+    }
+    ctx->total_sb = sb; ctx->total_vec = vec;
+    QCK(cudaMalloc(&ctx->d_codes, std::max<size_t>(16, sb * sb_bytes(ctx->m))));
+    if (ctx->has_labels) QCK(cudaMalloc(&ctx->d_labels, std::max<size_t>(4, vec * 4)));
+    QCK(cudaMalloc(&ctx->d_sb_off, P * 8)); QCK(cudaMalloc(&ctx->d_label_off, P * 8));
+    QCK(cudaMalloc(&ctx->d_size, P * 4));
+    QCK(cudaMemcpy(ctx->d_sb_off, ctx->h_sb_off.data(), P * 8, cudaMemcpyHostToDevice));
+    QCK(cudaMemcpy(ctx->d_label_off, ctx->h_label_off.data(), P * 8, cudaMemcpyHostToDevice));
+    QCK(cudaMemcpy(ctx->d_size, ctx->h_size.data(), P * 4, cudaMemcpyHostToDevice));
+    ctx->begun = true;
+    return QADC_OK;
+}
+
+int qadc_upload_codes(qadc_ctx* ctx, int part_i, uint32_t first, uint32_t count, const uint8_t* codes,
+                      const uint32_t* labels, int on_device) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "qadc_begin_database must be called first");
+    if (part_i < 0 || part_i >= ctx->parts) return fail(ctx, QADC_EINVAL, "bad partition index");
+    if (count == 0) return QADC_OK;
+    if (!codes) return fail(ctx, QADC_EINVAL, "codes is null");
+    if (first % kSbVec != 0) return fail(ctx, QADC_EINVAL, "first must be a multiple of 256");
+    if (static_cast<uint64_t>(first) + count > ctx->h_size[part_i]) return fail(ctx, QADC_EINVAL, "range exceeds partition size");
+    if (first + count != ctx->h_size[part_i] && count % kSbVec != 0)
+        return fail(ctx, QADC_EINVAL, "only the last chunk of a partition may be ragged");
+    if (ctx->has_labels && !labels) return fail(ctx, QADC_EINVAL, "labels is null but the database has labels");
+    QCK(cudaSetDevice(ctx->device));
+    const int M = ctx->m, CS = M / 2;
+    uint8_t* dst = ctx->d_codes + ctx->h_sb_off[part_i] * sb_bytes(M);
+    const uint32_t kChunk = 1u << 23;   // vectors per staging chunk (64/128 MiB)
+    for (uint32_t off = 0; off < count; off += kChunk) {
+        const uint32_t n = std::min(kChunk, count - off);
+        const uint8_t* src = codes + static_cast<size_t>(off) * CS;
+        if (!on_device) {
+            ENSURE(ctx->staging, static_cast<size_t>(n) * CS);
+            QCK(cudaMemcpyAsync(ctx->staging.p, src, static_cast<size_t>(n) * CS, cudaMemcpyHostToDevice, ctx->stream));
+            src = ctx->staging.as<uint8_t>();
+        }
+        const uint32_t groups = ((n + kSbVec - 1) / kSbVec) * 32;
+        const unsigned blocks = (groups + 255) / 256;
+        if (M == 16) transpose_codes_kernel<16><<<blocks, 256, 0, ctx->stream>>>(src, n, dst, first + off);
+        else transpose_codes_kernel<32><<<blocks, 256, 0, ctx->stream>>>(src, n, dst, first + off);
+        QCK(cudaGetLastError());
+        if (!on_device) QCK(cudaStreamSynchronize(ctx->stream));   // staging is reused
+    }
+    if (ctx->has_labels)
+        QCK(cudaMemcpyAsync(ctx->d_labels + ctx->h_label_off[part_i] + first, labels, static_cast<size_t>(count) * 4,
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    QCK(cudaStreamSynchronize(ctx->stream));
+    ctx->finalized = false;
+    return QADC_OK;
+}
+
+int qadc_set_position_base(qadc_ctx* ctx, int part_i, uint32_t pos_base) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "qadc_begin_database must be called first");
+    if (part_i < 0 || part_i >= ctx->parts) return fail(ctx, QADC_EINVAL, "bad partition index");
+    ctx->h_pos_base[part_i] = pos_base;
+    ctx->finalized = false;
+    return QADC_OK;
+}
+
+int qadc_set_prefix(qadc_ctx* ctx, int part_i, const uint8_t* codes, uint32_t count, int on_device) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "qadc_begin_database must be called first");
+    if (part_i < 0 || part_i >= ctx->parts) return fail(ctx, QADC_EINVAL, "bad partition index");
+    if (!codes || count == 0) return fail(ctx, QADC_EINVAL, "empty prefix");
+    QCK(cudaSetDevice(ctx->device));
+    cudaFree(ctx->h_explicit_prefix[part_i]);
+    ctx->h_explicit_prefix[part_i] = nullptr;
+    const size_t bytes = static_cast<size_t>(count) * (ctx->m / 2);
+    QCK(cudaMalloc(&ctx->h_explicit_prefix[part_i], bytes));
+    QCK(cudaMemcpy(ctx->h_explicit_prefix[part_i], codes, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    ctx->h_explicit_count[part_i] = count;
+    ctx->finalized = false;
+    return QADC_OK;
+}
+
+int qadc_finalize(qadc_ctx* ctx, float keep) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "qadc_begin_database must be called first");
+    QCK(cudaSetDevice(ctx->device));
+    const int P = ctx->parts, M = ctx->m, CS = M / 2;
+    ctx->h_start_size.assign(P, 0); ctx->h_start_off.assign(P, 0);
+    std::vector<uint8_t> has_explicit(P, 0);
+    uint64_t off = 0;
+    ctx->max_start = 0;
+    for (int p = 0; p < P; ++p) {
+        uint32_t s;
+        if (ctx->h_explicit_prefix[p]) { s = ctx->h_explicit_count[p]; has_explicit[p] = 1; }
+        else {
+            if (ctx->h_pos_base[p] != 0)
+                return fail(ctx, QADC_EINVAL, "a shard with a position base needs an explicit prefix (qadc_set_prefix)");
+            const uint32_t size = ctx->h_size[p];
+            // starts_sizes[p] = max(1u, (unsigned)(size * keep)), float32 (db_query_4.cpp:125-126)
+            s = size == 0 ? 0u : std::max(1u, static_cast<unsigned>(static_cast<float>(size) * keep));
+            s = std::min(s, size);
+        }
+        ctx->h_start_size[p] = s; ctx->h_start_off[p] = off; off += s;
+        ctx->max_start = std::max(ctx->max_start, s);
+    }
+    cudaFree(ctx->d_starts); cudaFree(ctx->d_start_off); cudaFree(ctx->d_start_size); cudaFree(ctx->d_pos_base);
+    ctx->d_starts = nullptr; ctx->d_start_off = nullptr; ctx->d_start_size = nullptr; ctx->d_pos_base = nullptr;
+    QCK(cudaMalloc(&ctx->d_starts, std::max<size_t>(16, off * CS)));
+    QCK(cudaMalloc(&ctx->d_start_off, P * 8)); QCK(cudaMalloc(&ctx->d_start_size, P * 4));
+    QCK(cudaMalloc(&ctx->d_pos_base, P * 4));
+    QCK(cudaMemcpy(ctx->d_start_off, ctx->h_start_off.data(), P * 8, cudaMemcpyHostToDevice));
+    QCK(cudaMemcpy(ctx->d_start_size, ctx->h_start_size.data(), P * 4, cudaMemcpyHostToDevice));
+    QCK(cudaMemcpy(ctx->d_pos_base, ctx->h_pos_base.data(), P * 4, cudaMemcpyHostToDevice));
+    uint8_t* d_flags = nullptr;
+    QCK(cudaMalloc(&d_flags, P));
+    QCK(cudaMemcpy(d_flags, has_explicit.data(), P, cudaMemcpyHostToDevice));
+    dim3 grid(P, std::max(1u, std::min(64u, (ctx->max_start + 255) / 256)));
+    if (M == 16)
+        extract_prefix_kernel<16><<<grid, 256, 0, ctx->stream>>>(ctx->d_codes, ctx->d_sb_off, ctx->d_start_size,
+                                                                 ctx->d_start_off, d_flags, ctx->d_starts);
+    else
+        extract_prefix_kernel<32><<<grid, 256, 0, ctx->stream>>>(ctx->d_codes, ctx->d_sb_off, ctx->d_start_size,
+                                                                 ctx->d_start_off, d_flags, ctx->d_starts);
+    QCK(cudaGetLastError());
+    for (int p = 0; p < P; ++p)
+        if (ctx->h_explicit_prefix[p])
+            QCK(cudaMemcpyAsync(ctx->d_starts + ctx->h_start_off[p] * CS, ctx->h_explicit_prefix[p],
+                                static_cast<size_t>(ctx->h_explicit_count[p]) * CS, cudaMemcpyDeviceToDevice, ctx->stream));
+    QCK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_flags);
+    ctx->finalized = true;
+    return QADC_OK;
+}
+
+int qadc_search_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, uint32_t* d_ids,
+                       int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys) {
+    int rc = check_search_args(ctx, nq, ma, r);
+    if (rc) return rc;
+    QCK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    rc = tables_device(ctx, d_queries, nq, ma, r, nullptr, true);
+    if (rc) return rc;
+    QCK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    rc = scan_device(ctx, ctx->b_assign.as<int32_t>(), ctx->b_qtables.as<int8_t>(), nq, ma, r, d_ids, d_dists,
+                     d_counts, d_keys);
+    if (rc) return rc;
+    QCK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    QCK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return QADC_OK;
+}
+
+int qadc_synchronize(qadc_ctx* ctx) {
+    if (!ctx) return QADC_EINVAL;
+    QCK(cudaSetDevice(ctx->device));
+    QCK(cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_err) {
+        *ctx->h_err = 0;
+        QCK(cudaMemset(ctx->d_err, 0, sizeof(int)));
+        return fail(ctx, QADC_EBOUND, "Max quantization bound too high. Try larger keep value.");
+    }
+    return QADC_OK;
+}
+
+int qadc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, uint32_t* out_ids, int8_t* out_dists,
+                int32_t* out_counts, qadc_metrics* metrics) {
+    int rc = check_search_args(ctx, nq, ma, r);
+    if (rc) return rc;
+    if (!queries || !out_ids || !out_dists) return fail(ctx, QADC_EINVAL, "null buffer");
+    QCK(cudaSetDevice(ctx->device));
+    const size_t nr = static_cast<size_t>(nq) * r;
+    ENSURE(ctx->b_queries, static_cast<size_t>(nq) * ctx->dim * 4);
+    ENSURE(ctx->b_ids, nr * 4); ENSURE(ctx->b_dists, nr); ENSURE(ctx->b_counts, static_cast<size_t>(nq) * 4);
+    QCK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    QCK(cudaMemcpyAsync(ctx->b_queries.p, queries, static_cast<size_t>(nq) * ctx->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+    rc = qadc_search_device(ctx, ctx->b_queries.as<float>(), nq, ma, r, ctx->b_ids.as<uint32_t>(),
+                            ctx->b_dists.as<int8_t>(), ctx->b_counts.as<int32_t>(), nullptr);
+    if (rc) return rc;
+    QCK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    QCK(cudaMemcpyAsync(out_ids, ctx->b_ids.p, nr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    QCK(cudaMemcpyAsync(out_dists, ctx->b_dists.p, nr, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_counts) QCK(cudaMemcpyAsync(out_counts, ctx->b_counts.p, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    QCK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    rc = qadc_synchronize(ctx);
+    if (metrics) {
+        float ms = 0;
+        auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return static_cast<double>(ms) * 1e3; };
+        metrics->index_us = el(0, 1);
+        metrics->rotate_us = 0;   // rotation is fused into the table kernel
+        metrics->table_us = el(1, 2);
+        metrics->scan_us = el(2, 4);
+        metrics->h2d_us = el(5, 0);
+        metrics->d2h_us = el(6, 7);
+    }
+    return rc;
+}
+
+int qadc_last_launch_count(const qadc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int qadc_last_scan_ms(qadc_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return QADC_EINVAL;
+    if (!ctx->scan_timed) return fail(ctx, QADC_ESTATE, "enable with qadc_set_option(ctx, \"time_scan\", 1)");
+    QCK(cudaStreamSynchronize(ctx->stream));
+    QCK(cudaEventElapsedTime(ms, ctx->ev_scan0, ctx->ev_scan1));
+    return QADC_OK;
+}
+
+int qadc_merge_shards_device(qadc_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_ids, int G, int nq, int r,
+                             uint32_t* d_out_ids, int8_t* d_out_dists, int32_t* d_out_counts, uint64_t* d_out_keys) {
+    if (!ctx || !d_keys || G <= 0 || nq <= 0 || r <= 0 || r > kMergeCap / 2) return fail(ctx, QADC_EINVAL, "bad merge arguments");
+    QCK(cudaSetDevice(ctx->device));
+    MergeArgs mg{};
+    mg.in_keys = d_keys; mg.in_ids = d_ids; mg.L = G; mg.r = r; mg.nq = nq; mg.shard_major = 1;
+    mg.out_keys = d_out_keys; mg.out_ids = d_out_ids; mg.out_dists = d_out_dists; mg.out_counts = d_out_counts;
+    return run_merge(ctx, mg);
+}
+
+int qadc_build_tables(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, const int32_t* assign_in,
+                      int32_t* out_assign, float* out_tables, float* out_qmin, float* out_qmax, int8_t* out_qtables) {
+    int rc = check_search_args(ctx, nq, ma, r);
+    if (rc) return rc;
+    if (!queries) return fail(ctx, QADC_EINVAL, "queries is null");
+    QCK(cudaSetDevice(ctx->device));
+    const size_t nqa = static_cast<size_t>(nq) * ma, td = static_cast<size_t>(ctx->m) * 16;
+    ENSURE(ctx->b_queries, static_cast<size_t>(nq) * ctx->dim * 4);
+    QCK(cudaMemcpyAsync(ctx->b_queries.p, queries, static_cast<size_t>(nq) * ctx->dim * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int32_t* d_ain = nullptr;
+    if (assign_in) {
+        ENSURE(ctx->b_ids, nqa * 4);
+        QCK(cudaMemcpyAsync(ctx->b_ids.p, assign_in, nqa * 4, cudaMemcpyHostToDevice, ctx->stream));
+        d_ain = ctx->b_ids.as<int32_t>();
+    }
+    ctx->launches = 0;
+    rc = tables_device(ctx, ctx->b_queries.as<float>(), nq, ma, r, d_ain, false);
+    if (rc) return rc;
+    QCK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_assign) QCK(cudaMemcpyAsync(out_assign, ctx->b_assign.p, nqa * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_tables) QCK(cudaMemcpyAsync(out_tables, ctx->b_tables.p, nqa * td * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_qmin) QCK(cudaMemcpyAsync(out_qmin, ctx->b_qmin.p, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_qmax) QCK(cudaMemcpyAsync(out_qmax, ctx->b_qmax.p, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_qtables) QCK(cudaMemcpyAsync(out_qtables, ctx->b_qtables.p, nqa * td, cudaMemcpyDeviceToHost, ctx->stream));
+    return qadc_synchronize(ctx);
+}
+
+int qadc_scan_with_tables(qadc_ctx* ctx, const int32_t* assign, const int8_t* qtables, int nq, int ma, int r,
+                          uint32_t* out_ids, int8_t* out_dists, int32_t* out_counts) {
+    int rc = check_search_args(ctx, nq, ma, r);
+    if (rc) return rc;
+    if (!assign || !qtables || !out_ids || !out_dists) return fail(ctx, QADC_EINVAL, "null buffer");
+    const size_t nqa = static_cast<size_t>(nq) * ma, td = static_cast<size_t>(ctx->m) * 16, nr = static_cast<size_t>(nq) * r;
+    for (size_t i = 0; i < nqa * td; ++i)
+        if (qtables[i] < 0) return fail(ctx, QADC_EINVAL, "int8 table entries must be in [0,127] (db_query_4.cpp:44-55)");
+    for (size_t i = 0; i < nqa; ++i)
+        if (assign[i] < 0 || assign[i] >= ctx->parts) return fail(ctx, QADC_EINVAL, "assign entry out of range");
+    QCK(cudaSetDevice(ctx->device));
+    ENSURE(ctx->b_assign, nqa * 4); ENSURE(ctx->b_qtables, nqa * td);
+    ENSURE(ctx->b_ids, nr * 4); ENSURE(ctx->b_dists, nr); ENSURE(ctx->b_counts, static_cast<size_t>(nq) * 4);
+    QCK(cudaMemcpyAsync(ctx->b_assign.p, assign, nqa * 4, cudaMemcpyHostToDevice, ctx->stream));
+    QCK(cudaMemcpyAsync(ctx->b_qtables.p, qtables, nqa * td, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches = 0;
+    rc = scan_device(ctx, ctx->b_assign.as<int32_t>(), ctx->b_qtables.as<int8_t>(), nq, ma, r, ctx->b_ids.as<uint32_t>(),
+                     ctx->b_dists.as<int8_t>(), ctx->b_counts.as<int32_t>(), nullptr);
+    if (rc) return rc;
+    QCK(cudaMemcpyAsync(out_ids, ctx->b_ids.p, nr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    QCK(cudaMemcpyAsync(out_dists, ctx->b_dists.p, nr, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_counts) QCK(cudaMemcpyAsync(out_counts, ctx->b_counts.p, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    QCK(cudaStreamSynchronize(ctx->stream));
+    return QADC_OK;
+}
+
+int qadc_dump_distances(qadc_ctx* ctx, int part_i, const int8_t* qtable, int8_t* out) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "no database");
+    if (part_i < 0 || part_i >= ctx->parts || !qtable || !out) return fail(ctx, QADC_EINVAL, "bad argument");
+    const int M = ctx->m;
+    for (int i = 0; i < M * 16; ++i)
+        if (qtable[i] < 0) return fail(ctx, QADC_EINVAL, "int8 table entries must be in [0,127]");
+    const uint32_t size = ctx->h_size[part_i];
+    if (size == 0) return QADC_OK;
+    QCK(cudaSetDevice(ctx->device));
+    ENSURE(ctx->b_dump, static_cast<size_t>(size) + M * 16);
+    int8_t* d_t = ctx->b_dump.as<int8_t>();
+    int8_t* d_o = d_t + M * 16;
+    QCK(cudaMemcpyAsync(d_t, qtable, M * 16, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t* native = ctx->d_codes + ctx->h_sb_off[part_i] * sb_bytes(M);
+    const uint32_t n_sb = (size + kSbVec - 1) / kSbVec;
+    if (M == 16) dump_distances_kernel<16><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o);
+    else dump_distances_kernel<32><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o);
+    QCK(cudaGetLastError());
+    QCK(cudaMemcpyAsync(out, d_o, size, cudaMemcpyDeviceToHost, ctx->stream));
+    QCK(cudaStreamSynchronize(ctx->stream));
+    return QADC_OK;
+}
+
+int qadc_download_codes(qadc_ctx* ctx, int part_i, uint8_t* out_codes) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "no database");
+    if (part_i < 0 || part_i >= ctx->parts || !out_codes) return fail(ctx, QADC_EINVAL, "bad argument");
+    const int M = ctx->m, CS = M / 2;
+    const uint32_t size = ctx->h_size[part_i];
+    if (size == 0) return QADC_OK;
+    QCK(cudaSetDevice(ctx->device));
+    ENSURE(ctx->b_dump, static_cast<size_t>(size) * CS);
+    const uint8_t* native = ctx->d_codes + ctx->h_sb_off[part_i] * sb_bytes(M);
+    if (M == 16) untranspose_codes_kernel<16><<<(size + 255) / 256, 256, 0, ctx->stream>>>(native, size, ctx->b_dump.as<uint8_t>());
+    else untranspose_codes_kernel<32><<<(size + 255) / 256, 256, 0, ctx->stream>>>(native, size, ctx->b_dump.as<uint8_t>());
+    QCK(cudaGetLastError());
+    QCK(cudaMemcpyAsync(out_codes, ctx->b_dump.p, static_cast<size_t>(size) * CS, cudaMemcpyDeviceToHost, ctx->stream));
+    QCK(cudaStreamSynchronize(ctx->stream));
+    return QADC_OK;
+}
+
+int qadc_set_option(qadc_ctx* ctx, const char* key, long value) {
+    if (!ctx || !key) return QADC_EINVAL;
+    if (!strcmp(key, "flat_qb")) ctx->opt_flat_qb = value;
+    else if (!strcmp(key, "flat_chunks")) ctx->opt_flat_chunks = value;
+    else if (!strcmp(key, "time_scan")) ctx->scan_timed = value != 0;
+    else return fail(ctx, QADC_EINVAL, std::string("unknown option ") + key);
+    return QADC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+// qadc_device.cuh — device-side building blocks of the B200 Quick ADC scan (sm_100a).
+//
+// Device code layout ("nibble planes"), the GPU counterpart of the reference's transposed
+// 16-vector blocks (simd_layout.hpp:41-65):
+//   superblock = 256 consecutive vectors = M/4 quads x 32 lanes x 16 bytes (M*128 bytes)
+//   the uint4 at (quad q, lane l) holds 4 words, word s = sub-quantiser j = 4q+s,
+//   nibble k of the word = centroid index of vector 8*l + k for that sub-quantiser.
+// A warp reads one quad of a superblock with one conflict-free 128-bit access per lane,
+// and the low/high 16 bits of a word are directly the PRMT selectors of 4 vectors.
+//
+// Lookup (the GPU analogue of vpshufb in scan_avx_4, simd_scan.hpp:157-173): the 16-entry
+// int8 table of a sub-quantiser is one uint4 {T0,T1,T2,T3}; every entry is in [0,127]
+// (QuantizerMAX, db_query_4.cpp:44-55), so PRMT's sign-replicate mode (selector bit 3)
+// returns 0 for them:
+//   lo = prmt(T0, T1, w)               -> T[idx] if idx < 8 else 0
+//   hi = prmt(T2, T3, w ^ 0x88888888)  -> T[idx] if idx >= 8 else 0
+// Two sub-quantisers are added in byte lanes (<= 254, no carry), widened to 16-bit lanes
+// and accumulated; the accumulators start at 0x8000 - bound so bit 15 of a lane is set iff
+// sum >= bound.  Signed saturation of the reference (vpaddsb on values in [0,127]) equals
+// min(127, sum), and only sums < bound <= 127 are ever selected.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace qadc {
+
+constexpr int kSbVec = 256;              // vectors per superblock
+constexpr uint64_t kEmptyKey = ~0ull;    // sorts after every real key
+
+__host__ __device__ constexpr int sb_bytes(int m) { return m * 128; }
+
+// canonical sort key (SURVEY §8c Stage S): distance, probe rank, position
+__host__ __device__ __forceinline__ uint64_t make_key(uint32_t d, uint32_t probe_rank, uint32_t pos) {
+    return (static_cast<uint64_t>(d) << 48) | (static_cast<uint64_t>(probe_rank) << 32) | pos;
+}
+
+// ---- PTX helpers: mbarrier + TMA bulk copy ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- the lookup-accumulate core ----------------------------------------------------------
+// Raw prmt.b32: bit 3 of a selector nibble replicates the SIGN of the selected byte
+// (__byte_perm masks the selector with 0x7777, so it cannot be used here).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+
+// Two sub-quantisers (words w0,w1 with tables t0,t1) for the 8 vectors of a group.
+// acc[0]: vectors (0,2)  acc[1]: (1,3)  acc[2]: (4,6)  acc[3]: (5,7)   as 16-bit lanes.
+__device__ __forceinline__ void lut_pair(uint32_t w0, uint32_t w1, const uint4& t0, const uint4& t1,
+                                         uint32_t (&acc)[4]) {
+    const uint32_t x0 = w0 ^ 0x88888888u, x1 = w1 ^ 0x88888888u;
+    const uint32_t pa = prmt(t0.x, t0.y, w0) + prmt(t0.z, t0.w, x0) + prmt(t1.x, t1.y, w1) +
+                        prmt(t1.z, t1.w, x1);
+    const uint32_t pb = prmt(t0.x, t0.y, w0 >> 16) + prmt(t0.z, t0.w, x0 >> 16) +
+                        prmt(t1.x, t1.y, w1 >> 16) + prmt(t1.z, t1.w, x1 >> 16);
+    acc[0] += pa & 0x00ff00ffu;
+    acc[1] += (pa >> 8) & 0x00ff00ffu;
+    acc[2] += pb & 0x00ff00ffu;
+    acc[3] += (pb >> 8) & 0x00ff00ffu;
+}
+
+// One quad = 4 sub-quantisers.
+__device__ __forceinline__ void lut_quad(const uint4& w, const uint4 (&t)[4], uint32_t (&acc)[4]) {
+    lut_pair(w.x, w.y, t[0], t[1], acc);
+    lut_pair(w.z, w.w, t[2], t[3], acc);
+}
+
+// accumulator start value for "pass iff sum < bound" (bound <= 127)
+__device__ __forceinline__ uint32_t acc_init(uint32_t bound) { return 0x80008000u - bound * 0x00010001u; }
+// true iff at least one of the 8 sums is < bound
+__device__ __forceinline__ bool any_below(const uint32_t (&acc)[4]) {
+    return (acc[0] & acc[1] & acc[2] & acc[3] & 0x80008000u) != 0x80008000u;
+}
+// sum of vector k (0..7) of the group, given the bound the accumulators were started with;
+// only meaningful while sum + 0x8000 - bound < 0x10000 (always: sum <= 127*32)
+__device__ __forceinline__ uint32_t lane_sum(const uint32_t (&acc)[4], int k, uint32_t bound) {
+    const uint32_t reg = acc[((k >> 2) << 1) | (k & 1)];
+    const uint32_t v = (reg >> (((k >> 1) & 1) * 16)) & 0xffffu;
+    return v + bound - 0x8000u;
+}
+
+// ---- bounded candidate lists: bitonic sort of u64 keys in shared memory ------------------
+// Sorts n (power of two) keys ascending with the threads [0, nthreads) of a group that
+// synchronises through `sync()` (a __syncwarp or a named barrier).
+template <typename Sync>
+__device__ __forceinline__ void bitonic_sort_u64(uint64_t* keys, int n, int tid, int nthreads, Sync sync) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < (n >> 1); i += nthreads) {
+                // i-th compare-exchange of this stage: indices (a, a^j) with bit j of a clear
+                const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int b = a | j;
+                const uint64_t ka = keys[a], kb = keys[b];
+                const bool up = (a & k) == 0;
+                if ((ka > kb) == up) { keys[a] = kb; keys[b] = ka; }
+            }
+            sync();
+        }
+    }
+}
+
+// Same with a 32-bit payload carried along (shard merge: ids travel with their keys).
+template <typename Sync>
+__device__ __forceinline__ void bitonic_sort_u64_u32(uint64_t* keys, uint32_t* vals, int n, int tid,
+                                                     int nthreads, Sync sync) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < (n >> 1); i += nthreads) {
+                const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int b = a | j;
+                const uint64_t ka = keys[a], kb = keys[b];
+                const bool up = (a & k) == 0;
+                if ((ka > kb) == up) {
+                    keys[a] = kb; keys[b] = ka;
+                    const uint32_t va = vals[a]; vals[a] = vals[b]; vals[b] = va;
+                }
+            }
+            sync();
+        }
+    }
+}
+
+struct WarpSync {
+    __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+struct BlockSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// Per-warp candidate list in shared memory.  Holds the r smallest keys seen so far plus
+// the candidates appended since the last compaction.  Because a warp visits its vectors in
+// increasing canonical order (probe rank, then position), a later vector whose distance
+// EQUALS the r-th held distance can never enter the top r, so the pass test is the strict
+// `d < bound` of the reference heap (binheap.hpp:93) and ties resolve to the earlier
+// position — the stated tie-break.
+struct WarpList {
+    uint64_t* keys;  // cap entries, unused slots hold kEmptyKey
+    int* count;      // entries in use
+    int* bound;      // pass iff d < *bound
+
+    __device__ __forceinline__ void push(uint64_t key) {
+        const int i = atomicAdd(count, 1);
+        keys[i] = key;
+    }
+    // Keep the r smallest. All 32 lanes call it.
+    __device__ __forceinline__ void compact(int cap, int r, int lane) {
+        __syncwarp();
+        bitonic_sort_u64(keys, cap, lane, 32, WarpSync());
+        const int n = min(*count, r);
+        __syncwarp();
+        for (int i = r + lane; i < cap; i += 32) keys[i] = kEmptyKey;
+        if (lane == 0) {
+            *count = n;
+            *bound = (n == r) ? static_cast<int>(keys[r - 1] >> 48) : 127;
+        }
+        __syncwarp();
+    }
+};
+
+}  // namespace qadc

@@ -1,0 +1,424 @@
+// qadc_scan.cuh — layout, scan, distance-dump and top-r merge kernels (sm_100a).
+// Replaces, on the device: interleave_partition_4 (simd_layout.hpp:55-65), scan_avx_4<16|32>
+// + compare_extract_matches_sse + bh_push (simd_scan.hpp:63-187) and the result heap
+// kv_binheap<unsigned,int8_t> (binheap.hpp:75-116) under the canonical selection rule.
+#pragma once
+#include "qadc_device.cuh"
+
+namespace qadc {
+
+// ------------------------------------------------------------------------------------------
+// Layout: row-major codes -> nibble-plane superblocks.  One thread per (superblock, lane):
+// it reads its 8 consecutive codes (8*M/2 contiguous bytes) and emits M words.  Vectors
+// past the end of the partition replicate the last one, like the reference's pad lanes
+// (simd_layout.hpp:46-50); the scan never selects them (position check).
+// ------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(256) transpose_codes_kernel(const uint8_t* __restrict__ codes,  // chunk, row-major
+                                                              uint32_t count,        // vectors in this chunk
+                                                              uint8_t* __restrict__ out,  // partition base (native)
+                                                              uint32_t first) {      // multiple of 256
+    constexpr int CS = M / 2;
+    const uint32_t gidx = blockIdx.x * blockDim.x + threadIdx.x;   // group index inside the chunk
+    const uint32_t n_groups = ((count + kSbVec - 1) / kSbVec) * 32;
+    if (gidx >= n_groups) return;
+    uint32_t word[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) word[j] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t v = gidx * 8 + k;
+        if (v >= count) v = count - 1;
+        const uint8_t* c = codes + static_cast<size_t>(v) * CS;
+#pragma unroll
+        for (int b = 0; b < CS; ++b) {
+            const uint32_t byte = c[b];
+            word[2 * b] |= (byte & 15u) << (4 * k);
+            word[2 * b + 1] |= (byte >> 4) << (4 * k);
+        }
+    }
+    const uint32_t sb = first / kSbVec + gidx / 32, lane = gidx % 32;
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(sb) * sb_bytes(M));
+#pragma unroll
+    for (int q = 0; q < M / 4; ++q)
+        dst[q * 32 + lane] = make_uint4(word[4 * q], word[4 * q + 1], word[4 * q + 2], word[4 * q + 3]);
+}
+
+// Inverse (tests: layout round trip).
+template <int M>
+__global__ void __launch_bounds__(256) untranspose_codes_kernel(const uint8_t* __restrict__ native, uint32_t size,
+                                                                uint8_t* __restrict__ codes) {
+    constexpr int CS = M / 2;
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= size) return;
+    const uint32_t sb = v / kSbVec, lane = (v % kSbVec) / 8, k = v % 8;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(native + static_cast<size_t>(sb) * sb_bytes(M));
+#pragma unroll
+    for (int b = 0; b < CS; ++b) {
+        const int j0 = 2 * b, j1 = 2 * b + 1;
+        const uint32_t lo = (w[((j0 / 4) * 32 + lane) * 4 + (j0 % 4)] >> (4 * k)) & 15u;
+        const uint32_t hi = (w[((j1 / 4) * 32 + lane) * 4 + (j1 % 4)] >> (4 * k)) & 15u;
+        codes[static_cast<size_t>(v) * CS + b] = static_cast<uint8_t>(lo | (hi << 4));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared pieces of the scan kernels
+// ------------------------------------------------------------------------------------------
+// Append every vector of a group whose sum is below the bound.  pos0 = position of vector
+// k=0 inside the (local) partition.
+__device__ __forceinline__ void emit_candidates(const uint32_t (&acc)[4], uint32_t bound, uint32_t pos0,
+                                                uint32_t size, uint32_t pos_base, uint32_t probe_rank,
+                                                WarpList& list) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t reg = acc[((k >> 2) << 1) | (k & 1)];
+        const uint32_t v = (reg >> (((k >> 1) & 1) * 16)) & 0xffffu;
+        if (!(v & 0x8000u) && pos0 + k < size) list.push(make_key(v + bound - 0x8000u, probe_rank, pos_base + pos0 + k));
+    }
+}
+
+// Writes a warp's final sorted list (r keys, kEmptyKey padded) to global memory.
+__device__ __forceinline__ void store_list(const WarpList& list, uint64_t* dst, int r, int lane) {
+    for (int i = lane; i < r; i += 32) dst[i] = list.keys[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Flat scan: grid = (chunks along the database, query groups of QB).  NW consumer warps +
+// one producer warp per CTA; the producer streams tiles of NW*G superblocks through an
+// NS-stage shared-memory ring with TMA bulk copies; consumer warp w owns superblocks
+// [w*G, w*G+G) of every tile.  Each warp keeps one candidate list per query.
+// ------------------------------------------------------------------------------------------
+struct FlatScanArgs {
+    const uint8_t* codes;   // native layout of the partition
+    uint32_t n_sb;          // superblocks in the partition
+    uint32_t size;          // vectors in the (local) partition
+    uint32_t pos_base;      // position of local vector 0 in the full partition
+    uint32_t sb_per_chunk;
+    const int8_t* qtabs;    // [nq][M*16]
+    int nq, r, cap;
+    uint64_t* lists;        // [nq][n_lists][r]
+    int n_lists;            // gridDim.x * NW
+};
+
+template <int M, int QB, int G, int NW, int NS>
+struct FlatCfg {
+    static constexpr int kQuads = M / 4;
+    static constexpr int kSbBytes = M * 128;
+    static constexpr int kTileSb = NW * G;
+    static constexpr int kTileBytes = kTileSb * kSbBytes;
+    static constexpr bool kRegTab = (QB == 1 && M == 16);
+    static constexpr int kThreads = (NW + 1) * 32;
+    static size_t smem_bytes(int cap) {
+        return static_cast<size_t>(NS) * kTileBytes + static_cast<size_t>(QB) * M * 16 +
+               static_cast<size_t>(NW) * QB * cap * 8 + static_cast<size_t>(NW) * QB * 8 + 2 * NS * 8 + 128;
+    }
+};
+
+template <int M, int QB, int G, int NW, int NS>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatScanArgs a) {
+    using Cfg = FlatCfg<M, QB, G, NW, NS>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* tiles = smem;
+    uint4* qtab = reinterpret_cast<uint4*>(tiles + static_cast<size_t>(NS) * Cfg::kTileBytes);   // [QB][M]
+    uint64_t* lists = reinterpret_cast<uint64_t*>(qtab + QB * M);                                 // [NW][QB][cap]
+    int* cnt = reinterpret_cast<int*>(lists + static_cast<size_t>(NW) * QB * a.cap);              // [NW][QB]
+    int* bnd = cnt + NW * QB;
+    uint64_t* full = reinterpret_cast<uint64_t*>(bnd + NW * QB);
+    uint64_t* empty = full + NS;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sb0 = min(blockIdx.x * a.sb_per_chunk, a.n_sb);
+    const uint32_t sb1 = min(sb0 + a.sb_per_chunk, a.n_sb);
+    const uint32_t n_tiles = (sb1 - sb0 + Cfg::kTileSb - 1) / Cfg::kTileSb;
+    const int qbase = blockIdx.y * QB;
+    const int nqb = min(QB, a.nq - qbase);
+
+    // ---- init ----
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < QB * M; i += blockDim.x) {
+        const int qi = i / M;
+        qtab[i] = (qi < nqb) ? reinterpret_cast<const uint4*>(a.qtabs)[static_cast<size_t>(qbase) * M + i]
+                             : make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+    }
+    for (int i = threadIdx.x; i < NW * QB * a.cap; i += blockDim.x) lists[i] = kEmptyKey;
+    for (int i = threadIdx.x; i < NW * QB; i += blockDim.x) { cnt[i] = 0; bnd[i] = 127; }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ---- producer: one elected lane drives the TMA ring ----
+        if (lane == 0) {
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const int s = t % NS;
+                if (t >= NS) mbar_wait(&empty[s], ((t / NS) & 1) ^ 1);
+                const uint32_t tsb = sb0 + t * Cfg::kTileSb;
+                const uint32_t bytes = min(static_cast<uint32_t>(Cfg::kTileSb), sb1 - tsb) * Cfg::kSbBytes;
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s(tiles + static_cast<size_t>(s) * Cfg::kTileBytes,
+                         a.codes + static_cast<size_t>(tsb) * Cfg::kSbBytes, bytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    WarpList wl[QB];
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) {
+        wl[qi].keys = lists + (static_cast<size_t>(warp) * QB + qi) * a.cap;
+        wl[qi].count = cnt + warp * QB + qi;
+        wl[qi].bound = bnd + warp * QB + qi;
+    }
+    uint4 treg[Cfg::kRegTab ? M : 1];
+    if constexpr (Cfg::kRegTab) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) treg[j] = qtab[j];
+    }
+
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        const int s = t % NS;
+        mbar_wait(&full[s], (t / NS) & 1);
+        const uint8_t* tile = tiles + static_cast<size_t>(s) * Cfg::kTileBytes;
+        const uint32_t tsb = sb0 + t * Cfg::kTileSb + warp * G;   // first superblock of this warp
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) {
+            if (qi < nqb) {
+                const uint32_t bound = *wl[qi].bound;
+                uint32_t acc[G][4];
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[g][i] = acc_init(bound);
+#pragma unroll
+                for (int q = 0; q < Cfg::kQuads; ++q) {
+                    uint4 tq[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if constexpr (Cfg::kRegTab) tq[i] = treg[4 * q + i];
+                        else tq[i] = qtab[qi * M + 4 * q + i];
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const uint4 w = *reinterpret_cast<const uint4*>(
+                            tile + static_cast<size_t>(warp * G + g) * Cfg::kSbBytes + q * 512 + lane * 16);
+                        lut_quad(w, tq, acc[g]);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (tsb + g < sb1 && any_below(acc[g]))
+                        emit_candidates(acc[g], bound, (tsb + g) * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi)
+            if (qi < nqb && *wl[qi].count > a.cap - G * kSbVec) wl[qi].compact(a.cap, a.r, lane);
+    }
+
+    // ---- final: sort and publish one list per (warp, query) ----
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) {
+        if (qi < nqb) {
+            wl[qi].compact(a.cap, a.r, lane);
+            store_list(wl[qi],
+                       a.lists + (static_cast<size_t>(qbase + qi) * a.n_lists + blockIdx.x * NW + warp) * a.r,
+                       a.r, lane);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// IVF scan: grid = (probe chunks, queries); each warp takes whole probes of its query in
+// rank order (rank a0+warp, a0+warp+NW, ...), loads that probe's int8 table and streams the
+// inverted list with coalesced 128-bit loads (lists are short and mostly L2-resident).
+// ------------------------------------------------------------------------------------------
+struct IvfScanArgs {
+    const uint8_t* codes;            // native layout, all partitions
+    const uint64_t* part_sb_off;     // [K] first superblock of partition p
+    const uint32_t* part_size;       // [K]
+    const uint32_t* part_pos_base;   // [K]
+    const int32_t* assign;           // [nq][ma]
+    const int8_t* qtabs;             // [nq][ma][M*16]
+    int nq, ma, r, cap, probes_per_chunk;
+    uint64_t* lists;                 // [nq][n_lists][r]
+    int n_lists;                     // gridDim.x * NW
+};
+
+template <int M, int NW>
+__global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) {
+    constexpr int kQuads = M / 4, kSbBytes = M * 128;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem);                         // [NW][cap]
+    int* cnt = reinterpret_cast<int*>(lists + static_cast<size_t>(NW) * a.cap);  // [NW]
+    int* bnd = cnt + NW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.y;
+    const int a0 = blockIdx.x * a.probes_per_chunk, a1 = min(a0 + a.probes_per_chunk, a.ma);
+
+    WarpList wl{lists + static_cast<size_t>(warp) * a.cap, cnt + warp, bnd + warp};
+    for (int i = lane; i < a.cap; i += 32) wl.keys[i] = kEmptyKey;
+    if (lane == 0) { *wl.count = 0; *wl.bound = 127; }
+    __syncwarp();
+
+    for (int ar = a0 + warp; ar < a1; ar += NW) {
+        const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
+        const uint32_t size = a.part_size[p];
+        if (size == 0) continue;   // db_query_4.cpp:291-293
+        const uint32_t pos_base = a.part_pos_base[p];
+        const uint4* tsrc = reinterpret_cast<const uint4*>(a.qtabs) + (static_cast<size_t>(q) * a.ma + ar) * M;
+        uint4 treg[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) treg[j] = __ldg(tsrc + j);
+        const uint8_t* base = a.codes + a.part_sb_off[p] * kSbBytes;
+        const uint32_t n_sb = (size + kSbVec - 1) / kSbVec;
+        for (uint32_t sb = 0; sb < n_sb; ++sb) {
+            const uint32_t bound = *wl.bound;
+            uint32_t acc[4] = {acc_init(bound), acc_init(bound), acc_init(bound), acc_init(bound)};
+            const uint4* src = reinterpret_cast<const uint4*>(base + static_cast<size_t>(sb) * kSbBytes) + lane;
+            uint4 w[kQuads];
+#pragma unroll
+            for (int qd = 0; qd < kQuads; ++qd) w[qd] = __ldg(src + qd * 32);
+#pragma unroll
+            for (int qd = 0; qd < kQuads; ++qd) {
+                const uint4 tq[4] = {treg[4 * qd], treg[4 * qd + 1], treg[4 * qd + 2], treg[4 * qd + 3]};
+                lut_quad(w[qd], tq, acc);
+            }
+            if (any_below(acc)) emit_candidates(acc, bound, sb * kSbVec + lane * 8, size, pos_base, ar, wl);
+            __syncwarp();
+            if (*wl.count > a.cap - kSbVec) wl.compact(a.cap, a.r, lane);
+        }
+    }
+    wl.compact(a.cap, a.r, lane);
+    store_list(wl, a.lists + (static_cast<size_t>(q) * a.n_lists + blockIdx.x * NW + warp) * a.r, a.r, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage D: quantised distance of every vector of one partition for one table — runs the
+// same lookup core as the scan kernels and writes min(127, sum).
+// ------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(256) dump_distances_kernel(const uint8_t* __restrict__ native, uint32_t size,
+                                                             const int8_t* __restrict__ qtab,
+                                                             int8_t* __restrict__ out) {
+    constexpr int kQuads = M / 4, kSbBytes = M * 128;
+    const uint32_t sb = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (static_cast<uint64_t>(sb) * kSbVec >= size) return;
+    uint32_t acc[4] = {acc_init(0), acc_init(0), acc_init(0), acc_init(0)};
+    const uint4* src = reinterpret_cast<const uint4*>(native + static_cast<size_t>(sb) * kSbBytes) + lane;
+    const uint4* t = reinterpret_cast<const uint4*>(qtab);
+#pragma unroll
+    for (int qd = 0; qd < kQuads; ++qd) {
+        const uint4 tq[4] = {__ldg(t + 4 * qd), __ldg(t + 4 * qd + 1), __ldg(t + 4 * qd + 2), __ldg(t + 4 * qd + 3)};
+        lut_quad(__ldg(src + qd * 32), tq, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t pos = sb * kSbVec + lane * 8 + k;
+        if (pos < size) out[pos] = static_cast<int8_t>(min(127u, lane_sum(acc, k, 0)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Top-r merge: one CTA per query streams L sorted lists of r keys (optionally with ids) and
+// keeps the r smallest in a shared-memory buffer (bitonic sort, bound filter).  Used to merge
+// per-warp lists of the scan kernels, per-split prefix lists, and the shards of a
+// multi-GPU database after the NCCL all-gather.
+// Outputs (any may be null): keys, ids, int8 distances, count of real entries.
+// Label resolution (IVF): id = labels[label_off[assign[q][rank]] + (pos - pos_base[part])]
+// when `labels` is given; otherwise id = in_ids[...] if given, else the key's low 32 bits.
+// ------------------------------------------------------------------------------------------
+struct MergeArgs {
+    const uint64_t* in_keys;   // [nq][L][r]  (or [L][nq][r] when shard_major)
+    const uint32_t* in_ids;    // same shape or null
+    int L, r, nq, shard_major;
+    uint64_t* out_keys;        // [nq][r]
+    uint32_t* out_ids;
+    int8_t* out_dists;
+    int32_t* out_counts;
+    float* out_rth_value;      // [nq]: float bits of the r-th key >> 32 (prefix qmax), FLT_MAX if < r keys
+    // label resolution
+    const uint32_t* labels;
+    const uint64_t* label_off;       // [K]
+    const uint32_t* part_pos_base;   // [K]
+    const int32_t* assign;           // [nq][ma]
+    int ma;
+};
+
+constexpr int kMergeCap = 2048;      // supports r <= 1024
+constexpr int kMergeThreads = 256;
+
+__global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(const MergeArgs a) {
+    __shared__ uint64_t keys[kMergeCap];
+    __shared__ uint32_t vals[kMergeCap];   // payload: index of the source slot
+    __shared__ int count;
+    __shared__ unsigned long long bound_key;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < kMergeCap; i += kMergeThreads) { keys[i] = kEmptyKey; vals[i] = 0; }
+    if (tid == 0) { count = 0; bound_key = kEmptyKey; }
+    __syncthreads();
+    const int total = a.L * a.r;
+    const int step = kMergeCap / 2;   // inputs per round; buffer holds <= r <= cap/2 before a round
+    for (int base = 0; base < total; base += step) {
+        const unsigned long long bk = bound_key;
+        for (int i = base + tid; i < min(base + step, total); i += kMergeThreads) {
+            const int l = i / a.r, e = i % a.r;
+            const size_t src = a.shard_major ? (static_cast<size_t>(l) * a.nq + q) * a.r + e
+                                             : (static_cast<size_t>(q) * a.L + l) * a.r + e;
+            const uint64_t k = a.in_keys[src];
+            if (k < bk) {
+                const int slot = atomicAdd(&count, 1);
+                keys[slot] = k;
+                vals[slot] = static_cast<uint32_t>(src);
+            }
+        }
+        __syncthreads();
+        if (count > kMergeCap - step || base + step >= total) {
+            bitonic_sort_u64_u32(keys, vals, kMergeCap, tid, kMergeThreads, BlockSync());
+            const int n = min(count, a.r);
+            __syncthreads();
+            for (int i = a.r + tid; i < kMergeCap; i += kMergeThreads) keys[i] = kEmptyKey;
+            if (tid == 0) { count = n; bound_key = (n == a.r) ? keys[a.r - 1] : kEmptyKey; }
+            __syncthreads();
+        }
+    }
+    if (total == 0) __syncthreads();
+    const int n = count;
+    for (int i = tid; i < a.r; i += kMergeThreads) {
+        const uint64_t k = keys[i];
+        const bool real = i < n;
+        const size_t o = static_cast<size_t>(q) * a.r + i;
+        if (a.out_keys) a.out_keys[o] = real ? k : kEmptyKey;
+        if (a.out_dists) a.out_dists[o] = real ? static_cast<int8_t>(k >> 48) : static_cast<int8_t>(127);
+        if (a.out_ids) {
+            uint32_t id = 0;
+            if (real) {
+                const uint32_t pos = static_cast<uint32_t>(k);
+                if (a.labels) {
+                    const uint32_t rank = static_cast<uint32_t>(k >> 32) & 0xffffu;
+                    const int p = a.assign[static_cast<size_t>(q) * a.ma + rank];
+                    id = a.labels[a.label_off[p] + (pos - a.part_pos_base[p])];
+                } else if (a.in_ids) {
+                    id = a.in_ids[vals[i]];
+                } else {
+                    id = pos;
+                }
+            }
+            a.out_ids[o] = id;
+        }
+    }
+    if (tid == 0) {
+        if (a.out_counts) a.out_counts[q] = n;
+        if (a.out_rth_value)
+            a.out_rth_value[q] = (n == a.r) ? __uint_as_float(static_cast<uint32_t>(keys[a.r - 1] >> 32))
+                                            : 3.402823466e+38f;
+    }
+}
+
+}  // namespace qadc

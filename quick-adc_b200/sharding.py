@@ -1,0 +1,54 @@
+"""Host-side sharding of a database across the GPUs of one box.
+
+Flat: contiguous ranges of whole 256-vector superblocks, so that global position =
+shard offset + local position and the canonical order is preserved.  IVF: whole lists are
+assigned to GPUs (greedy by size); a list is never split.  Every shard keeps a replica of
+the keep-prefixes, so all shards derive identical quantisation bounds without a collective;
+the only exchange step is one all-gather of the per-shard top-r (key, id) lists.
+"""
+import numpy as np
+
+SB = 256
+
+
+def start_size(size, keep):
+    """starts_sizes[p] = max(1u, (unsigned)(size * keep)) in float32 (db_query_4.cpp:125-126)."""
+    if size == 0:
+        return 0
+    return max(1, int(np.float32(size) * np.float32(keep)))
+
+
+def flat_shard_range(n, rank, world):
+    """[lo, hi) of shard `rank`: superblocks split as evenly as possible, in order."""
+    n_sb = (n + SB - 1) // SB
+    base, extra = divmod(n_sb, world)
+    sb_lo = rank * base + min(rank, extra)
+    sb_hi = sb_lo + base + (1 if rank < extra else 0)
+    return min(sb_lo * SB, n), min(sb_hi * SB, n)
+
+
+def ivf_list_owner(sizes, world):
+    """Greedy longest-first assignment of whole lists to shards. Returns owner[p]."""
+    sizes = np.asarray(sizes, np.int64)
+    owner = np.zeros(len(sizes), np.int32)
+    load = np.zeros(world, np.int64)
+    for p in np.argsort(-sizes, kind="stable"):
+        g = int(np.argmin(load))
+        owner[p] = g
+        load[g] += sizes[p]
+    return owner
+
+
+def all_gather_topk(keys, ids, group=None):
+    """One all-gather of the per-shard top-r lists: keys int64 [nq, r], ids int32 [nq, r]
+    -> ([G, nq, r], [G, nq, r]) in rank order, the layout qadc_merge_shards_device reads.
+    NCCL on CUDA tensors (NVLink/NVSwitch), gloo on CPU tensors (tests)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    nq = keys.shape[0]
+    gk = torch.empty((world * nq,) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
+    gi = torch.empty((world * nq,) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
+    dist.all_gather_into_tensor(gk, keys.contiguous(), group=group)   # concatenation along dim 0
+    dist.all_gather_into_tensor(gi, ids.contiguous(), group=group)
+    return gk.view((world,) + tuple(keys.shape)), gi.view((world,) + tuple(ids.shape))

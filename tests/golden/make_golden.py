@@ -1,0 +1,96 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libqadc_ref.so,
+built from /root/reference by oracle/Makefile).  Run in the CPU container:
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or fixtures, so these files are what pins the
+oracle and the CUDA path to the reference's behaviour on the GPU box, where
+/root/reference does not exist.  Every array below that starts with ``ref_`` was produced
+by reference code; the rest are the seeded inputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle.pyoracle import Ref  # noqa: E402
+import synth  # noqa: E402
+
+
+def flat_case(ref, name, seed, dim, m, n, nq, r, keep):
+    rng = np.random.default_rng(seed)
+    cb = synth.make_pq(rng, dim, m)
+    codes = synth.make_codes(rng, n, m)
+    queries = synth.make_queries(rng, nq, dim)
+    out = dict(dim=dim, m=m, r=r, keep=np.float32(keep), codebooks=cb, codes=codes, queries=queries)
+    out["ref_interleaved"] = ref.interleave(codes)
+    out["ref_tables_direct"] = ref.tables(queries, m, cb, False)        # compute_dists_single_simd_cg
+    out["ref_tables_blas"] = ref.tables(queries, m, cb, True)           # compute_dists_multiple_blas_cg
+    h = ref.flat(dim, m, cb, codes)
+    h.prepare(keep)
+    out["ref_start_size"] = np.array([h.starts_size(0)], np.uint32)
+    res = h.search(queries, 1, r, nthreads=1, blas_tables=False, want_tables=True)   # what `db_query_4 -b1` runs
+    out["ref_heap_keys"], out["ref_heap_vals"], out["ref_heap_sizes"] = res["keys"], res["vals"], res["sizes"]
+    out["ref_tables_used"] = res["tables"]                                # after the in-place clamp
+    qmin = np.zeros(nq, np.float32)
+    qmax = np.zeros(nq, np.float32)
+    qt = np.zeros((nq, 1, m, 16), np.int8)
+    dist = np.zeros((nq, n), np.int8)
+    for q in range(nq):
+        a = np.zeros(1, np.int32)
+        qmin[q], qmax[q] = h.query_bounds(a, out["ref_tables_direct"][q], r)
+        qmin[q] = max(qmin[q], 0.0)                                       # db_query_4.cpp:262-263
+        qt[q, 0] = ref.quantize(res["tables"][q, 0], qmin[q], qmax[q])    # QuantizerMAX
+        dist[q] = ref.dump_distances(out["ref_interleaved"], n, m, qt[q, 0])   # scan_avx_4 per-vector values
+    out.update(ref_qmin=qmin, ref_qmax=qmax, ref_qtables=qt, ref_distances=dist)
+    h.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "heap sizes", res["sizes"], "d<127 per query", (dist < 127).sum(1))
+
+
+def ivf_case(ref, name, seed, dim, m, n, K, ma, nq, r, keep, empty=()):
+    rng = np.random.default_rng(seed)
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2.0 * rng.standard_normal((K, dim))).astype(np.float32)
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty)
+    queries = synth.make_queries(rng, nq, dim)
+    out = dict(dim=dim, m=m, r=r, ma=ma, keep=np.float32(keep), codebooks=cb, centroids=cents, codes=codes,
+               labels=labels, offsets=offsets, queries=queries)
+    h = ref.ivf(dim, m, cb, cents, codes, labels, offsets)
+    h.prepare(keep)
+    out["ref_start_size"] = np.array([h.starts_size(p) for p in range(K)], np.uint32)
+    # K <= 256, so find_k_neighbors is correct as shipped
+    out["ref_assign_fkn"] = ref.find_k_neighbors(queries, cents, ma)
+    res = h.search(queries, ma, r, nthreads=1, blas_tables=False, want_tables=True)
+    out["ref_assign"] = res["assign"]
+    out["ref_heap_keys"], out["ref_heap_vals"], out["ref_heap_sizes"] = res["keys"], res["vals"], res["sizes"]
+    out["ref_tables_used"] = res["tables"]                                # blas form (ma > 1), clamped
+    qmin = np.zeros(nq, np.float32)
+    qmax = np.zeros(nq, np.float32)
+    qt = np.zeros((nq, ma, m, 16), np.int8)
+    for q in range(nq):
+        qmin[q], qmax[q] = h.query_bounds(res["assign"][q], res["tables"][q], r)
+        qmin[q] = max(qmin[q], 0.0)
+        qt[q] = ref.quantize(res["tables"][q], qmin[q], qmax[q])
+    out.update(ref_qmin=qmin, ref_qmax=qmax, ref_qtables=qt)
+    h.close()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "heap sizes", res["sizes"])
+
+
+def main():
+    ref = Ref()
+    # n = 3003: not a multiple of 16 -> exercises the pad-lane duplicate quirk
+    flat_case(ref, "flat_m16", seed=101, dim=128, m=16, n=3003, nq=8, r=20, keep=0.05)
+    # 96-d, m=32 -> sq_dim 3 (only reachable by direct template instantiation)
+    flat_case(ref, "flat_m32", seed=102, dim=96, m=32, n=2048, nq=6, r=16, keep=0.05)
+    ivf_case(ref, "ivf_m16", seed=103, dim=128, m=16, n=6000, K=24, ma=5, nq=8, r=20, keep=0.08, empty=(3,))
+    ivf_case(ref, "ivf_m32", seed=104, dim=96, m=32, n=4000, K=12, ma=3, nq=6, r=10, keep=0.1)
+
+
+if __name__ == "__main__":
+    main()

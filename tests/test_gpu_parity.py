@@ -1,0 +1,379 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs and against the golden vectors of the unmodified reference.
+
+Parity protocol: Stage T float tables/bounds (tolerance 1e-5 relative; bit-equal
+to the oracle, which uses the same explicit float operations), Stage D per-vector int8
+distances bit-exact, Stage S canonical top-r bit-exact, Stage R tie-class equivalence against
+the raw reference heap."""
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from test_oracle import FLAT, IVF, FLOAT_RTOL, load, rel_err, blas_scale, tie_class_check
+
+pytestmark = pytest.mark.gpu
+
+
+def flat_index(qadc, dim, m, cb, codes, keep):
+    ix = qadc.Index(0)
+    ix.set_pq(dim, m, cb)
+    ix.load_flat(codes, keep)
+    return ix
+
+
+def ivf_index(qadc, dim, m, cb, cents, codes, labels, offsets, keep):
+    ix = qadc.Index(0)
+    ix.set_pq(dim, m, cb)
+    ix.set_coarse(cents)
+    ix.load_ivf(codes, labels, offsets, keep)
+    return ix
+
+
+# ---- layout ------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m", [(1, 16), (255, 16), (256, 16), (257, 32), (3003, 16), (70000, 32)])
+def test_layout_round_trip(qadc, n, m):
+    rng = np.random.default_rng(n + m)
+    codes = synth.make_codes(rng, n, m)
+    ix = flat_index(qadc, 8 * m, m, synth.make_pq(rng, 8 * m, m), codes, 1.0)
+    assert np.array_equal(ix.download_codes(0), codes)
+    ix.close()
+
+
+def test_chunked_upload_equals_single_upload(qadc):
+    rng = np.random.default_rng(3)
+    m, n = 16, 256 * 9 + 77
+    codes = synth.make_codes(rng, n, m)
+    ix = qadc.Index(0)
+    ix.set_pq(128, m, synth.make_pq(rng, 128, m))
+    ix.begin_database([n], False)
+    for first in range(0, n, 768):
+        ix.upload_codes(0, first, codes[first:first + 768])
+    ix.finalize(0.1)
+    assert np.array_equal(ix.download_codes(0), codes)
+    ix.close()
+
+
+# ---- Stage D: per-vector distances ---------------------------------------------------------
+@pytest.mark.parametrize("n,m", [(1, 16), (300, 16), (4099, 16), (2048, 32), (50001, 32), (200000, 16)])
+def test_distances_bit_exact_vs_oracle(qadc, oracle, n, m):
+    rng = np.random.default_rng(n * 7 + m)
+    codes = synth.make_codes(rng, n, m)
+    ix = flat_index(qadc, 8 * m, m, synth.make_pq(rng, 8 * m, m), codes, 1.0)
+    for p_sat in (0.0, 0.15, 0.6):
+        qt = synth.make_qtables(rng, (), m, hi=128 // m * 3, p_sat=p_sat)
+        assert np.array_equal(ix.dump_distances(0, qt), oracle.distances(codes, qt))
+    # extreme tables: all zero, all 127, single large entries
+    for qt in (np.zeros((m, 16), np.int8), np.full((m, 16), 127, np.int8)):
+        assert np.array_equal(ix.dump_distances(0, qt), oracle.distances(codes, qt))
+    ix.close()
+
+
+@pytest.mark.parametrize("name", FLAT)
+def test_distances_match_reference_golden(qadc, name):
+    g = load(name)
+    ix = flat_index(qadc, int(g["dim"]), int(g["m"]), g["codebooks"], g["codes"], float(g["keep"]))
+    for q in range(g["queries"].shape[0]):
+        assert np.array_equal(ix.dump_distances(0, g["ref_qtables"][q, 0]), g["ref_distances"][q])   # scan_avx_4 values
+    ix.close()
+
+
+def test_negative_table_entries_rejected(qadc):
+    rng = np.random.default_rng(1)
+    ix = flat_index(qadc, 128, 16, synth.make_pq(rng, 128, 16), synth.make_codes(rng, 100, 16), 1.0)
+    qt = np.zeros((16, 16), np.int8)
+    qt[3, 5] = -1
+    with pytest.raises(qadc.QadcError):
+        ix.dump_distances(0, qt)
+    ix.close()
+
+
+# ---- Stage S: canonical top-r with injected tables -----------------------------------------
+@pytest.mark.parametrize("n,m,nq,r", [(300, 16, 3, 10), (5000, 16, 9, 100), (70001, 16, 5, 100), (4096, 32, 4, 50),
+                                      (60000, 32, 7, 100), (1000, 16, 2, 700), (50, 16, 2, 100)])
+@pytest.mark.parametrize("qb", [0, 1, 2, 4])
+def test_flat_scan_with_tables_bit_exact(qadc, oracle, n, m, nq, r, qb):
+    rng = np.random.default_rng(n + 13 * m + nq)
+    codes = synth.make_codes(rng, n, m)
+    ix = flat_index(qadc, 8 * m, m, synth.make_pq(rng, 8 * m, m), codes, 1.0)
+    ix.set_option("flat_qb", qb)
+    qt = synth.make_qtables(rng, (nq, 1), m, hi=max(3, 200 // m), p_sat=0.1)
+    ids, d, cnt = ix.scan_with_tables(np.zeros((nq, 1), np.int32), qt, r)
+    offsets = np.array([0, n], np.int64)
+    for q in range(nq):
+        e_ids, e_d, e_cnt, _ = oracle.scan_with_tables(codes, None, offsets, np.zeros(1, np.int32), qt[q], r)
+        assert cnt[q] == e_cnt
+        assert np.array_equal(d[q], e_d)
+        assert np.array_equal(ids[q], e_ids)
+    ix.close()
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 64])
+def test_flat_scan_independent_of_chunking(qadc, oracle, chunks):
+    rng = np.random.default_rng(99)
+    n, m, nq, r = 123457, 16, 3, 100
+    codes = synth.make_codes(rng, n, m)
+    ix = flat_index(qadc, 128, m, synth.make_pq(rng, 128, m), codes, 1.0)
+    ix.set_option("flat_chunks", chunks)
+    qt = synth.make_qtables(rng, (nq, 1), m, hi=14, p_sat=0.05)
+    ids, d, cnt = ix.scan_with_tables(np.zeros((nq, 1), np.int32), qt, r)
+    for q in range(nq):
+        e_ids, e_d, e_cnt, _ = oracle.scan_with_tables(codes, None, np.array([0, n], np.int64), np.zeros(1, np.int32), qt[q], r)
+        assert cnt[q] == e_cnt and np.array_equal(d[q], e_d) and np.array_equal(ids[q], e_ids)
+    ix.close()
+
+
+def test_flat_scan_degenerate_ties(qadc, oracle):
+    """All vectors identical / all-zero tables: the answer is the first r positions."""
+    n, m, r = 10000, 16, 100
+    codes = np.zeros((n, m // 2), np.uint8)
+    ix = flat_index(qadc, 128, m, synth.make_pq(np.random.default_rng(0), 128, m), codes, 1.0)
+    for val in (0, 5):
+        qt = np.full((2, 1, m, 16), val, np.int8)
+        ids, d, cnt = ix.scan_with_tables(np.zeros((2, 1), np.int32), qt, r)
+        assert np.all(cnt == r) and np.all(d == min(127, val * m))
+        assert np.array_equal(ids[0], np.arange(r, dtype=np.uint32))
+    # nothing below 127 -> sentinels only (db_query_4.cpp:276)
+    qt = np.full((1, 1, m, 16), 127, np.int8)
+    ids, d, cnt = ix.scan_with_tables(np.zeros((1, 1), np.int32), qt, r)
+    assert cnt[0] == 0 and np.all(ids == 0) and np.all(d == 127)
+    ix.close()
+
+
+@pytest.mark.parametrize("name", IVF)
+def test_ivf_scan_with_reference_tables(qadc, oracle, name):
+    """Injected assign + the reference's own int8 tables: canonical result bit-exact vs the
+    oracle, tie-class equivalent to the raw reference heap (Stage R)."""
+    g = load(name)
+    r, m, ma = int(g["r"]), int(g["m"]), int(g["ma"])
+    codes, labels, offsets = g["codes"], g["labels"], g["offsets"]
+    ix = ivf_index(qadc, int(g["dim"]), m, g["codebooks"], g["centroids"], codes, labels, offsets, float(g["keep"]))
+    ids, d, cnt = ix.scan_with_tables(g["ref_assign"], g["ref_qtables"], r)
+    checked = 0
+    for q in range(g["queries"].shape[0]):
+        a = g["ref_assign"][q]
+        e_ids, e_d, e_cnt, _ = oracle.scan_with_tables(codes, labels, offsets, a, g["ref_qtables"][q], r)
+        assert cnt[q] == e_cnt and np.array_equal(d[q], e_d) and np.array_equal(ids[q], e_ids)
+        d_parts = [oracle.distances(codes[offsets[p]:offsets[p + 1]], g["ref_qtables"][q, k])
+                   if offsets[p + 1] > offsets[p] else np.zeros(0, np.int8) for k, p in enumerate(a)]
+        l_parts = [labels[offsets[p]:offsets[p + 1]] for p in a]
+        checked += tie_class_check(ids[q], d[q], cnt[q], g["ref_heap_keys"][q], g["ref_heap_vals"][q], d_parts, l_parts)
+    assert checked >= 1
+    ix.close()
+
+
+@pytest.mark.parametrize("name", FLAT)
+def test_flat_scan_vs_reference_heap(qadc, oracle, name):
+    g = load(name)
+    r = int(g["r"])
+    ix = flat_index(qadc, int(g["dim"]), int(g["m"]), g["codebooks"], g["codes"], float(g["keep"]))
+    ids, d, cnt = ix.scan_with_tables(np.zeros((g["queries"].shape[0], 1), np.int32), g["ref_qtables"], r)
+    checked = 0
+    for q in range(g["queries"].shape[0]):
+        checked += tie_class_check(ids[q], d[q], cnt[q], g["ref_heap_keys"][q], g["ref_heap_vals"][q],
+                                   [g["ref_distances"][q]], [None])
+    assert checked >= 1
+    ix.close()
+
+
+def test_ivf_random_large(qadc, oracle):
+    rng = np.random.default_rng(21)
+    n, K, m, ma, nq, r = 40000, 64, 16, 8, 12, 100
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(5, 17))
+    cb = synth.make_pq(rng, 128, m)
+    cents = rng.standard_normal((K, 128)).astype(np.float32)
+    ix = ivf_index(qadc, 128, m, cb, cents, codes, labels, offsets, 0.05)
+    assign = np.stack([rng.permutation(K)[:ma] for _ in range(nq)]).astype(np.int32)
+    assign[0, 2] = 5   # an empty partition among the probes
+    qt = synth.make_qtables(rng, (nq, ma), m, hi=12, p_sat=0.1)
+    ids, d, cnt = ix.scan_with_tables(assign, qt, r)
+    for q in range(nq):
+        e_ids, e_d, e_cnt, _ = oracle.scan_with_tables(codes, labels, offsets, assign[q], qt[q], r)
+        assert cnt[q] == e_cnt and np.array_equal(d[q], e_d) and np.array_equal(ids[q], e_ids)
+    ix.close()
+
+
+# ---- Stage T: tables, bounds, int8 tables ---------------------------------------------------
+@pytest.mark.parametrize("name", FLAT + IVF)
+def test_table_pipeline_vs_oracle_and_reference(qadc, oracle, name):
+    g = load(name)
+    r, m = int(g["r"]), int(g["m"])
+    ivf = "centroids" in g
+    ma = int(g["ma"]) if ivf else 1
+    n = g["codes"].shape[0]
+    if ivf:
+        ix = ivf_index(qadc, int(g["dim"]), m, g["codebooks"], g["centroids"], g["codes"], g["labels"], g["offsets"],
+                       float(g["keep"]))
+    else:
+        ix = flat_index(qadc, int(g["dim"]), m, g["codebooks"], g["codes"], float(g["keep"]))
+    out = ix.build_tables(g["queries"], ma, r)
+    assert out["rc"] == 0
+    db = dict(dim=int(g["dim"]), m=m, codebooks=g["codebooks"], codes=g["codes"], keep=float(g["keep"]),
+              offsets=g["offsets"] if ivf else np.array([0, n], np.int64))
+    if ivf:
+        db.update(centroids=g["centroids"], labels=g["labels"])
+    exp = oracle.search(db, g["queries"], ma, r)
+    # the device uses the oracle's explicit float operations: expect bit equality
+    assert np.array_equal(out["assign"], exp["assign"])
+    assert np.array_equal(out["tables"], exp["tables"])
+    assert np.array_equal(out["qmin"], exp["qmin"]) and np.array_equal(out["qmax"], exp["qmax"])
+    assert np.array_equal(out["qtables"], exp["qtables"])
+    # and the stated tolerance against the reference itself
+    if ivf:
+        assert np.array_equal(out["assign"], g["ref_assign"])
+        for q in range(g["queries"].shape[0]):
+            resid = g["queries"][q][None, :] - g["centroids"][out["assign"][q]]
+            assert rel_err(out["tables"][q], g["ref_tables_used"][q], blas_scale(resid, g["codebooks"], m)) <= FLOAT_RTOL
+    else:
+        assert rel_err(out["tables"][:, 0], g["ref_tables_direct"], 1e-30) <= FLOAT_RTOL
+    assert np.all(np.abs(out["qmax"] - g["ref_qmax"]) <= FLOAT_RTOL * g["ref_qmax"])
+    assert np.all(np.abs(out["qmin"] - g["ref_qmin"]) <= FLOAT_RTOL * np.maximum(g["ref_qmin"], 1e-3))
+    lsb = np.abs(out["qtables"].astype(int) - g["ref_qtables"].astype(int))
+    assert lsb.max() <= 1 and (lsb != 0).mean() <= 0.02
+    ix.close()
+
+
+def test_opq_rotation(qadc, oracle):
+    rng = np.random.default_rng(8)
+    dim, m, n, nq, r = 64, 16, 4000, 5, 20
+    cb = synth.make_pq(rng, dim, m)
+    rot = np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32)
+    codes = synth.make_codes(rng, n, m)
+    q = synth.make_queries(rng, nq, dim)
+    ix = qadc.Index(0)
+    ix.set_pq(dim, m, cb, rotation=rot)
+    ix.load_flat(codes, 0.05)
+    out = ix.build_tables(q, 1, r)
+    db = dict(dim=dim, m=m, codebooks=cb, rotation=rot, codes=codes, keep=0.05, offsets=np.array([0, n], np.int64))
+    exp = oracle.search(db, q, 1, r)
+    assert np.array_equal(out["tables"], exp["tables"]) and np.array_equal(out["qtables"], exp["qtables"])
+    ids, d, cnt = ix.search(q, 1, r)
+    assert np.array_equal(ids, exp["ids"]) and np.array_equal(d, exp["d"]) and np.array_equal(cnt, exp["count"])
+    ix.close()
+
+
+def test_coarse_assignment_large_k(qadc, oracle):
+    """More than 256 cells: the fixed assignment (the reference's own is wrong there)."""
+    rng = np.random.default_rng(12)
+    dim, K, m, n, nq, ma, r = 32, 1500, 16, 30000, 20, 16, 50
+    cb = synth.make_pq(rng, dim, m)
+    cents = rng.standard_normal((K, dim)).astype(np.float32)
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m)
+    q = synth.make_queries(rng, nq, dim)
+    ix = ivf_index(qadc, dim, m, cb, cents, codes, labels, offsets, 0.3)
+    out = ix.build_tables(q, ma, r)
+    exp_assign, _ = oracle.coarse_assign(q, cents, ma)
+    assert np.array_equal(out["assign"], exp_assign)
+    ix.close()
+
+
+# ---- end to end ----------------------------------------------------------------------------
+@pytest.mark.parametrize("name", FLAT + IVF)
+def test_search_end_to_end_golden_inputs(qadc, oracle, name):
+    g = load(name)
+    r, m = int(g["r"]), int(g["m"])
+    ivf = "centroids" in g
+    ma = int(g["ma"]) if ivf else 1
+    n = g["codes"].shape[0]
+    db = dict(dim=int(g["dim"]), m=m, codebooks=g["codebooks"], codes=g["codes"], keep=float(g["keep"]),
+              offsets=g["offsets"] if ivf else np.array([0, n], np.int64))
+    if ivf:
+        db.update(centroids=g["centroids"], labels=g["labels"])
+        ix = ivf_index(qadc, db["dim"], m, g["codebooks"], g["centroids"], g["codes"], g["labels"], g["offsets"], db["keep"])
+    else:
+        ix = flat_index(qadc, db["dim"], m, g["codebooks"], g["codes"], db["keep"])
+    ids, d, cnt = ix.search(g["queries"], ma, r)
+    exp = oracle.search(db, g["queries"], ma, r)
+    assert np.array_equal(cnt, exp["count"]) and np.array_equal(d, exp["d"]) and np.array_equal(ids, exp["ids"])
+    # recall-style agreement with the raw reference heap: same distance multiset wherever the
+    # int8 tables agree exactly with the reference's
+    for q in range(g["queries"].shape[0]):
+        if np.array_equal(exp["qtables"][q], g["ref_qtables"][q]):
+            real = g["ref_heap_vals"][q] < 127
+            if len(np.unique(g["ref_heap_keys"][q][real])) == real.sum():
+                assert np.array_equal(np.sort(d[q]), np.sort(g["ref_heap_vals"][q]))
+    ix.close()
+
+
+@pytest.mark.parametrize("n,m,dim,nq,r,keep", [(200000, 16, 128, 33, 100, 0.01), (150000, 32, 96, 17, 100, 0.01)])
+def test_search_flat_medium(qadc, oracle, n, m, dim, nq, r, keep):
+    rng = np.random.default_rng(n + m)
+    cb = synth.make_pq(rng, dim, m)
+    codes = synth.make_codes(rng, n, m)
+    q = synth.make_queries(rng, nq, dim)
+    ix = flat_index(qadc, dim, m, cb, codes, keep)
+    ids, d, cnt = ix.search(q, 1, r)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=keep, offsets=np.array([0, n], np.int64)),
+                        q, 1, r, want_tables=False)
+    assert np.array_equal(cnt, exp["count"]) and np.array_equal(d, exp["d"]) and np.array_equal(ids, exp["ids"])
+    ix.close()
+
+
+def test_search_reports_bound_error(qadc):
+    """Prefix smaller than r -> QADC_EBOUND, the reference's 'Max quantization bound too high' exit."""
+    rng = np.random.default_rng(5)
+    ix = flat_index(qadc, 128, 16, synth.make_pq(rng, 128, 16), synth.make_codes(rng, 500, 16), 0.01)
+    with pytest.raises(qadc.QadcError) as e:
+        ix.search(synth.make_queries(rng, 2, 128), 1, 10)
+    assert e.value.code == qadc.QADC_EBOUND
+    ix.close()
+
+
+def test_argument_errors(qadc):
+    rng = np.random.default_rng(5)
+    ix = qadc.Index(0)
+    with pytest.raises(qadc.QadcError):
+        ix.set_pq(128, 8, synth.make_pq(rng, 128, 8))          # (8,4) unsupported, db_query_4.cpp:32-34
+    with pytest.raises(qadc.QadcError):
+        ix.set_pq(128, 16, synth.make_pq(rng, 128, 16), bits=8)   # sq_bits must be 4, :396-400
+    ix.set_pq(128, 16, synth.make_pq(rng, 128, 16))
+    with pytest.raises(qadc.QadcError):
+        ix.search(synth.make_queries(rng, 1, 128), 1, 10)      # no database yet
+    ix.load_flat(synth.make_codes(rng, 1000, 16), 0.5)
+    with pytest.raises(qadc.QadcError):
+        ix.search(synth.make_queries(rng, 1, 128), 2, 10)      # flat needs ma = 1
+    ix.close()
+
+
+# ---- sharded flat database on one GPU: N "virtual" shards + merge == unsharded ---------------
+@pytest.mark.parametrize("G", [2, 3, 8])
+def test_virtual_shards_merge_equals_single(qadc, oracle, G):
+    import torch
+    rng = np.random.default_rng(G)
+    dim, m, n, nq, r, keep = 128, 16, 100000, 9, 100, 0.01
+    cb = synth.make_pq(rng, dim, m)
+    codes = synth.make_codes(rng, n, m)
+    q = synth.make_queries(rng, nq, dim)
+    single = flat_index(qadc, dim, m, cb, codes, keep)
+    s_ids, s_d, s_cnt = single.search(q, 1, r)
+    single.close()
+    from qadc_b200 import sharding
+    prefix = codes[:sharding.start_size(n, keep)]
+    dq = torch.from_numpy(q).cuda()
+    keys = torch.empty((G, nq, r), dtype=torch.int64, device="cuda")
+    ids = torch.empty((G, nq, r), dtype=torch.int32, device="cuda")
+    for g in range(G):
+        lo, hi = sharding.flat_shard_range(n, g, G)
+        ix = qadc.Index(0)
+        ix.set_pq(dim, m, cb)
+        ix.begin_database([hi - lo], False)
+        ix.upload_codes(0, 0, codes[lo:hi])
+        ix.set_position_base(0, lo)
+        ix.set_prefix(0, prefix)
+        ix.finalize(keep)
+        d_tmp = torch.empty((nq, r), dtype=torch.int8, device="cuda")
+        c_tmp = torch.empty(nq, dtype=torch.int32, device="cuda")
+        ix.search_device(dq.data_ptr(), nq, 1, r, ids[g].data_ptr(), d_tmp.data_ptr(), c_tmp.data_ptr(), keys[g].data_ptr())
+        ix.synchronize()
+        ix.close()
+    mi = qadc.Index(0)
+    o_ids = torch.empty((nq, r), dtype=torch.int32, device="cuda")
+    o_d = torch.empty((nq, r), dtype=torch.int8, device="cuda")
+    o_c = torch.empty(nq, dtype=torch.int32, device="cuda")
+    mi.merge_shards_device(keys.data_ptr(), ids.data_ptr(), G, nq, r, o_ids.data_ptr(), o_d.data_ptr(), o_c.data_ptr())
+    mi.synchronize()
+    assert np.array_equal(o_ids.cpu().numpy().view(np.uint32), s_ids)
+    assert np.array_equal(o_d.cpu().numpy(), s_d)
+    assert np.array_equal(o_c.cpu().numpy(), s_cnt)
+    mi.close()
