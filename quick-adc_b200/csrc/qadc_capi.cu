@@ -55,7 +55,7 @@ struct qadc_ctx {
     uint32_t max_start = 0;
     // scratch
     DevBuf staging, b_queries, b_assign, b_tables, b_tmin, b_qmax, b_qmin, b_qtables, b_lists, b_plists, b_ids,
-        b_dists, b_counts, b_keys, b_dump;
+        b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound;
     int* d_err = nullptr;
     int* h_err = nullptr;   // pinned
     // options / accounting
@@ -134,12 +134,12 @@ __global__ void extract_prefix_kernel(const uint8_t* __restrict__ native, const 
 }
 
 // ---- flat scan dispatch ---------------------------------------------------------------------
-template <int M, int QB, int G, int NW, int NS>
+template <int M, int QB, int NW, int NS>
 int launch_flat(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
-    using Cfg = FlatCfg<M, QB, G, NW, NS>;
+    using Cfg = FlatCfg<M, QB, NW, NS>;
     const size_t smem = Cfg::smem_bytes(a.cap);
     if (smem > kMaxSmem) return QADC_ENOMEM;
-    auto kern = scan_flat_kernel<M, QB, G, NW, NS>;
+    auto kern = scan_flat_kernel<M, QB, NW, NS>;
     QCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     dim3 grid(chunks, (a.nq + QB - 1) / QB);
     kern<<<grid, Cfg::kThreads, smem, ctx->stream>>>(a);
@@ -148,32 +148,34 @@ int launch_flat(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
     return QADC_OK;
 }
 
-struct FlatPlan { int qb, g, chunks, cap; uint32_t sb_per_chunk; };
+struct FlatPlan { int qb, nw, chunks, cap; uint32_t sb_per_chunk; };
 
-// Chooses queries-per-pass, tile shape and chunk count for the flat scan.
+size_t flat_smem(int M, int qb, int nw, int cap) {
+    if (M == 16) {
+        if (qb == 1) return nw == 16 ? FlatCfg<16, 1, 16, 4>::smem_bytes(cap) : FlatCfg<16, 1, 8, 4>::smem_bytes(cap);
+        return qb == 2 ? FlatCfg<16, 2, 8, 4>::smem_bytes(cap) : FlatCfg<16, 4, 8, 4>::smem_bytes(cap);
+    }
+    return qb == 1 ? FlatCfg<32, 1, 8, 4>::smem_bytes(cap) : FlatCfg<32, 2, 8, 4>::smem_bytes(cap);
+}
+
+// Chooses queries-per-pass, warps per CTA and chunk count for the flat scan.
 int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     const int M = ctx->m;
     int qb = static_cast<int>(ctx->opt_flat_qb);
     if (qb <= 0) qb = (nq >= 4) ? ((M == 16) ? 4 : 2) : ((nq >= 2) ? 2 : 1);
     if (M == 32 && qb > 2) qb = 2;
     if (qb > 4) qb = 4;
+    if (qb == 3) qb = 2;
     while (qb > nq && qb > 1) qb >>= 1;
-    bool found = false;
-    for (; qb >= 1 && !found; qb >>= 1) {
-        for (int g = (M == 16 && qb == 1) ? 2 : 1; g >= 1 && !found; --g) {
-            const int cap = next_pow2(r + g * kSbVec);
-            size_t smem;
-            if (M == 16)
-                smem = qb == 1 ? (g == 2 ? FlatCfg<16, 1, 2, kNW, 4>::smem_bytes(cap) : FlatCfg<16, 1, 1, kNW, 4>::smem_bytes(cap))
-                               : (qb == 2 ? FlatCfg<16, 2, 1, kNW, 4>::smem_bytes(cap) : FlatCfg<16, 4, 1, kNW, 4>::smem_bytes(cap));
-            else
-                smem = qb == 1 ? FlatCfg<32, 1, 1, kNW, 4>::smem_bytes(cap) : FlatCfg<32, 2, 1, kNW, 4>::smem_bytes(cap);
-            if (smem <= kMaxSmem) { pl.qb = qb; pl.g = g; pl.cap = cap; found = true; }
-        }
-    }
-    if (!found) return fail(ctx, QADC_EINVAL, "r too large for the scan kernel's shared-memory lists");
+    const int cap = next_pow2(r + kSbVec);
+    while (qb > 1 && flat_smem(M, qb, 8, cap) > kMaxSmem) qb >>= 1;
+    int nw = (M == 16 && qb == 1) ? 16 : 8;
+    if (flat_smem(M, qb, nw, cap) > kMaxSmem) nw = 8;
+    if (flat_smem(M, qb, nw, cap) > kMaxSmem)
+        return fail(ctx, QADC_EINVAL, "r too large for the scan kernel's shared-memory lists");
+    pl.qb = qb; pl.cap = cap; pl.nw = nw;
     const uint32_t n_sb = static_cast<uint32_t>(ctx->total_sb);
-    const int tile_sb = kNW * pl.g;
+    const int tile_sb = pl.nw;
     const int qgroups = (nq + pl.qb - 1) / pl.qb;
     long chunks = ctx->opt_flat_chunks;
     if (chunks <= 0) chunks = std::max(1, (2 * ctx->sm_count + qgroups - 1) / qgroups);
@@ -184,6 +186,27 @@ int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     pl.sb_per_chunk = std::max<uint32_t>(spc, tile_sb);
     pl.chunks = static_cast<int>((n_sb + pl.sb_per_chunk - 1) / pl.sb_per_chunk);
     if (pl.chunks < 1) pl.chunks = 1;
+    return QADC_OK;
+}
+
+// Seeds the per-query shared bound from the keep-prefixes (prefix_hist + prefix_bound kernels).
+int seed_shared_bound(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables, int nq, int ma, int r) {
+    ENSURE(ctx->b_hist, static_cast<size_t>(nq) * 128 * 4);
+    ENSURE(ctx->b_sbound, static_cast<size_t>(nq) * 4);
+    QCK(cudaMemsetAsync(ctx->b_hist.p, 0, static_cast<size_t>(nq) * 128 * 4, ctx->stream));
+    PrefixBoundArgs pa;
+    pa.starts = ctx->d_starts; pa.start_off = ctx->d_start_off; pa.start_size = ctx->d_start_size;
+    pa.assign = d_assign; pa.qtabs = d_qtables; pa.ma = ma;
+    pa.nsplit = (ctx->K == 0) ? static_cast<int>(std::min<uint32_t>(64, std::max<uint32_t>(1, ctx->max_start / 8192))) : 1;
+    pa.hist = ctx->b_hist.as<unsigned int>();
+    dim3 grid(pa.nsplit, nq);
+    if (ctx->m == 16) prefix_hist_kernel<16><<<grid, 256, 0, ctx->stream>>>(pa);
+    else prefix_hist_kernel<32><<<grid, 256, 0, ctx->stream>>>(pa);
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    prefix_bound_kernel<<<nq, 128, 0, ctx->stream>>>(pa.hist, r, ctx->b_sbound.as<int>());
+    ctx->launches++;
+    QCK(cudaGetLastError());
     return QADC_OK;
 }
 
@@ -200,25 +223,29 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
     const int M = ctx->m;
     const bool flat = (ctx->K == 0);
     int n_lists = 0;
+    const PipeK pk{1u, 0xffffffffu};
+    int rc = seed_shared_bound(ctx, d_assign, d_qtables, nq, ma, r);
+    if (rc) return rc;
     if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0, ctx->stream));
     if (flat) {
         FlatPlan pl;
-        int rc = plan_flat(ctx, nq, r, pl);
+        rc = plan_flat(ctx, nq, r, pl);
         if (rc) return rc;
-        n_lists = pl.chunks * kNW;
+        n_lists = pl.chunks * pl.nw;
         ENSURE(ctx->b_lists, static_cast<size_t>(nq) * n_lists * r * 8);
         FlatScanArgs a;
         a.codes = ctx->d_codes; a.n_sb = static_cast<uint32_t>(ctx->total_sb); a.size = ctx->h_size[0];
         a.pos_base = ctx->h_pos_base[0]; a.sb_per_chunk = pl.sb_per_chunk; a.qtabs = d_qtables; a.nq = nq;
         a.r = r; a.cap = pl.cap; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
+        a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk;
         if (M == 16) {
-            if (pl.qb == 1 && pl.g == 2) rc = launch_flat<16, 1, 2, kNW, 4>(ctx, a, pl.chunks);
-            else if (pl.qb == 1) rc = launch_flat<16, 1, 1, kNW, 4>(ctx, a, pl.chunks);
-            else if (pl.qb == 2) rc = launch_flat<16, 2, 1, kNW, 4>(ctx, a, pl.chunks);
-            else rc = launch_flat<16, 4, 1, kNW, 4>(ctx, a, pl.chunks);
+            if (pl.qb == 1 && pl.nw == 16) rc = launch_flat<16, 1, 16, 4>(ctx, a, pl.chunks);
+            else if (pl.qb == 1) rc = launch_flat<16, 1, 8, 4>(ctx, a, pl.chunks);
+            else if (pl.qb == 2) rc = launch_flat<16, 2, 8, 4>(ctx, a, pl.chunks);
+            else rc = launch_flat<16, 4, 8, 4>(ctx, a, pl.chunks);
         } else {
-            if (pl.qb == 1) rc = launch_flat<32, 1, 1, kNW, 4>(ctx, a, pl.chunks);
-            else rc = launch_flat<32, 2, 1, kNW, 4>(ctx, a, pl.chunks);
+            if (pl.qb == 1) rc = launch_flat<32, 1, 8, 4>(ctx, a, pl.chunks);
+            else rc = launch_flat<32, 2, 8, 4>(ctx, a, pl.chunks);
         }
         if (rc) return rc == QADC_ENOMEM ? fail(ctx, rc, "scan kernel shared memory exceeds 227 KB") : rc;
     } else {
@@ -234,6 +261,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         a.codes = ctx->d_codes; a.part_sb_off = ctx->d_sb_off; a.part_size = ctx->d_size;
         a.part_pos_base = ctx->d_pos_base; a.assign = d_assign; a.qtabs = d_qtables; a.nq = nq; a.ma = ma;
         a.r = r; a.cap = cap; a.probes_per_chunk = ppc; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
+        a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk;
         dim3 grid(chunks, nq);
         if (M == 16) {
             QCK(cudaFuncSetAttribute(scan_ivf_kernel<16, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -376,7 +404,7 @@ void qadc_destroy(qadc_ctx* c) {
     cudaFree(c->d_codebooks); cudaFree(c->d_rotation); cudaFree(c->d_centroids);
     for (DevBuf* b : {&c->staging, &c->b_queries, &c->b_assign, &c->b_tables, &c->b_tmin, &c->b_qmax, &c->b_qmin,
                       &c->b_qtables, &c->b_lists, &c->b_plists, &c->b_ids, &c->b_dists, &c->b_counts, &c->b_keys,
-                      &c->b_dump})
+                      &c->b_dump, &c->b_hist, &c->b_sbound})
         cudaFree(b->p);
     cudaFree(c->d_err);
     cudaFreeHost(c->h_err);
@@ -717,8 +745,8 @@ int qadc_dump_distances(qadc_ctx* ctx, int part_i, const int8_t* qtable, int8_t*
     QCK(cudaMemcpyAsync(d_t, qtable, M * 16, cudaMemcpyHostToDevice, ctx->stream));
     const uint8_t* native = ctx->d_codes + ctx->h_sb_off[part_i] * sb_bytes(M);
     const uint32_t n_sb = (size + kSbVec - 1) / kSbVec;
-    if (M == 16) dump_distances_kernel<16><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o);
-    else dump_distances_kernel<32><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o);
+    if (M == 16) dump_distances_kernel<16><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o, PipeK{1u, 0xffffffffu});
+    else dump_distances_kernel<32><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o, PipeK{1u, 0xffffffffu});
     QCK(cudaGetLastError());
     QCK(cudaMemcpyAsync(out, d_o, size, cudaMemcpyDeviceToHost, ctx->stream));
     QCK(cudaStreamSynchronize(ctx->stream));

@@ -14,9 +14,9 @@
 // returns 0 for them:
 //   lo = prmt(T0, T1, w)               -> T[idx] if idx < 8 else 0
 //   hi = prmt(T2, T3, w ^ 0x88888888)  -> T[idx] if idx >= 8 else 0
-// Two sub-quantisers are added in byte lanes (<= 254, no carry), widened to 16-bit lanes
-// and accumulated; the accumulators start at 0x8000 - bound so bit 15 of a lane is set iff
-// sum >= bound.  Signed saturation of the reference (vpaddsb on values in [0,127]) equals
+// Two sub-quantisers are added in byte lanes (<= 254, no carry), split into even/odd bytes
+// and accumulated in 16-bit lanes that start at 0x8000 - bound, so the top bit of a lane is
+// set iff sum >= bound.  Signed saturation of the reference (vpaddsb on values in [0,127]) equals
 // min(127, sum), and only sums < bound <= 127 are ever selected.
 #pragma once
 #include <cstdint>
@@ -84,39 +84,74 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
     return d;
 }
 
+// Accumulators of one group of 8 vectors.  Vector k of the group lives in a 16-bit lane:
+//   k=0: ea[15:0]   k=2: ea[31:16]   k=1: oa[23:8]   k=3: oa[39:24]
+//   k=4: eb[15:0]   k=6: eb[31:16]   k=5: ob[23:8]   k=7: ob[39:24]
+// Every lane starts at 0x8000 - bound, so its top bit is set iff sum >= bound.
+// The odd bytes of a pair sum stay where they are (o = p - e, bytes 1 and 3) and are
+// accumulated in 64 bits, which needs no shift at all.
+struct GroupAcc {
+    uint32_t ea, eb;
+    uint64_t oa, ob;
+};
+
+// `one` / `neg1` are the constants 1 and -1 passed as kernel arguments: the compiler cannot
+// fold them, so a*one+b is emitted as IMAD / IMAD.WIDE on the FMA pipe instead of competing
+// with PRMT/LOP3/SHF for the ALU pipe, which is what bounds this kernel.
+struct PipeK {
+    uint32_t one, neg1;
+};
+
+__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const PipeK& k) { return a * k.one + b; }
+
+__device__ __forceinline__ void acc_init(GroupAcc& g, uint32_t bound) {
+    const uint32_t lane = 0x8000u - bound;
+    g.ea = g.eb = lane * 0x00010001u;
+    g.oa = g.ob = (static_cast<uint64_t>(lane) << 8) | (static_cast<uint64_t>(lane) << 24);
+}
+
 // Two sub-quantisers (words w0,w1 with tables t0,t1) for the 8 vectors of a group.
-// acc[0]: vectors (0,2)  acc[1]: (1,3)  acc[2]: (4,6)  acc[3]: (5,7)   as 16-bit lanes.
-__device__ __forceinline__ void lut_pair(uint32_t w0, uint32_t w1, const uint4& t0, const uint4& t1,
-                                         uint32_t (&acc)[4]) {
+__device__ __forceinline__ void lut_pair(uint32_t w0, uint32_t w1, const uint4& t0, const uint4& t1, GroupAcc& g,
+                                         const PipeK& k) {
     const uint32_t x0 = w0 ^ 0x88888888u, x1 = w1 ^ 0x88888888u;
-    const uint32_t pa = prmt(t0.x, t0.y, w0) + prmt(t0.z, t0.w, x0) + prmt(t1.x, t1.y, w1) +
-                        prmt(t1.z, t1.w, x1);
-    const uint32_t pb = prmt(t0.x, t0.y, w0 >> 16) + prmt(t0.z, t0.w, x0 >> 16) +
-                        prmt(t1.x, t1.y, w1 >> 16) + prmt(t1.z, t1.w, x1 >> 16);
-    acc[0] += pa & 0x00ff00ffu;
-    acc[1] += (pa >> 8) & 0x00ff00ffu;
-    acc[2] += pb & 0x00ff00ffu;
-    acc[3] += (pb >> 8) & 0x00ff00ffu;
+    const uint32_t pa = fadd(fadd(prmt(t0.x, t0.y, w0), prmt(t0.z, t0.w, x0), k),
+                             fadd(prmt(t1.x, t1.y, w1), prmt(t1.z, t1.w, x1), k), k);
+    const uint32_t pb = fadd(fadd(prmt(t0.x, t0.y, w0 >> 16), prmt(t0.z, t0.w, x0 >> 16), k),
+                             fadd(prmt(t1.x, t1.y, w1 >> 16), prmt(t1.z, t1.w, x1 >> 16), k), k);
+    const uint32_t ea = pa & 0x00ff00ffu, eb = pb & 0x00ff00ffu;
+    g.ea = fadd(ea, g.ea, k);
+    g.eb = fadd(eb, g.eb, k);
+    g.oa = static_cast<uint64_t>(ea * k.neg1 + pa) * k.one + g.oa;   // IMAD, then IMAD.WIDE
+    g.ob = static_cast<uint64_t>(eb * k.neg1 + pb) * k.one + g.ob;
 }
 
 // One quad = 4 sub-quantisers.
-__device__ __forceinline__ void lut_quad(const uint4& w, const uint4 (&t)[4], uint32_t (&acc)[4]) {
-    lut_pair(w.x, w.y, t[0], t[1], acc);
-    lut_pair(w.z, w.w, t[2], t[3], acc);
+__device__ __forceinline__ void lut_quad(const uint4& w, const uint4 (&t)[4], GroupAcc& g, const PipeK& k) {
+    lut_pair(w.x, w.y, t[0], t[1], g, k);
+    lut_pair(w.z, w.w, t[2], t[3], g, k);
 }
 
-// accumulator start value for "pass iff sum < bound" (bound <= 127)
-__device__ __forceinline__ uint32_t acc_init(uint32_t bound) { return 0x80008000u - bound * 0x00010001u; }
 // true iff at least one of the 8 sums is < bound
-__device__ __forceinline__ bool any_below(const uint32_t (&acc)[4]) {
-    return (acc[0] & acc[1] & acc[2] & acc[3] & 0x80008000u) != 0x80008000u;
+__device__ __forceinline__ bool any_below(const GroupAcc& g) {
+    const uint32_t e = g.ea & g.eb & 0x80008000u;                                                   // bits 15, 31
+    const uint32_t o1 = static_cast<uint32_t>(g.oa) & static_cast<uint32_t>(g.ob) & 0x00800000u;     // bit 23
+    const uint32_t o3 = static_cast<uint32_t>(g.oa >> 32) & static_cast<uint32_t>(g.ob >> 32) & 0x80u;   // bit 39
+    return (e | o1 | o3) != 0x80808080u;
 }
-// sum of vector k (0..7) of the group, given the bound the accumulators were started with;
-// only meaningful while sum + 0x8000 - bound < 0x10000 (always: sum <= 127*32)
-__device__ __forceinline__ uint32_t lane_sum(const uint32_t (&acc)[4], int k, uint32_t bound) {
-    const uint32_t reg = acc[((k >> 2) << 1) | (k & 1)];
-    const uint32_t v = (reg >> (((k >> 1) & 1) * 16)) & 0xffffu;
-    return v + bound - 0x8000u;
+// raw 16-bit lane of vector k (0..7)
+__device__ __forceinline__ uint32_t lane_raw(const GroupAcc& g, int k) {
+    const uint32_t e = (k & 4) ? g.eb : g.ea;
+    const uint64_t o = (k & 4) ? g.ob : g.oa;
+    switch (k & 3) {
+        case 0: return e & 0xffffu;
+        case 2: return e >> 16;
+        case 1: return static_cast<uint32_t>(o >> 8) & 0xffffu;
+        default: return static_cast<uint32_t>(o >> 24) & 0xffffu;
+    }
+}
+// sum of vector k given the bound the accumulators were started with (sum <= 127*32)
+__device__ __forceinline__ uint32_t lane_sum(const GroupAcc& g, int k, uint32_t bound) {
+    return lane_raw(g, k) + bound - 0x8000u;
 }
 
 // ---- bounded candidate lists: bitonic sort of u64 keys in shared memory ------------------
@@ -176,22 +211,32 @@ struct BlockSync {
 struct WarpList {
     uint64_t* keys;  // cap entries, unused slots hold kEmptyKey
     int* count;      // entries in use
-    int* bound;      // pass iff d < *bound
+    int* bound;      // strict local bound: pass iff d < *bound
 
     __device__ __forceinline__ void push(uint64_t key) {
         const int i = atomicAdd(count, 1);
         keys[i] = key;
     }
-    // Keep the r smallest. All 32 lanes call it.
-    __device__ __forceinline__ void compact(int cap, int r, int lane) {
+    // Keep the r smallest (sorted). All 32 lanes call it. Only the occupied power-of-two prefix is
+    // sorted.  When the list is full its r-th distance is also published to the query's shared
+    // bound (any vector farther than it can no longer be in the top r of the whole scan).
+    __device__ __forceinline__ void compact(int cap, int r, int lane, int* shared_bound) {
         __syncwarp();
-        bitonic_sort_u64(keys, cap, lane, 32, WarpSync());
-        const int n = min(*count, r);
+        const int cnt = *count;
+        int n_sort = 32;
+        while (n_sort < cnt) n_sort <<= 1;
+        n_sort = min(n_sort, cap);
+        bitonic_sort_u64(keys, n_sort, lane, 32, WarpSync());
+        const int n = min(cnt, r);
         __syncwarp();
-        for (int i = r + lane; i < cap; i += 32) keys[i] = kEmptyKey;
+        for (int i = r + lane; i < n_sort; i += 32) keys[i] = kEmptyKey;
         if (lane == 0) {
             *count = n;
-            *bound = (n == r) ? static_cast<int>(keys[r - 1] >> 48) : 127;
+            if (n == r) {
+                const int d = static_cast<int>(keys[r - 1] >> 48);
+                *bound = d;
+                if (shared_bound) atomicMin(shared_bound, d);
+            }
         }
         __syncwarp();
     }

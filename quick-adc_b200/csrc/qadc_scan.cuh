@@ -67,13 +67,11 @@ __global__ void __launch_bounds__(256) untranspose_codes_kernel(const uint8_t* _
 // ------------------------------------------------------------------------------------------
 // Append every vector of a group whose sum is below the bound.  pos0 = position of vector
 // k=0 inside the (local) partition.
-__device__ __forceinline__ void emit_candidates(const uint32_t (&acc)[4], uint32_t bound, uint32_t pos0,
-                                                uint32_t size, uint32_t pos_base, uint32_t probe_rank,
-                                                WarpList& list) {
+__device__ __forceinline__ void emit_candidates(const GroupAcc& g, uint32_t bound, uint32_t pos0, uint32_t size,
+                                                uint32_t pos_base, uint32_t probe_rank, WarpList& list) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const uint32_t reg = acc[((k >> 2) << 1) | (k & 1)];
-        const uint32_t v = (reg >> (((k >> 1) & 1) * 16)) & 0xffffu;
+        const uint32_t v = lane_raw(g, k);
         if (!(v & 0x8000u) && pos0 + k < size) list.push(make_key(v + bound - 0x8000u, probe_rank, pos_base + pos0 + k));
     }
 }
@@ -83,11 +81,16 @@ __device__ __forceinline__ void store_list(const WarpList& list, uint64_t* dst, 
     for (int i = lane; i < r; i += 32) dst[i] = list.keys[i];
 }
 
+// The query's shared bound: the smallest distance v for which some list already holds r records
+// with d <= v (seeded from the keep-prefix by prefix_bound kernels).  A vector can only be in
+// the top r if d <= v.  Read with a volatile load so every tile sees recent updates.
+__device__ __forceinline__ int load_shared_bound(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
 // ------------------------------------------------------------------------------------------
 // Flat scan: grid = (chunks along the database, query groups of QB).  NW consumer warps +
-// one producer warp per CTA; the producer streams tiles of NW*G superblocks through an
-// NS-stage shared-memory ring with TMA bulk copies; consumer warp w owns superblocks
-// [w*G, w*G+G) of every tile.  Each warp keeps one candidate list per query.
+// one producer warp per CTA; the producer streams tiles of NW superblocks through an NS-stage
+// shared-memory ring with TMA bulk copies; consumer warp w owns superblock w of every tile.
+// Each warp keeps one candidate list per query.
 // ------------------------------------------------------------------------------------------
 struct FlatScanArgs {
     const uint8_t* codes;   // native layout of the partition
@@ -99,14 +102,15 @@ struct FlatScanArgs {
     int nq, r, cap;
     uint64_t* lists;        // [nq][n_lists][r]
     int n_lists;            // gridDim.x * NW
+    int* shared_bound;      // [nq]
+    PipeK k;                // {1, -1}
 };
 
-template <int M, int QB, int G, int NW, int NS>
+template <int M, int QB, int NW, int NS>
 struct FlatCfg {
     static constexpr int kQuads = M / 4;
     static constexpr int kSbBytes = M * 128;
-    static constexpr int kTileSb = NW * G;
-    static constexpr int kTileBytes = kTileSb * kSbBytes;
+    static constexpr int kTileBytes = NW * kSbBytes;
     static constexpr bool kRegTab = (QB == 1 && M == 16);
     static constexpr int kThreads = (NW + 1) * 32;
     static size_t smem_bytes(int cap) {
@@ -115,9 +119,9 @@ struct FlatCfg {
     }
 };
 
-template <int M, int QB, int G, int NW, int NS>
+template <int M, int QB, int NW, int NS>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatScanArgs a) {
-    using Cfg = FlatCfg<M, QB, G, NW, NS>;
+    using Cfg = FlatCfg<M, QB, NW, NS>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* tiles = smem;
     uint4* qtab = reinterpret_cast<uint4*>(tiles + static_cast<size_t>(NS) * Cfg::kTileBytes);   // [QB][M]
@@ -130,9 +134,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sb0 = min(blockIdx.x * a.sb_per_chunk, a.n_sb);
     const uint32_t sb1 = min(sb0 + a.sb_per_chunk, a.n_sb);
-    const uint32_t n_tiles = (sb1 - sb0 + Cfg::kTileSb - 1) / Cfg::kTileSb;
+    const uint32_t n_tiles = (sb1 - sb0 + NW - 1) / NW;
     const int qbase = blockIdx.y * QB;
     const int nqb = min(QB, a.nq - qbase);
+    const PipeK pk = a.k;
 
     // ---- init ----
     if (threadIdx.x == 0) {
@@ -154,8 +159,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const int s = t % NS;
                 if (t >= NS) mbar_wait(&empty[s], ((t / NS) & 1) ^ 1);
-                const uint32_t tsb = sb0 + t * Cfg::kTileSb;
-                const uint32_t bytes = min(static_cast<uint32_t>(Cfg::kTileSb), sb1 - tsb) * Cfg::kSbBytes;
+                const uint32_t tsb = sb0 + t * NW;
+                const uint32_t bytes = min(static_cast<uint32_t>(NW), sb1 - tsb) * Cfg::kSbBytes;
                 mbar_arrive_expect_tx(&full[s], bytes);
                 bulk_g2s(tiles + static_cast<size_t>(s) * Cfg::kTileBytes,
                          a.codes + static_cast<size_t>(tsb) * Cfg::kSbBytes, bytes, &full[s]);
@@ -177,55 +182,57 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 #pragma unroll
         for (int j = 0; j < M; ++j) treg[j] = qtab[j];
     }
+    const int compact_at = min(a.cap - kSbVec, 2 * a.r);
 
     for (uint32_t t = 0; t < n_tiles; ++t) {
         const int s = t % NS;
+        int gb[QB];
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) gb[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
         mbar_wait(&full[s], (t / NS) & 1);
-        const uint8_t* tile = tiles + static_cast<size_t>(s) * Cfg::kTileBytes;
-        const uint32_t tsb = sb0 + t * Cfg::kTileSb + warp * G;   // first superblock of this warp
+        const uint32_t sb = sb0 + t * NW + warp;   // this warp's superblock
+        const uint8_t* src = tiles + static_cast<size_t>(s) * Cfg::kTileBytes + static_cast<size_t>(warp) * Cfg::kSbBytes +
+                             lane * 16;
+        if (sb < sb1) {
+            uint4 w[Cfg::kQuads];
 #pragma unroll
-        for (int qi = 0; qi < QB; ++qi) {
-            if (qi < nqb) {
-                const uint32_t bound = *wl[qi].bound;
-                uint32_t acc[G][4];
+            for (int q = 0; q < Cfg::kQuads; ++q) w[q] = *reinterpret_cast<const uint4*>(src + q * 512);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);   // the words are in registers: release the stage early
 #pragma unroll
-                for (int g = 0; g < G; ++g)
+            for (int qi = 0; qi < QB; ++qi) {
+                if (qi < nqb) {
+                    const uint32_t bound = static_cast<uint32_t>(min(*wl[qi].bound, gb[qi] + 1));
+                    GroupAcc g;
+                    acc_init(g, bound);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[g][i] = acc_init(bound);
+                    for (int q = 0; q < Cfg::kQuads; ++q) {
+                        uint4 tq[4];
 #pragma unroll
-                for (int q = 0; q < Cfg::kQuads; ++q) {
-                    uint4 tq[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if constexpr (Cfg::kRegTab) tq[i] = treg[4 * q + i];
-                        else tq[i] = qtab[qi * M + 4 * q + i];
+                        for (int i = 0; i < 4; ++i) {
+                            if constexpr (Cfg::kRegTab) tq[i] = treg[4 * q + i];
+                            else tq[i] = qtab[qi * M + 4 * q + i];
+                        }
+                        lut_quad(w[q], tq, g, pk);
                     }
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const uint4 w = *reinterpret_cast<const uint4*>(
-                            tile + static_cast<size_t>(warp * G + g) * Cfg::kSbBytes + q * 512 + lane * 16);
-                        lut_quad(w, tq, acc[g]);
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    if (tsb + g < sb1 && any_below(acc[g]))
-                        emit_candidates(acc[g], bound, (tsb + g) * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi]);
+                    if (any_below(g)) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi]);
                 }
             }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+            __syncwarp();
 #pragma unroll
-        for (int qi = 0; qi < QB; ++qi)
-            if (qi < nqb && *wl[qi].count > a.cap - G * kSbVec) wl[qi].compact(a.cap, a.r, lane);
+            for (int qi = 0; qi < QB; ++qi)
+                if (qi < nqb && *wl[qi].count >= compact_at) wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
     }
 
     // ---- final: sort and publish one list per (warp, query) ----
 #pragma unroll
     for (int qi = 0; qi < QB; ++qi) {
         if (qi < nqb) {
-            wl[qi].compact(a.cap, a.r, lane);
+            wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
             store_list(wl[qi],
                        a.lists + (static_cast<size_t>(qbase + qi) * a.n_lists + blockIdx.x * NW + warp) * a.r,
                        a.r, lane);
@@ -248,6 +255,8 @@ struct IvfScanArgs {
     int nq, ma, r, cap, probes_per_chunk;
     uint64_t* lists;                 // [nq][n_lists][r]
     int n_lists;                     // gridDim.x * NW
+    int* shared_bound;               // [nq]
+    PipeK k;
 };
 
 template <int M, int NW>
@@ -260,11 +269,14 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.y;
     const int a0 = blockIdx.x * a.probes_per_chunk, a1 = min(a0 + a.probes_per_chunk, a.ma);
+    const PipeK pk = a.k;
 
     WarpList wl{lists + static_cast<size_t>(warp) * a.cap, cnt + warp, bnd + warp};
     for (int i = lane; i < a.cap; i += 32) wl.keys[i] = kEmptyKey;
     if (lane == 0) { *wl.count = 0; *wl.bound = 127; }
     __syncwarp();
+    const int compact_at = min(a.cap - kSbVec, 2 * a.r);
+    int* sbound = a.shared_bound + q;
 
     for (int ar = a0 + warp; ar < a1; ar += NW) {
         const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
@@ -278,8 +290,9 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
         const uint8_t* base = a.codes + a.part_sb_off[p] * kSbBytes;
         const uint32_t n_sb = (size + kSbVec - 1) / kSbVec;
         for (uint32_t sb = 0; sb < n_sb; ++sb) {
-            const uint32_t bound = *wl.bound;
-            uint32_t acc[4] = {acc_init(bound), acc_init(bound), acc_init(bound), acc_init(bound)};
+            const uint32_t bound = static_cast<uint32_t>(min(*wl.bound, load_shared_bound(sbound) + 1));
+            GroupAcc g;
+            acc_init(g, bound);
             const uint4* src = reinterpret_cast<const uint4*>(base + static_cast<size_t>(sb) * kSbBytes) + lane;
             uint4 w[kQuads];
 #pragma unroll
@@ -287,15 +300,80 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
 #pragma unroll
             for (int qd = 0; qd < kQuads; ++qd) {
                 const uint4 tq[4] = {treg[4 * qd], treg[4 * qd + 1], treg[4 * qd + 2], treg[4 * qd + 3]};
-                lut_quad(w[qd], tq, acc);
+                lut_quad(w[qd], tq, g, pk);
             }
-            if (any_below(acc)) emit_candidates(acc, bound, sb * kSbVec + lane * 8, size, pos_base, ar, wl);
+            if (any_below(g)) emit_candidates(g, bound, sb * kSbVec + lane * 8, size, pos_base, ar, wl);
             __syncwarp();
-            if (*wl.count > a.cap - kSbVec) wl.compact(a.cap, a.r, lane);
+            if (*wl.count >= compact_at) wl.compact(a.cap, a.r, lane, sbound);
         }
     }
-    wl.compact(a.cap, a.r, lane);
+    wl.compact(a.cap, a.r, lane, sbound);
     store_list(wl, a.lists + (static_cast<size_t>(q) * a.n_lists + blockIdx.x * NW + warp) * a.r, a.r, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-bound seed: the r-th smallest int8 distance among the keep-prefixes of the probed
+// partitions.  Those prefix vectors are part of the scanned database, so at least r scanned
+// vectors have d <= seed and nothing farther can reach the top r.  Two tiny kernels:
+// a 128-bin histogram per query (grid = (splits, queries)) and its scan (grid = queries).
+// ------------------------------------------------------------------------------------------
+struct PrefixBoundArgs {
+    const uint8_t* starts;
+    const uint64_t* start_off;
+    const uint32_t* start_size;
+    const int32_t* assign;     // [nq][ma]
+    const int8_t* qtabs;       // [nq][ma][M*16]
+    int ma, nsplit;
+    unsigned int* hist;        // [nq][128], zeroed
+};
+
+template <int M>
+__global__ void __launch_bounds__(256) prefix_hist_kernel(const PrefixBoundArgs a) {
+    constexpr int CS = M / 2;
+    __shared__ unsigned int hist[128];
+    __shared__ int8_t tab[M * 16];
+    const int split = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+    if (tid < 128) hist[tid] = 0;
+    for (int ar = 0; ar < a.ma; ++ar) {
+        const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
+        const uint32_t n = a.start_size[p];
+        const uint32_t v0 = static_cast<uint32_t>(static_cast<uint64_t>(n) * split / a.nsplit);
+        const uint32_t v1 = static_cast<uint32_t>(static_cast<uint64_t>(n) * (split + 1) / a.nsplit);
+        if (v1 == v0) continue;
+        __syncthreads();
+        for (int i = tid; i < M * 16; i += 256) tab[i] = a.qtabs[(static_cast<size_t>(q) * a.ma + ar) * M * 16 + i];
+        __syncthreads();
+        const uint8_t* codes = a.starts + a.start_off[p] * CS;
+        for (uint32_t v = v0 + tid; v < v1; v += 256) {
+            const uint8_t* c = codes + static_cast<size_t>(v) * CS;
+            int sum = 0;
+#pragma unroll
+            for (int b = 0; b < CS; ++b) {
+                const uint32_t byte = c[b];
+                sum += tab[(2 * b) * 16 + (byte & 15u)] + tab[(2 * b + 1) * 16 + (byte >> 4)];
+            }
+            atomicAdd(&hist[min(sum, 127)], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < 127 && hist[tid]) atomicAdd(&a.hist[static_cast<size_t>(q) * 128 + tid], hist[tid]);
+}
+
+__global__ void __launch_bounds__(128) prefix_bound_kernel(const unsigned int* __restrict__ hist, int r,
+                                                          int* __restrict__ shared_bound) {
+    __shared__ unsigned int h[128];
+    const int q = blockIdx.x;
+    h[threadIdx.x] = hist[static_cast<size_t>(q) * 128 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int cum = 0;
+        int b = 126;   // fewer than r prefix vectors below 127: everything below 127 may pass
+        for (int d = 0; d < 127; ++d) {
+            cum += h[d];
+            if (cum >= static_cast<unsigned int>(r)) { b = d; break; }
+        }
+        shared_bound[q] = b;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -305,23 +383,24 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
 template <int M>
 __global__ void __launch_bounds__(256) dump_distances_kernel(const uint8_t* __restrict__ native, uint32_t size,
                                                              const int8_t* __restrict__ qtab,
-                                                             int8_t* __restrict__ out) {
+                                                             int8_t* __restrict__ out, const PipeK pk) {
     constexpr int kQuads = M / 4, kSbBytes = M * 128;
     const uint32_t sb = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
     if (static_cast<uint64_t>(sb) * kSbVec >= size) return;
-    uint32_t acc[4] = {acc_init(0), acc_init(0), acc_init(0), acc_init(0)};
+    GroupAcc g;
+    acc_init(g, 0);
     const uint4* src = reinterpret_cast<const uint4*>(native + static_cast<size_t>(sb) * kSbBytes) + lane;
     const uint4* t = reinterpret_cast<const uint4*>(qtab);
 #pragma unroll
     for (int qd = 0; qd < kQuads; ++qd) {
         const uint4 tq[4] = {__ldg(t + 4 * qd), __ldg(t + 4 * qd + 1), __ldg(t + 4 * qd + 2), __ldg(t + 4 * qd + 3)};
-        lut_quad(__ldg(src + qd * 32), tq, acc);
+        lut_quad(__ldg(src + qd * 32), tq, g, pk);
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t pos = sb * kSbVec + lane * 8 + k;
-        if (pos < size) out[pos] = static_cast<int8_t>(min(127u, lane_sum(acc, k, 0)));
+        if (pos < size) out[pos] = static_cast<int8_t>(min(127u, lane_sum(g, k, 0)));
     }
 }
 

@@ -228,7 +228,8 @@ def test_table_pipeline_vs_oracle_and_reference(qadc, oracle, name):
     else:
         assert rel_err(out["tables"][:, 0], g["ref_tables_direct"], 1e-30) <= FLOAT_RTOL
     assert np.all(np.abs(out["qmax"] - g["ref_qmax"]) <= FLOAT_RTOL * g["ref_qmax"])
-    assert np.all(np.abs(out["qmin"] - g["ref_qmin"]) <= FLOAT_RTOL * np.maximum(g["ref_qmin"], 1e-3))
+    # qmin is a minimum over BLAS-form entries on the reference side: same norm-scaled tolerance
+    assert np.all(np.abs(out["qmin"] - g["ref_qmin"]) <= FLOAT_RTOL * float(g["ref_tables_used"].max()))
     lsb = np.abs(out["qtables"].astype(int) - g["ref_qtables"].astype(int))
     assert lsb.max() <= 1 and (lsb != 0).mean() <= 0.02
     ix.close()
