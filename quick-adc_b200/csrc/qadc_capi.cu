@@ -178,7 +178,8 @@ int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     const int tile_sb = pl.nw;
     const int qgroups = (nq + pl.qb - 1) / pl.qb;
     long chunks = ctx->opt_flat_chunks;
-    if (chunks <= 0) chunks = std::max(1, (2 * ctx->sm_count + qgroups - 1) / qgroups);
+    // ~16 waves of CTAs: the tail of the last wave costs at most a few percent
+    if (chunks <= 0) chunks = std::max(1, (16 * ctx->sm_count + qgroups - 1) / qgroups);
     const long max_chunks = std::max<long>(1, (n_sb + tile_sb - 1) / tile_sb);
     chunks = std::min(chunks, max_chunks);
     uint32_t spc = static_cast<uint32_t>((n_sb + chunks - 1) / chunks);

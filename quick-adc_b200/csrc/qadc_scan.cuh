@@ -184,11 +184,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
     }
     const int compact_at = min(a.cap - kSbVec, 2 * a.r);
 
+    // shared bounds are prefetched one tile ahead (a stale bound is only more permissive)
+    int gb[QB];
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) gb[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
+
     for (uint32_t t = 0; t < n_tiles; ++t) {
         const int s = t % NS;
-        int gb[QB];
-#pragma unroll
-        for (int qi = 0; qi < QB; ++qi) gb[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
         mbar_wait(&full[s], (t / NS) & 1);
         const uint32_t sb = sb0 + t * NW + warp;   // this warp's superblock
         const uint8_t* src = tiles + static_cast<size_t>(s) * Cfg::kTileBytes + static_cast<size_t>(warp) * Cfg::kSbBytes +
@@ -197,6 +199,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
             uint4 w[Cfg::kQuads];
 #pragma unroll
             for (int q = 0; q < Cfg::kQuads; ++q) w[q] = *reinterpret_cast<const uint4*>(src + q * 512);
+            int gb_next[QB];
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) gb_next[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);   // the words are in registers: release the stage early
 #pragma unroll
@@ -220,8 +225,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
             }
             __syncwarp();
 #pragma unroll
-            for (int qi = 0; qi < QB; ++qi)
+            for (int qi = 0; qi < QB; ++qi) {
                 if (qi < nqb && *wl[qi].count >= compact_at) wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
+                gb[qi] = gb_next[qi];
+            }
         } else {
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
