@@ -152,7 +152,7 @@ struct FlatPlan { int qb, nw, chunks, cap; uint32_t sb_per_chunk; };
 
 size_t flat_smem(int M, int qb, int nw, int cap) {
     if (M == 16) {
-        if (qb == 1) return nw == 16 ? FlatCfg<16, 1, 16, 4>::smem_bytes(cap) : FlatCfg<16, 1, 8, 4>::smem_bytes(cap);
+        if (qb == 1) return nw == 15 ? FlatCfg<16, 1, 15, 4>::smem_bytes(cap) : FlatCfg<16, 1, 8, 4>::smem_bytes(cap);
         return qb == 2 ? FlatCfg<16, 2, 8, 4>::smem_bytes(cap) : FlatCfg<16, 4, 8, 4>::smem_bytes(cap);
     }
     return qb == 1 ? FlatCfg<32, 1, 8, 4>::smem_bytes(cap) : FlatCfg<32, 2, 8, 4>::smem_bytes(cap);
@@ -169,7 +169,7 @@ int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     while (qb > nq && qb > 1) qb >>= 1;
     const int cap = next_pow2(r + kSbVec);
     while (qb > 1 && flat_smem(M, qb, 8, cap) > kMaxSmem) qb >>= 1;
-    int nw = (M == 16 && qb == 1) ? 16 : 8;
+    int nw = (M == 16 && qb == 1) ? 15 : 8;
     if (flat_smem(M, qb, nw, cap) > kMaxSmem) nw = 8;
     if (flat_smem(M, qb, nw, cap) > kMaxSmem)
         return fail(ctx, QADC_EINVAL, "r too large for the scan kernel's shared-memory lists");
@@ -240,7 +240,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         a.r = r; a.cap = pl.cap; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
         a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk;
         if (M == 16) {
-            if (pl.qb == 1 && pl.nw == 16) rc = launch_flat<16, 1, 16, 4>(ctx, a, pl.chunks);
+            if (pl.qb == 1 && pl.nw == 15) rc = launch_flat<16, 1, 15, 4>(ctx, a, pl.chunks);
             else if (pl.qb == 1) rc = launch_flat<16, 1, 8, 4>(ctx, a, pl.chunks);
             else if (pl.qb == 2) rc = launch_flat<16, 2, 8, 4>(ctx, a, pl.chunks);
             else rc = launch_flat<16, 4, 8, 4>(ctx, a, pl.chunks);

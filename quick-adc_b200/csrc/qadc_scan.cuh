@@ -184,30 +184,38 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
     }
     const int compact_at = min(a.cap - kSbVec, 2 * a.r);
 
-    // shared bounds are prefetched one tile ahead (a stale bound is only more permissive)
-    int gb[QB];
+    // loop state kept in registers: this warp's superblock, its slot inside a stage, ring position
+    uint32_t sb = sb0 + warp;
+    uint32_t n_left = (sb < sb1) ? (sb1 - sb + NW - 1) / NW : 0;   // tiles in which this warp has a superblock
+    uint32_t slot = smem_u32(tiles) + warp * Cfg::kSbBytes + lane * 16;
+    uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
+    pin(slot); pin(full_a); pin(empty_a); pin(sb); pin(n_left);
+    uint32_t stage = 0, phase = 0;
+    int lbound[QB], gb[QB];   // strict local bound, shared bound (refreshed once per ring revolution)
 #pragma unroll
-    for (int qi = 0; qi < QB; ++qi) gb[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
+    for (int qi = 0; qi < QB; ++qi) {
+        lbound[qi] = 127;
+        gb[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
+    }
 
     for (uint32_t t = 0; t < n_tiles; ++t) {
-        const int s = t % NS;
-        mbar_wait(&full[s], (t / NS) & 1);
-        const uint32_t sb = sb0 + t * NW + warp;   // this warp's superblock
-        const uint8_t* src = tiles + static_cast<size_t>(s) * Cfg::kTileBytes + static_cast<size_t>(warp) * Cfg::kSbBytes +
-                             lane * 16;
-        if (sb < sb1) {
+        mbar_wait_a(full_a + stage * 8, phase);
+        if (t < n_left) {
+            const uint32_t src = slot + stage * Cfg::kTileBytes;
             uint4 w[Cfg::kQuads];
 #pragma unroll
-            for (int q = 0; q < Cfg::kQuads; ++q) w[q] = *reinterpret_cast<const uint4*>(src + q * 512);
+            for (int q = 0; q < Cfg::kQuads; ++q) w[q] = lds128(src + q * 512);
             int gb_next[QB];
+            if (stage == 0) {
 #pragma unroll
-            for (int qi = 0; qi < QB; ++qi) gb_next[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
+                for (int qi = 0; qi < QB; ++qi) gb_next[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
+            }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);   // the words are in registers: release the stage early
+            if (lane == 0) mbar_arrive_a(empty_a + stage * 8);   // the words are in registers: release the stage early
 #pragma unroll
             for (int qi = 0; qi < QB; ++qi) {
                 if (qi < nqb) {
-                    const uint32_t bound = static_cast<uint32_t>(min(*wl[qi].bound, gb[qi] + 1));
+                    const uint32_t bound = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
                     GroupAcc g;
                     acc_init(g, bound);
 #pragma unroll
@@ -220,19 +228,27 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
                         }
                         lut_quad(w[q], tq, g, pk);
                     }
-                    if (any_below(g)) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi]);
+                    const bool mine = any_below(g);
+                    if (__any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
+                        if (mine) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi]);
+                        __syncwarp();
+                        if (*wl[qi].count >= compact_at) {
+                            wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
+                            lbound[qi] = *wl[qi].bound;
+                        }
+                    }
                 }
             }
-            __syncwarp();
+            if (stage == 0) {
 #pragma unroll
-            for (int qi = 0; qi < QB; ++qi) {
-                if (qi < nqb && *wl[qi].count >= compact_at) wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
-                gb[qi] = gb_next[qi];
+                for (int qi = 0; qi < QB; ++qi) gb[qi] = gb_next[qi];
             }
         } else {
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) mbar_arrive_a(empty_a + stage * 8);
         }
+        sb += NW;
+        if (++stage == NS) { stage = 0; phase ^= 1; }
     }
 
     // ---- final: sort and publish one list per (warp, query) ----
