@@ -47,9 +47,10 @@ def load_library(build_if_missing=True):
         except Exception as e:  # a stale .so is still better than none; a missing one is fatal below
             if not os.path.exists(LIB_PATH):
                 raise RuntimeError(f"cannot build libqadc_b200.so: {e}")
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-    L = C.CDLL(LIB_PATH)
+    path = os.environ.get("QADC_LIB", LIB_PATH)   # development knob: an alternative build of the same library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(path)
     vp, i32, u32, f32 = C.c_void_p, C.c_int, C.c_uint32, C.c_float
     L.qadc_abi_version.restype = i32
     L.qadc_create.argtypes = [i32, vp, C.POINTER(vp)]

@@ -23,7 +23,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    extra = os.environ.get("QADC_NVCC_EXTRA", "").split()
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     subprocess.check_call(cmd)
     return OUT
 

@@ -96,6 +96,14 @@ int ensure(qadc_ctx* ctx, DevBuf& b, size_t bytes) {
         if (rc__) return rc__;                               \
     } while (0)
 
+PipeK make_pipek() {
+#ifdef QADC_CORE_PACKED
+    return PipeK{1u, 0xffffffffu};
+#else
+    return PipeK{1u, 0xffffffffu, 1u, 1u << 8, 1u << 16, 1u << 24};
+#endif
+}
+
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 void free_db(qadc_ctx* c) {
@@ -224,7 +232,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
     const int M = ctx->m;
     const bool flat = (ctx->K == 0);
     int n_lists = 0;
-    const PipeK pk{1u, 0xffffffffu};
+    const PipeK pk = make_pipek();
     int rc = seed_shared_bound(ctx, d_assign, d_qtables, nq, ma, r);
     if (rc) return rc;
     if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0, ctx->stream));
@@ -746,8 +754,8 @@ int qadc_dump_distances(qadc_ctx* ctx, int part_i, const int8_t* qtable, int8_t*
     QCK(cudaMemcpyAsync(d_t, qtable, M * 16, cudaMemcpyHostToDevice, ctx->stream));
     const uint8_t* native = ctx->d_codes + ctx->h_sb_off[part_i] * sb_bytes(M);
     const uint32_t n_sb = (size + kSbVec - 1) / kSbVec;
-    if (M == 16) dump_distances_kernel<16><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o, PipeK{1u, 0xffffffffu});
-    else dump_distances_kernel<32><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o, PipeK{1u, 0xffffffffu});
+    if (M == 16) dump_distances_kernel<16><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o, make_pipek());
+    else dump_distances_kernel<32><<<(n_sb + 7) / 8, 256, 0, ctx->stream>>>(native, size, d_t, d_o, make_pipek());
     QCK(cudaGetLastError());
     QCK(cudaMemcpyAsync(out, d_o, size, cudaMemcpyDeviceToHost, ctx->stream));
     QCK(cudaStreamSynchronize(ctx->stream));

@@ -108,6 +108,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
     return d;
 }
 
+#ifdef QADC_CORE_PACKED   // earlier variant, kept for A/B runs (-DQADC_CORE_PACKED)
 // Accumulators of one group of 8 vectors.  Vector k of the group lives in a 16-bit lane:
 //   k=0: ea[15:0]   k=2: ea[31:16]   k=1: oa[23:8]   k=3: oa[39:24]
 //   k=4: eb[15:0]   k=6: eb[31:16]   k=5: ob[23:8]   k=7: ob[39:24]
@@ -177,6 +178,44 @@ __device__ __forceinline__ uint32_t lane_raw(const GroupAcc& g, int k) {
 __device__ __forceinline__ uint32_t lane_sum(const GroupAcc& g, int k, uint32_t bound) {
     return lane_raw(g, k) + bound - 0x8000u;
 }
+
+#else
+// Variant: one 32-bit accumulator per vector, fed with IDP.4A (dot product with a one-hot byte
+// selector) so that neither the even/odd split nor the final test needs ALU-pipe masks.
+struct GroupAcc {
+    uint32_t v[8];   // sum - bound (negative <=> candidate)
+};
+struct PipeK {
+    uint32_t one, neg1, s0, s1, s2, s3;   // 1, -1, and the byte selectors 1, 1<<8, 1<<16, 1<<24
+};
+__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const PipeK& k) { return a * k.one + b; }
+__device__ __forceinline__ void acc_init(GroupAcc& g, uint32_t bound) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g.v[i] = 0u - bound;
+}
+__device__ __forceinline__ void lut_pair(uint32_t w0, uint32_t w1, const uint4& t0, const uint4& t1, GroupAcc& g,
+                                         const PipeK& k) {
+    const uint32_t x0 = w0 ^ 0x88888888u, x1 = w1 ^ 0x88888888u;
+    const uint32_t pa = fadd(fadd(prmt(t0.x, t0.y, w0), prmt(t0.z, t0.w, x0), k),
+                             fadd(prmt(t1.x, t1.y, w1), prmt(t1.z, t1.w, x1), k), k);
+    const uint32_t pb = fadd(fadd(prmt(t0.x, t0.y, w0 >> 16), prmt(t0.z, t0.w, x0 >> 16), k),
+                             fadd(prmt(t1.x, t1.y, w1 >> 16), prmt(t1.z, t1.w, x1 >> 16), k), k);
+    g.v[0] = __dp4a(pa, k.s0, g.v[0]); g.v[1] = __dp4a(pa, k.s1, g.v[1]);
+    g.v[2] = __dp4a(pa, k.s2, g.v[2]); g.v[3] = __dp4a(pa, k.s3, g.v[3]);
+    g.v[4] = __dp4a(pb, k.s0, g.v[4]); g.v[5] = __dp4a(pb, k.s1, g.v[5]);
+    g.v[6] = __dp4a(pb, k.s2, g.v[6]); g.v[7] = __dp4a(pb, k.s3, g.v[7]);
+}
+__device__ __forceinline__ void lut_quad(const uint4& w, const uint4 (&t)[4], GroupAcc& g, const PipeK& k) {
+    lut_pair(w.x, w.y, t[0], t[1], g, k);
+    lut_pair(w.z, w.w, t[2], t[3], g, k);
+}
+__device__ __forceinline__ bool any_below(const GroupAcc& g) {
+    return static_cast<int>(g.v[0] | g.v[1] | g.v[2] | g.v[3] | g.v[4] | g.v[5] | g.v[6] | g.v[7]) < 0;
+}
+// 16-bit "raw lane" compatible with the packed variant: bit 15 set <=> sum >= bound
+__device__ __forceinline__ uint32_t lane_raw(const GroupAcc& g, int k) { return (g.v[k] + 0x8000u) & 0xffffu; }
+__device__ __forceinline__ uint32_t lane_sum(const GroupAcc& g, int k, uint32_t bound) { return g.v[k] + bound; }
+#endif
 
 // ---- bounded candidate lists: bitonic sort of u64 keys in shared memory ------------------
 // Sorts n (power of two) keys ascending with the threads [0, nthreads) of a group that
