@@ -298,7 +298,12 @@ def run_ours(args):
         step_device()
         scan_ms.append(ix.last_scan_ms())   # CUDA events on the launching stream around the scan kernel
 
+    prof = os.environ.get("QADC_PROFILE_RANGE") == "1"   # ncu --profile-from-start off: only the timed steps
+    if prof:
+        torch.cuda.profiler.start()
     ms_step = timed(step_device_timed, args.steps)
+    if prof:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
     n_launch = launches[0]
     for _ in range(2):

@@ -25,6 +25,9 @@ struct DevBuf {
 
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kNW = 8;
+#ifndef QADC_NS1
+#define QADC_NS1 4   // ring stages of the single-query 16x4 flat kernel
+#endif
 
 }  // namespace
 
@@ -160,7 +163,7 @@ struct FlatPlan { int qb, nw, chunks, cap; uint32_t sb_per_chunk; };
 
 size_t flat_smem(int M, int qb, int nw, int cap) {
     if (M == 16) {
-        if (qb == 1) return nw == 15 ? FlatCfg<16, 1, 15, 4>::smem_bytes(cap) : FlatCfg<16, 1, 8, 4>::smem_bytes(cap);
+        if (qb == 1) return nw == 15 ? FlatCfg<16, 1, 15, QADC_NS1>::smem_bytes(cap) : FlatCfg<16, 1, 8, 4>::smem_bytes(cap);
         return qb == 2 ? FlatCfg<16, 2, 8, 4>::smem_bytes(cap) : FlatCfg<16, 4, 8, 4>::smem_bytes(cap);
     }
     return qb == 1 ? FlatCfg<32, 1, 8, 4>::smem_bytes(cap) : FlatCfg<32, 2, 8, 4>::smem_bytes(cap);
@@ -248,7 +251,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         a.r = r; a.cap = pl.cap; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
         a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk;
         if (M == 16) {
-            if (pl.qb == 1 && pl.nw == 15) rc = launch_flat<16, 1, 15, 4>(ctx, a, pl.chunks);
+            if (pl.qb == 1 && pl.nw == 15) rc = launch_flat<16, 1, 15, QADC_NS1>(ctx, a, pl.chunks);
             else if (pl.qb == 1) rc = launch_flat<16, 1, 8, 4>(ctx, a, pl.chunks);
             else if (pl.qb == 2) rc = launch_flat<16, 2, 8, 4>(ctx, a, pl.chunks);
             else rc = launch_flat<16, 4, 8, 4>(ctx, a, pl.chunks);

@@ -188,6 +188,15 @@ struct GroupAcc {
 struct PipeK {
     uint32_t one, neg1, s0, s1, s2, s3;   // 1, -1, and the byte selectors 1, 1<<8, 1<<16, 1<<24
 };
+// selector of vectors 4..7 = upper half of the word.  With QADC_SHIFT_FMA the shift is a
+// multiply-high by 2^16 (s2) on the FMA pipe instead of SHF on the ALU pipe.
+__device__ __forceinline__ uint32_t hi16(uint32_t w, const PipeK& k) {
+#ifdef QADC_SHIFT_FMA
+    return __umulhi(w, k.s2);
+#else
+    return w >> 16;
+#endif
+}
 __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const PipeK& k) { return a * k.one + b; }
 __device__ __forceinline__ void acc_init(GroupAcc& g, uint32_t bound) {
 #pragma unroll
@@ -198,8 +207,8 @@ __device__ __forceinline__ void lut_pair(uint32_t w0, uint32_t w1, const uint4& 
     const uint32_t x0 = w0 ^ 0x88888888u, x1 = w1 ^ 0x88888888u;
     const uint32_t pa = fadd(fadd(prmt(t0.x, t0.y, w0), prmt(t0.z, t0.w, x0), k),
                              fadd(prmt(t1.x, t1.y, w1), prmt(t1.z, t1.w, x1), k), k);
-    const uint32_t pb = fadd(fadd(prmt(t0.x, t0.y, w0 >> 16), prmt(t0.z, t0.w, x0 >> 16), k),
-                             fadd(prmt(t1.x, t1.y, w1 >> 16), prmt(t1.z, t1.w, x1 >> 16), k), k);
+    const uint32_t pb = fadd(fadd(prmt(t0.x, t0.y, hi16(w0, k)), prmt(t0.z, t0.w, hi16(x0, k)), k),
+                             fadd(prmt(t1.x, t1.y, hi16(w1, k)), prmt(t1.z, t1.w, hi16(x1, k)), k), k);
     g.v[0] = __dp4a(pa, k.s0, g.v[0]); g.v[1] = __dp4a(pa, k.s1, g.v[1]);
     g.v[2] = __dp4a(pa, k.s2, g.v[2]); g.v[3] = __dp4a(pa, k.s3, g.v[3]);
     g.v[4] = __dp4a(pb, k.s0, g.v[4]); g.v[5] = __dp4a(pb, k.s1, g.v[5]);

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (raw + source pages) into a short text report. Usage: tools_ncu_summary.py rep [out.txt]"""
+"""Summarise an .ncu-rep (raw + source pages) into a short text report. Usage: tools/ncu_summary.py rep [out.txt]"""
 import csv, subprocess, sys, io
 from collections import Counter
 rep = sys.argv[1]
