@@ -1,0 +1,109 @@
+"""The C++ host mirror (quick-adc_b200/host): the reference's db_query_4 command line on top of
+the C ABI.  CPU: it builds, links the library and rejects bad input like the reference does.
+GPU: its results equal the oracle's canonical results and its CSV has the reference's columns."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "quick-adc_b200", "host")
+CLI = os.path.join(HOST, "db_query_4")
+
+
+@pytest.fixture(scope="module")
+def cli(qadc):
+    qadc.load_library()
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    return CLI
+
+
+def test_cli_builds_and_prints_usage(cli):
+    p = subprocess.run([cli], capture_output=True, text=True)
+    assert p.returncode == 1 and "Usage: db_query_4 [-r R] [-m MA] [-k KEEP_PERCENT] [-b BATCH_SIZE]" in p.stderr
+
+
+def test_cli_rejects_non_database(cli, tmp_path):
+    f = tmp_path / "x.qdb"
+    f.write_bytes(b"not a database at all, just bytes" * 4)
+    p = subprocess.run([cli, str(f), str(f), str(f)], capture_output=True, text=True)
+    assert p.returncode == 1 and "not a .qdb database" in p.stderr
+
+
+def test_pq_data_round_trip(qadc, tmp_path):
+    """.pq.data/.opq.data in the reference's format (quantizers.cpp:27-46)."""
+    from qadc_b200 import dbfile
+    import struct
+    rng = np.random.default_rng(0)
+    cb = synth.make_pq(rng, 64, 16)
+    rot = rng.standard_normal((64, 64)).astype(np.float32)
+    path = tmp_path / "q.opq.data"
+    dbfile.write_pq_data(path, 64, 16, cb, rot)
+    raw = path.read_bytes()
+    assert struct.unpack("iii", raw[:12]) == (64, 16, 4)
+    assert len(raw) == 12 + 4 * (64 * 16 + 64 * 64)
+    assert np.array_equal(np.frombuffer(raw[12:12 + 4 * 64 * 16], np.float32), cb.reshape(-1))
+
+
+def run_cli(cli, tmp_path, db_kwargs, queries, gt, r, ma, keep_percent, batch):
+    from qadc_b200 import dbfile
+    dbfile.write_qdb(tmp_path / "db.qdb", **db_kwargs)
+    dbfile.write_vecs(tmp_path / "q.fvecs", queries)
+    dbfile.write_vecs(tmp_path / "gt.ivecs", gt)
+    out = tmp_path / "res.bin"
+    p = subprocess.run([cli, "-r", str(r), "-m", str(ma), "-k", str(keep_percent), "-b", str(batch), "-o", str(out),
+                        str(tmp_path / "db.qdb"), str(tmp_path / "q.fvecs"), str(tmp_path / "gt.ivecs")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    lines = p.stdout.strip().splitlines()
+    assert lines[0] == "r,recall,ma,adc_type,keep,index_us,rotate_us,table_us,scan_us"   # db_query_4.cpp:387
+    fields = lines[1].split(",")
+    raw = np.fromfile(out, np.uint8).reshape(queries.shape[0], r * 5)
+    ids = raw[:, :4 * r].copy().view(np.uint32)
+    d = raw[:, 4 * r:].view(np.int8)
+    return fields, ids, d
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [1, 7])
+def test_cli_flat_matches_oracle(cli, oracle, tmp_path, batch):
+    rng = np.random.default_rng(31)
+    dim, m, n, nq, r = 128, 16, 30000, 20, 50
+    cb = synth.make_pq(rng, dim, m)
+    codes = synth.make_codes(rng, n, m)
+    q = synth.make_queries(rng, nq, dim)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=np.float32(2 * 0.01), offsets=np.array([0, n], np.int64)),
+                        q, 1, r, want_tables=False)
+    gt = exp["ids"][:, :1].astype(np.int32).copy()
+    gt[::2] = n + 5   # half of the queries cannot be recalled
+    fields, ids, d = run_cli(cli, tmp_path, dict(dim=dim, m=m, codebooks=cb, codes=codes), q, gt, r, 1, 2, batch)
+    assert fields[0] == str(r) and fields[2] == "1" and fields[3] == "qadc"
+    assert abs(float(fields[1]) - 0.5) < 1e-9
+    assert np.array_equal(d, exp["d"])
+    # the CLI sorts by distance only (like kv_binheap::sort): compare ids as sets per distance
+    for qi in range(nq):
+        for v in np.unique(d[qi]):
+            assert set(ids[qi][d[qi] == v].tolist()) == set(exp["ids"][qi][exp["d"][qi] == v].tolist())
+
+
+@pytest.mark.gpu
+def test_cli_ivf_matches_oracle(cli, oracle, tmp_path):
+    rng = np.random.default_rng(32)
+    dim, m, n, K, ma, nq, r = 96, 32, 20000, 40, 6, 9, 30
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(7,))
+    q = synth.make_queries(rng, nq, dim)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels,
+                             keep=np.float32(5 * 0.01), offsets=offsets), q, ma, r, want_tables=False)
+    gt = exp["ids"][:, :1].astype(np.int32).copy()
+    fields, ids, d = run_cli(cli, tmp_path, dict(dim=dim, m=m, codebooks=cb, codes=codes, centroids=cents, labels=labels,
+                                                 offsets=offsets), q, gt, r, ma, 5, 4)
+    assert float(fields[1]) == 1.0 and fields[2] == str(ma)
+    assert np.array_equal(d, exp["d"])
+    for qi in range(nq):
+        for v in np.unique(d[qi]):
+            assert set(ids[qi][d[qi] == v].tolist()) == set(exp["ids"][qi][exp["d"][qi] == v].tolist())
