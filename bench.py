@@ -85,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50", "-i", str(self.dev)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -292,16 +292,13 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches[0] = 0
-    scan_ms = []
-
-    def step_device_timed():
-        step_device()
-        scan_ms.append(ix.last_scan_ms())   # CUDA events on the launching stream around the scan kernel
 
     prof = os.environ.get("QADC_PROFILE_RANGE") == "1"   # ncu --profile-from-start off: only the timed steps
     if prof:
         torch.cuda.profiler.start()
-    ms_step = timed(step_device_timed, args.steps)
+    ms_step = timed(step_device, args.steps)
+    # CUDA events recorded on the launching stream around every scan launch of the timed steps
+    scan_ms = ix.scan_ms_history(min(args.steps, 64))
     if prof:
         torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
@@ -318,6 +315,23 @@ def run_ours(args):
     achieved = passes * n_local * CODE_BYTES / t_scan / 1e9
     peak, peak_src = measured_peak_hbm()
 
+    verify = None
+    if world == 1 and args.verify:
+        # full-size cross-check outside the timed region: the scan result of `--verify` queries must equal
+        # the canonical rule evaluated (numpy) on the per-vector distances of an independent kernel
+        res_ids = d_ids.cpu().numpy().view(np.uint32); res_d = d_d.cpu().numpy(); res_c = d_cnt.cpu().numpy()
+        tabs = ix.build_tables(queries[:args.verify], 1, R)
+        okv = True
+        for s_ in range(args.verify):
+            dist = ix.dump_distances(0, tabs["qtables"][s_, 0])
+            thr = res_d[s_][res_c[s_] - 1] if res_c[s_] == R else 126
+            pos = np.nonzero(dist <= thr)[0]
+            order = np.lexsort((pos, dist[pos]))[:R]
+            okv = okv and np.array_equal(res_ids[s_][:len(order)], pos[order].astype(np.uint32)) \
+                and np.array_equal(res_d[s_][:len(order)], dist[pos[order]])
+            del dist
+        verify = {"queries": args.verify, "method": "canonical top-r recomputed from qadc_dump_distances", "ok": bool(okv)}
+
     if rank == 0:
         value = N * nq / (ms_step * 1e-3)
         line = {
@@ -329,6 +343,7 @@ def run_ours(args):
             "e2e": {"value": N * nq / (ms_e2e * 1e-3), "unit": "vectors/s", "h2d_bytes_per_step": int(queries.nbytes),
                     "d2h_bytes_per_step": int(nq * R * 5 + nq * 4), "ms_per_step": ms_e2e},
             "gpu_launches": n_launch,
+            "verify": verify,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "scan_flat_kernel",
@@ -355,13 +370,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-vectors", type=int, default=int(os.environ.get("QADC_BENCH_N", 10 ** 9)))
     ap.add_argument("--queries", type=int, default=16)
     ap.add_argument("--qb", type=int, default=1, help="queries per pass of the flat scan (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verify", type=int, default=2, help="queries cross-checked at full size after timing (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

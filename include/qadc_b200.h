@@ -126,6 +126,9 @@ int qadc_last_launch_count(const qadc_ctx* ctx);
 /* Device time in milliseconds of the scan kernel(s) of the last search call (CUDA events on
  * the context's stream around the scan launches; synchronises the stream). */
 int qadc_last_scan_ms(qadc_ctx* ctx, float* ms);
+/* Same for the last n search calls (oldest first, at most 64): no host synchronisation is
+ * needed inside a timed region.  Returns how many values were written, or a negative code. */
+int qadc_scan_ms_history(qadc_ctx* ctx, float* ms, int n);
 
 /* Merge the local top-r lists of G shards (device buffers laid out [G][nq][r], as an NCCL
  * all-gather leaves them) into the global top-r under the same total order. */

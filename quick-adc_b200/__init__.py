@@ -70,6 +70,8 @@ def load_library(build_if_missing=True):
     L.qadc_synchronize.argtypes = [vp]
     L.qadc_last_launch_count.argtypes = [vp]
     L.qadc_last_scan_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.qadc_scan_ms_history.argtypes = [vp, C.POINTER(C.c_float), i32]
+    L.qadc_scan_ms_history.restype = i32
     L.qadc_merge_shards_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.qadc_build_tables.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.qadc_scan_with_tables.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
@@ -218,6 +220,13 @@ class Index:
         ms = C.c_float()
         self._ck(self.lib.qadc_last_scan_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def scan_ms_history(self, n):
+        buf = (C.c_float * n)()
+        got = self.lib.qadc_scan_ms_history(self.h, buf, n)
+        if got < 0:
+            self._ck(got)
+        return [buf[i] for i in range(got)]
 
     def set_option(self, key, value):
         self._ck(self.lib.qadc_set_option(self.h, key.encode(), int(value)))

@@ -25,6 +25,9 @@ struct DevBuf {
 
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kNW = 8;
+#ifndef QADC_NW1
+#define QADC_NW1 15  // consumer warps of the single-query 16x4 flat kernel
+#endif
 #ifndef QADC_NS1
 #define QADC_NS1 4   // ring stages of the single-query 16x4 flat kernel
 #endif
@@ -65,7 +68,9 @@ struct qadc_ctx {
     long opt_flat_qb = 0, opt_flat_chunks = 0;
     int launches = 0;
     cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_scan0 = nullptr, ev_scan1 = nullptr;
+    static constexpr int kScanRing = 64;
+    cudaEvent_t ev_scan0[kScanRing] = {}, ev_scan1[kScanRing] = {};   // ring: one pair per search call
+    long scan_seq = 0;
     bool scan_timed = false;
 };
 
@@ -163,7 +168,7 @@ struct FlatPlan { int qb, nw, chunks, cap; uint32_t sb_per_chunk; };
 
 size_t flat_smem(int M, int qb, int nw, int cap) {
     if (M == 16) {
-        if (qb == 1) return nw == 15 ? FlatCfg<16, 1, 15, QADC_NS1>::smem_bytes(cap) : FlatCfg<16, 1, 8, 4>::smem_bytes(cap);
+        if (qb == 1) return nw == QADC_NW1 ? FlatCfg<16, 1, QADC_NW1, QADC_NS1>::smem_bytes(cap) : FlatCfg<16, 1, 8, 4>::smem_bytes(cap);
         return qb == 2 ? FlatCfg<16, 2, 8, 4>::smem_bytes(cap) : FlatCfg<16, 4, 8, 4>::smem_bytes(cap);
     }
     return qb == 1 ? FlatCfg<32, 1, 8, 4>::smem_bytes(cap) : FlatCfg<32, 2, 8, 4>::smem_bytes(cap);
@@ -180,7 +185,7 @@ int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     while (qb > nq && qb > 1) qb >>= 1;
     const int cap = next_pow2(r + kSbVec);
     while (qb > 1 && flat_smem(M, qb, 8, cap) > kMaxSmem) qb >>= 1;
-    int nw = (M == 16 && qb == 1) ? 15 : 8;
+    int nw = (M == 16 && qb == 1) ? QADC_NW1 : 8;
     if (flat_smem(M, qb, nw, cap) > kMaxSmem) nw = 8;
     if (flat_smem(M, qb, nw, cap) > kMaxSmem)
         return fail(ctx, QADC_EINVAL, "r too large for the scan kernel's shared-memory lists");
@@ -238,7 +243,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
     const PipeK pk = make_pipek();
     int rc = seed_shared_bound(ctx, d_assign, d_qtables, nq, ma, r);
     if (rc) return rc;
-    if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0, ctx->stream));
+    if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0[ctx->scan_seq % qadc_ctx::kScanRing], ctx->stream));
     if (flat) {
         FlatPlan pl;
         rc = plan_flat(ctx, nq, r, pl);
@@ -251,7 +256,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         a.r = r; a.cap = pl.cap; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
         a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk;
         if (M == 16) {
-            if (pl.qb == 1 && pl.nw == 15) rc = launch_flat<16, 1, 15, QADC_NS1>(ctx, a, pl.chunks);
+            if (pl.qb == 1 && pl.nw == QADC_NW1) rc = launch_flat<16, 1, QADC_NW1, QADC_NS1>(ctx, a, pl.chunks);
             else if (pl.qb == 1) rc = launch_flat<16, 1, 8, 4>(ctx, a, pl.chunks);
             else if (pl.qb == 2) rc = launch_flat<16, 2, 8, 4>(ctx, a, pl.chunks);
             else rc = launch_flat<16, 4, 8, 4>(ctx, a, pl.chunks);
@@ -287,7 +292,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         ctx->launches++;
         QCK(cudaGetLastError());
     }
-    if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan1, ctx->stream));
+    if (ctx->scan_timed) { QCK(cudaEventRecord(ctx->ev_scan1[ctx->scan_seq % qadc_ctx::kScanRing], ctx->stream)); ctx->scan_seq++; }
     MergeArgs mg{};
     mg.in_keys = ctx->b_lists.as<uint64_t>(); mg.in_ids = nullptr; mg.L = n_lists; mg.r = r; mg.nq = nq;
     mg.shard_major = 0; mg.out_keys = d_keys; mg.out_ids = d_ids; mg.out_dists = d_dists; mg.out_counts = d_counts;
@@ -398,8 +403,8 @@ int qadc_create(int device, void* stream, qadc_ctx** out) {
     if (stream) c->stream = static_cast<cudaStream_t>(stream);
     else { QCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (auto& ev : c->ev) QCK(cudaEventCreate(&ev));
-    QCK(cudaEventCreate(&c->ev_scan0));
-    QCK(cudaEventCreate(&c->ev_scan1));
+    for (auto& ev : c->ev_scan0) QCK(cudaEventCreate(&ev));
+    for (auto& ev : c->ev_scan1) QCK(cudaEventCreate(&ev));
     QCK(cudaMalloc(&c->d_err, sizeof(int)));
     QCK(cudaMemset(c->d_err, 0, sizeof(int)));
     QCK(cudaMallocHost(&c->h_err, sizeof(int)));
@@ -421,7 +426,8 @@ void qadc_destroy(qadc_ctx* c) {
     cudaFree(c->d_err);
     cudaFreeHost(c->h_err);
     for (auto& ev : c->ev) cudaEventDestroy(ev);
-    cudaEventDestroy(c->ev_scan0); cudaEventDestroy(c->ev_scan1);
+    for (auto& ev : c->ev_scan0) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_scan1) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -671,12 +677,18 @@ int qadc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, uint
 
 int qadc_last_launch_count(const qadc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int qadc_last_scan_ms(qadc_ctx* ctx, float* ms) {
-    if (!ctx || !ms) return QADC_EINVAL;
+int qadc_last_scan_ms(qadc_ctx* ctx, float* ms) { return qadc_scan_ms_history(ctx, ms, 1) == 1 ? QADC_OK : QADC_ESTATE; }
+
+int qadc_scan_ms_history(qadc_ctx* ctx, float* ms, int n) {
+    if (!ctx || !ms || n <= 0) return QADC_EINVAL;
     if (!ctx->scan_timed) return fail(ctx, QADC_ESTATE, "enable with qadc_set_option(ctx, \"time_scan\", 1)");
     QCK(cudaStreamSynchronize(ctx->stream));
-    QCK(cudaEventElapsedTime(ms, ctx->ev_scan0, ctx->ev_scan1));
-    return QADC_OK;
+    const long have = std::min<long>(std::min<long>(n, ctx->scan_seq), qadc_ctx::kScanRing);
+    for (long i = 0; i < have; ++i) {
+        const long seq = ctx->scan_seq - have + i;
+        QCK(cudaEventElapsedTime(ms + i, ctx->ev_scan0[seq % qadc_ctx::kScanRing], ctx->ev_scan1[seq % qadc_ctx::kScanRing]));
+    }
+    return static_cast<int>(have);
 }
 
 int qadc_merge_shards_device(qadc_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_ids, int G, int nq, int r,

@@ -166,6 +166,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
                          a.codes + static_cast<size_t>(tsb) * Cfg::kSbBytes, bytes, &full[s]);
             }
         }
+#ifdef QADC_FINAL_SYNC
+        __syncthreads();
+#endif
         return;
     }
 
@@ -210,12 +213,18 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 #pragma unroll
                 for (int qi = 0; qi < QB; ++qi) gb_next[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
             }
+#ifndef QADC_LATE_RELEASE
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty_a + stage * 8);   // the words are in registers: release the stage early
+#endif
 #pragma unroll
             for (int qi = 0; qi < QB; ++qi) {
                 if (qi < nqb) {
+#ifdef QADC_NO_SHARED_BOUND
+                    const uint32_t bound = static_cast<uint32_t>(lbound[qi]);
+#else
                     const uint32_t bound = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
+#endif
                     GroupAcc g;
                     acc_init(g, bound);
 #pragma unroll
@@ -243,6 +252,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 #pragma unroll
                 for (int qi = 0; qi < QB; ++qi) gb[qi] = gb_next[qi];
             }
+#ifdef QADC_LATE_RELEASE
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(empty_a + stage * 8);
+#endif
         } else {
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty_a + stage * 8);
@@ -261,6 +274,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
                        a.r, lane);
         }
     }
+#ifdef QADC_FINAL_SYNC
+    __syncthreads();
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -481,10 +497,11 @@ __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(const MergeA
             }
         }
         __syncthreads();
-        if (count > kMergeCap - step || base + step >= total) {
+        const int c = count;
+        __syncthreads();   // every thread has read `count` before anyone pushes again (uniform decision)
+        if (c > kMergeCap - step || base + step >= total) {
             bitonic_sort_u64_u32(keys, vals, kMergeCap, tid, kMergeThreads, BlockSync());
-            const int n = min(count, a.r);
-            __syncthreads();
+            const int n = min(c, a.r);
             for (int i = a.r + tid; i < kMergeCap; i += kMergeThreads) keys[i] = kEmptyKey;
             if (tid == 0) { count = n; bound_key = (n == a.r) ? keys[a.r - 1] : kEmptyKey; }
             __syncthreads();

@@ -33,10 +33,11 @@ struct BlockTopK {
     // call after every round of <= kSelCap/2 pushes (all threads); force = last round
     __device__ __forceinline__ void maybe_compact(int k, int tid, bool force) {
         __syncthreads();
-        if (*count > kSelCap / 2 || force) {
+        const int c = *count;
+        __syncthreads();   // every thread has read the count before anyone pushes again (uniform decision)
+        if (c > kSelCap / 2 || force) {
             bitonic_sort_u64(keys, kSelCap, tid, kSelThreads, BlockSync());
-            const int n = min(*count, k);
-            __syncthreads();
+            const int n = min(c, k);
             for (int i = k + tid; i < kSelCap; i += kSelThreads) keys[i] = kEmptyKey;
             if (tid == 0) { *count = n; *bound_key = (n == k) ? keys[k - 1] : kEmptyKey; }
             __syncthreads();

@@ -378,3 +378,68 @@ def test_virtual_shards_merge_equals_single(qadc, oracle, G):
     assert np.array_equal(o_d.cpu().numpy(), s_d)
     assert np.array_equal(o_c.cpu().numpy(), s_cnt)
     mi.close()
+
+
+# ---- many queries / large databases: invariance properties ---------------------------------
+def test_many_queries_all_scan_variants_agree(qadc, oracle):
+    """Thousands of queries whose per-warp lists are all full (n_lists * r > one merge round):
+    every queries-per-pass variant and chunking returns the same result, repeatedly
+    (regression test for a racy count read in the merge kernel), spot-checked against the oracle."""
+    rng = np.random.default_rng(77)
+    n, dim, m, nq, r = 300000, 128, 16, 3000, 100
+    cb = synth.make_pq(rng, dim, m)
+    codes = synth.make_codes(rng, n, m)
+    q = synth.make_queries(rng, nq, dim)
+    ix = flat_index(qadc, dim, m, cb, codes, 0.01)
+    out = ix.build_tables(q, 1, r)
+    base = None
+    for qb, chunks in ((4, 0), (1, 0), (2, 0), (1, 3), (1, 0)):
+        ix.set_option("flat_qb", qb)
+        ix.set_option("flat_chunks", chunks)
+        ids, d, cnt = ix.scan_with_tables(out["assign"], out["qtables"], r)
+        if base is None:
+            base = (ids, d, cnt)
+            for s in (0, 1499, 2999):
+                e_ids, e_d, e_cnt, _ = oracle.scan_with_tables(codes, None, np.array([0, n], np.int64), out["assign"][s],
+                                                               out["qtables"][s], r)
+                assert np.array_equal(ids[s], e_ids) and np.array_equal(d[s], e_d) and cnt[s] == e_cnt
+        else:
+            assert np.array_equal(ids, base[0]) and np.array_equal(d, base[1]) and np.array_equal(cnt, base[2])
+    ix.close()
+
+
+def test_large_flat_planted_neighbours_and_dump_cross_check(qadc):
+    """2^26 vectors (512 MB of codes, several L2 sizes): (1) planted exact copies of the
+    query's own best code are returned first with the smallest distance; (2) the scan result
+    equals the canonical rule evaluated on the dump_distances output (an independent kernel and
+    an independent selection in numpy)."""
+    import torch
+    rng = np.random.default_rng(2026)
+    n, dim, m, nq, r = 1 << 26, 128, 16, 4, 100
+    cb = synth.make_pq(rng, dim, m)
+    q = synth.make_queries(rng, nq, dim)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    d_codes = torch.randint(0, 256, (n, m // 2), dtype=torch.uint8, device="cuda", generator=g)
+    # plant, for query 0, the code of its nearest centroids at a few known positions
+    best = np.array([np.argmin(((q[0, j * 8:(j + 1) * 8][None] - cb[j]) ** 2).sum(1)) for j in range(m)])
+    code = (best[0::2] | (best[1::2] << 4)).astype(np.uint8)
+    planted = np.array([5, 123456, 33554431, n - 1], np.int64)
+    d_codes[torch.from_numpy(planted).cuda()] = torch.from_numpy(code).cuda()
+    ix = qadc.Index(0)
+    ix.set_pq(dim, m, cb)
+    ix.begin_database([n], False)
+    ix.upload_codes_device(0, 0, n, d_codes.data_ptr())
+    ix.finalize(0.001)
+    del d_codes
+    ids, d, cnt = ix.search(q, 1, r)
+    assert np.array_equal(np.sort(ids[0][:4]), planted.astype(np.uint32)) and np.all(d[0][:4] == d[0][0])
+    assert np.all(d[0][4:] >= d[0][0])
+    out = ix.build_tables(q, 1, r)
+    for s in range(nq):
+        dist = ix.dump_distances(0, out["qtables"][s, 0])
+        thr = d[s][cnt[s] - 1] if cnt[s] == r else 126
+        pos = np.nonzero(dist <= thr)[0]
+        order = np.lexsort((pos, dist[pos]))[:r]
+        assert np.array_equal(ids[s][:len(order)], pos[order].astype(np.uint32))
+        assert np.array_equal(d[s][:len(order)], dist[pos[order]])
+    ix.close()

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Throughput of BASELINE.json configs 1-3 on one B200 (parity-test shapes, not bench lines), each with a
+spot check of a few queries against the oracle.  usage: tools/bench_configs.py [1] [2] [3]"""
+import os, sys, time, json
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import qadc_b200
+from oracle.pyoracle import Oracle
+
+oracle = Oracle()
+R = 100
+
+
+def run(name, ix, db, queries, ma, check=6, reps=3, qb=None):
+    nq = queries.shape[0]
+    if qb is not None:
+        ix.set_option("flat_qb", qb)
+    ids, d, cnt, met = ix.search(queries, ma, R, want_metrics=True)   # warm-up + result
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ids, d, cnt, met = ix.search(queries, ma, R, want_metrics=True)
+        ts.append(time.perf_counter() - t0)
+    t = min(ts)
+    sel = np.linspace(0, nq - 1, check).astype(int)
+    exp = oracle.search(db, queries[sel], ma, R, want_tables=False)
+    ok = bool(np.array_equal(ids[sel], exp["ids"]) and np.array_equal(d[sel], exp["d"]) and np.array_equal(cnt[sel], exp["count"]))
+    scanned = db["scanned_per_query"](exp["assign"]) if callable(db.get("scanned_per_query")) else db["scanned_per_query"]
+    out = dict(config=name, nq=nq, ma=ma, seconds=t, queries_per_s=nq / t, vectors_scanned_per_s=scanned * nq / t,
+               index_us=met.index_us, table_us=met.table_us, scan_us=met.scan_us, h2d_us=met.h2d_us, d2h_us=met.d2h_us,
+               launches=ix.last_launch_count(), oracle_spot_check=ok, qb=qb)
+    print(json.dumps(out), flush=True)
+
+
+def config1(nq=10000):
+    rng = np.random.default_rng(1235)
+    n, dim, m = 10 ** 6, 128, 16
+    cb = rng.standard_normal((m, 16, dim // m)).astype(np.float32)
+    codes = rng.integers(0, 256, (n, m // 2), dtype=np.uint8)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    ix = qadc_b200.Index(0); ix.set_pq(dim, m, cb); ix.load_flat(codes, 0.01)
+    db = dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=0.01, offsets=np.array([0, n], np.int64), scanned_per_query=n)
+    for qb in (1, 2, 4):
+        run("1: SIFT1M-shaped flat 16x4, 10k queries", ix, db, q, 1, qb=qb)
+    ix.close()
+
+
+def config2(nq=10000):
+    rng = np.random.default_rng(1236)
+    n, dim, m, K, ma = 10 ** 6, 128, 16, 4096, 64
+    cb = rng.standard_normal((m, 16, dim // m)).astype(np.float32)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    sizes = rng.multinomial(n, np.ones(K) / K)
+    offsets = np.zeros(K + 1, np.int64); offsets[1:] = np.cumsum(sizes)
+    labels = rng.permutation(n).astype(np.uint32)
+    codes = rng.integers(0, 256, (n, m // 2), dtype=np.uint8)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    ix = qadc_b200.Index(0); ix.set_pq(dim, m, cb); ix.set_coarse(cents); ix.load_ivf(codes, labels, offsets, 0.01)
+    db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=0.01, offsets=offsets,
+              scanned_per_query=float(ma * n / K))
+    run("2: SIFT1M-shaped IVF-4096 16x4, nprobe 64, 10k queries", ix, db, q, ma)
+    ix.close()
+
+
+def config3(nq=10000):
+    rng = np.random.default_rng(1237)
+    n, dim, m = 10 ** 7, 96, 32
+    cb = rng.standard_normal((m, 16, dim // m)).astype(np.float32)
+    codes = rng.integers(0, 256, (n, m // 2), dtype=np.uint8)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    ix = qadc_b200.Index(0); ix.set_pq(dim, m, cb); ix.load_flat(codes, 0.001)
+    db = dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=0.001, offsets=np.array([0, n], np.int64), scanned_per_query=n)
+    for qb in (1, 2):
+        run("3: Deep10M-shaped flat 32x4, 10k queries", ix, db, q, 1, check=3, qb=qb)
+    ix.close()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["1", "2", "3"]
+    for w in which:
+        {"1": config1, "2": config2, "3": config3}[w]()
