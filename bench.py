@@ -202,7 +202,9 @@ def run_ours(args):
     N, nq = args.n_vectors, args.queries
     cb, queries = make_quantizer_and_queries(nq)
 
-    stream = torch.cuda.current_stream(dev)
+    # one explicit stream for everything (library kernels, torch copies, NCCL, timing events)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     ix = qadc_b200.Index(local, stream.cuda_stream)
     ix.set_pq(DIM, M, cb)
     lo, hi = sharding.flat_shard_range(N, rank, world)

@@ -61,7 +61,7 @@ struct qadc_ctx {
     uint32_t max_start = 0;
     // scratch
     DevBuf staging, b_queries, b_assign, b_tables, b_tmin, b_qmax, b_qmin, b_qtables, b_lists, b_plists, b_ids,
-        b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound;
+        b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound, b_cdist;
     int* d_err = nullptr;
     int* h_err = nullptr;   // pinned
     // options / accounting
@@ -324,11 +324,20 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
     } else if (flat) {
         QCK(cudaMemsetAsync(d_assign, 0, nqa * 4, ctx->stream));
     } else {
-        const size_t smem = kSelCap * 8 + static_cast<size_t>(dim) * 4;
-        coarse_assign_kernel<<<nq, kSelThreads, smem, ctx->stream>>>(d_queries, dim, ctx->d_centroids, ctx->K, ma,
-                                                                   d_assign);
-        ctx->launches++;
-        QCK(cudaGetLastError());
+        // distances for chunks of queries (<= 1 GiB of floats at a time), then the per-query selection
+        const int chunk_q = std::max(1, static_cast<int>(std::min<size_t>(nq, (size_t(1) << 28) / ctx->K)));
+        ENSURE(ctx->b_cdist, static_cast<size_t>(chunk_q) * ctx->K * 4);
+        for (int q0 = 0; q0 < nq; q0 += chunk_q) {
+            const int n = std::min(chunk_q, nq - q0);
+            dim3 grid((n + kCoarseTQ - 1) / kCoarseTQ, (ctx->K + kCoarseTC - 1) / kCoarseTC);
+            coarse_dist_kernel<<<grid, 256, 0, ctx->stream>>>(d_queries + static_cast<size_t>(q0) * dim, n, dim,
+                                                              ctx->d_centroids, ctx->K, ctx->b_cdist.as<float>());
+            QCK(cudaGetLastError());
+            coarse_select_kernel<<<n, kSelThreads, 0, ctx->stream>>>(ctx->b_cdist.as<float>(), ctx->K, ma,
+                                                                    d_assign + static_cast<size_t>(q0) * ma);
+            QCK(cudaGetLastError());
+            ctx->launches += 2;
+        }
     }
     if (record_events) QCK(cudaEventRecord(ctx->ev[1], ctx->stream));
     // 2+3. residual, rotation, float tables
@@ -421,7 +430,7 @@ void qadc_destroy(qadc_ctx* c) {
     cudaFree(c->d_codebooks); cudaFree(c->d_rotation); cudaFree(c->d_centroids);
     for (DevBuf* b : {&c->staging, &c->b_queries, &c->b_assign, &c->b_tables, &c->b_tmin, &c->b_qmax, &c->b_qmin,
                       &c->b_qtables, &c->b_lists, &c->b_plists, &c->b_ids, &c->b_dists, &c->b_counts, &c->b_keys,
-                      &c->b_dump, &c->b_hist, &c->b_sbound})
+                      &c->b_dump, &c->b_hist, &c->b_sbound, &c->b_cdist})
         cudaFree(b->p);
     cudaFree(c->d_err);
     cudaFreeHost(c->h_err);

@@ -500,9 +500,11 @@ __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(const MergeA
         const int c = count;
         __syncthreads();   // every thread has read `count` before anyone pushes again (uniform decision)
         if (c > kMergeCap - step || base + step >= total) {
-            bitonic_sort_u64_u32(keys, vals, kMergeCap, tid, kMergeThreads, BlockSync());
+            int n_sort = 64;   // only the occupied power-of-two prefix needs sorting (the rest is empty)
+            while (n_sort < c) n_sort <<= 1;
+            bitonic_sort_u64_u32(keys, vals, n_sort, tid, kMergeThreads, BlockSync());
             const int n = min(c, a.r);
-            for (int i = a.r + tid; i < kMergeCap; i += kMergeThreads) keys[i] = kEmptyKey;
+            for (int i = a.r + tid; i < n_sort; i += kMergeThreads) keys[i] = kEmptyKey;
             if (tid == 0) { count = n; bound_key = (n == a.r) ? keys[a.r - 1] : kEmptyKey; }
             __syncthreads();
         }

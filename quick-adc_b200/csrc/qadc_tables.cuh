@@ -45,31 +45,66 @@ struct BlockTopK {
     }
 };
 
-// ---- coarse assignment: one CTA per query ----------------------------------------------
-// d(q,c) = sum_i fma(diff_i, diff_i, .) sequentially over the dimension; the ma smallest
-// under (d, c) ascending.  out_assign[q][a].
-__global__ void __launch_bounds__(kSelThreads) coarse_assign_kernel(const float* __restrict__ queries, int dim,
-                                                                    const float* __restrict__ centroids, int K,
-                                                                    int ma, int32_t* __restrict__ out_assign) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-    float* qv = reinterpret_cast<float*>(keys + kSelCap);
+// ---- coarse assignment ------------------------------------------------------------------------
+// d(q,c) = sum_i fma(diff_i, diff_i, .) sequentially over the dimension (the FIXED statement of
+// find_k_neighbors, neighbors.cpp:30-76 with the :64 stride bug removed); the ma smallest under
+// (d, c) ascending.  Two kernels: a shared-memory tiled distance kernel (32 queries x 64
+// centroids per CTA step, every (q,c) sum still strictly in dimension order, so results are
+// bit-identical to the oracle) and a per-query streaming selection.
+constexpr int kCoarseTQ = 32;   // queries per CTA
+constexpr int kCoarseTC = 64;   // centroids per tile
+constexpr int kCoarseTD = 32;   // dimensions per smem slab
+
+__global__ void __launch_bounds__(256) coarse_dist_kernel(const float* __restrict__ queries, int nq, int dim,
+                                                          const float* __restrict__ centroids, int K,
+                                                          float* __restrict__ dist) {   // [nq][K]
+    __shared__ float sq[kCoarseTQ][kCoarseTD + 1];
+    __shared__ float sc[kCoarseTC][kCoarseTD + 1];
+    const int tid = threadIdx.x;
+    const int tq = tid & 31;          // query inside the tile (lane)
+    const int tc0 = (tid >> 5) * 8;   // 8 centroids per thread, warp-uniform -> broadcast reads of sc
+    const int q0 = blockIdx.x * kCoarseTQ, c0 = blockIdx.y * kCoarseTC;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int d0 = 0; d0 < dim; d0 += kCoarseTD) {
+        const int dn = min(kCoarseTD, dim - d0);
+        __syncthreads();
+        for (int i = tid; i < kCoarseTQ * kCoarseTD; i += 256) {
+            const int r = i / kCoarseTD, c = i % kCoarseTD;
+            sq[r][c] = (q0 + r < nq && c < dn) ? queries[static_cast<size_t>(q0 + r) * dim + d0 + c] : 0.f;
+        }
+        for (int i = tid; i < kCoarseTC * kCoarseTD; i += 256) {
+            const int r = i / kCoarseTD, c = i % kCoarseTD;
+            sc[r][c] = (c0 + r < K && c < dn) ? __ldg(centroids + static_cast<size_t>(c0 + r) * dim + d0 + c) : 0.f;
+        }
+        __syncthreads();
+        for (int i = 0; i < dn; ++i) {
+            const float x = sq[tq][i];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float diff = __fsub_rn(x, sc[tc0 + k][i]);
+                acc[k] = __fmaf_rn(diff, diff, acc[k]);
+            }
+        }
+    }
+    if (q0 + tq < nq) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (c0 + tc0 + k < K) dist[static_cast<size_t>(q0 + tq) * K + c0 + tc0 + k] = acc[k];
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads) coarse_select_kernel(const float* __restrict__ dist, int K, int ma,
+                                                                    int32_t* __restrict__ out_assign) {
+    __shared__ uint64_t keys[kSelCap];
     __shared__ int count;
     __shared__ unsigned long long bound_key;
     const int q = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < dim; i += kSelThreads) qv[i] = queries[static_cast<size_t>(q) * dim + i];
+    const float* d = dist + static_cast<size_t>(q) * K;
     BlockTopK top{keys, &count, &bound_key};
     top.init(tid);
     for (int base = 0; base < K; base += kSelCap / 2) {
-        for (int c = base + tid; c < min(base + kSelCap / 2, K); c += kSelThreads) {
-            const float* cent = centroids + static_cast<size_t>(c) * dim;
-            float s = 0.f;
-            for (int i = 0; i < dim; ++i) {
-                const float diff = __fsub_rn(qv[i], __ldg(cent + i));
-                s = __fmaf_rn(diff, diff, s);
-            }
-            top.push((static_cast<uint64_t>(__float_as_uint(s)) << 32) | static_cast<uint32_t>(c));
-        }
+        for (int c = base + tid; c < min(base + kSelCap / 2, K); c += kSelThreads)
+            top.push((static_cast<uint64_t>(__float_as_uint(d[c])) << 32) | static_cast<uint32_t>(c));
         top.maybe_compact(ma, tid, base + kSelCap / 2 >= K);
     }
     for (int a = tid; a < ma; a += kSelThreads)
