@@ -202,21 +202,29 @@ __device__ __forceinline__ void acc_init(GroupAcc& g, uint32_t bound) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) g.v[i] = 0u - bound;
 }
+// FIRST: the accumulators are not read but started at `start` (= -bound), which saves the
+// eight register initialisations per group.
+template <bool FIRST>
 __device__ __forceinline__ void lut_pair(uint32_t w0, uint32_t w1, const uint4& t0, const uint4& t1, GroupAcc& g,
-                                         const PipeK& k) {
+                                         const PipeK& k, uint32_t start) {
     const uint32_t x0 = w0 ^ 0x88888888u, x1 = w1 ^ 0x88888888u;
     const uint32_t pa = fadd(fadd(prmt(t0.x, t0.y, w0), prmt(t0.z, t0.w, x0), k),
                              fadd(prmt(t1.x, t1.y, w1), prmt(t1.z, t1.w, x1), k), k);
     const uint32_t pb = fadd(fadd(prmt(t0.x, t0.y, hi16(w0, k)), prmt(t0.z, t0.w, hi16(x0, k)), k),
                              fadd(prmt(t1.x, t1.y, hi16(w1, k)), prmt(t1.z, t1.w, hi16(x1, k)), k), k);
-    g.v[0] = __dp4a(pa, k.s0, g.v[0]); g.v[1] = __dp4a(pa, k.s1, g.v[1]);
-    g.v[2] = __dp4a(pa, k.s2, g.v[2]); g.v[3] = __dp4a(pa, k.s3, g.v[3]);
-    g.v[4] = __dp4a(pb, k.s0, g.v[4]); g.v[5] = __dp4a(pb, k.s1, g.v[5]);
-    g.v[6] = __dp4a(pb, k.s2, g.v[6]); g.v[7] = __dp4a(pb, k.s3, g.v[7]);
+    g.v[0] = __dp4a(pa, k.s0, FIRST ? start : g.v[0]); g.v[1] = __dp4a(pa, k.s1, FIRST ? start : g.v[1]);
+    g.v[2] = __dp4a(pa, k.s2, FIRST ? start : g.v[2]); g.v[3] = __dp4a(pa, k.s3, FIRST ? start : g.v[3]);
+    g.v[4] = __dp4a(pb, k.s0, FIRST ? start : g.v[4]); g.v[5] = __dp4a(pb, k.s1, FIRST ? start : g.v[5]);
+    g.v[6] = __dp4a(pb, k.s2, FIRST ? start : g.v[6]); g.v[7] = __dp4a(pb, k.s3, FIRST ? start : g.v[7]);
+}
+// One quad = 4 sub-quantisers. FIRST = first quad of a vector (see lut_pair).
+template <bool FIRST>
+__device__ __forceinline__ void lut_quad_t(const uint4& w, const uint4 (&t)[4], GroupAcc& g, const PipeK& k, uint32_t start) {
+    lut_pair<FIRST>(w.x, w.y, t[0], t[1], g, k, start);
+    lut_pair<false>(w.z, w.w, t[2], t[3], g, k, start);
 }
 __device__ __forceinline__ void lut_quad(const uint4& w, const uint4 (&t)[4], GroupAcc& g, const PipeK& k) {
-    lut_pair(w.x, w.y, t[0], t[1], g, k);
-    lut_pair(w.z, w.w, t[2], t[3], g, k);
+    lut_quad_t<false>(w, t, g, k, 0u);
 }
 __device__ __forceinline__ bool any_below(const GroupAcc& g) {
     return static_cast<int>(g.v[0] | g.v[1] | g.v[2] | g.v[3] | g.v[4] | g.v[5] | g.v[6] | g.v[7]) < 0;

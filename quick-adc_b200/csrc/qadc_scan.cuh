@@ -76,6 +76,18 @@ __device__ __forceinline__ void emit_candidates(const GroupAcc& g, uint32_t boun
     }
 }
 
+// One quad of the scan; the first quad of a vector starts the accumulators at -bound.
+__device__ __forceinline__ void scan_quad(bool first, const uint4& w, const uint4 (&t)[4], GroupAcc& g, const PipeK& k,
+                                          uint32_t bound) {
+#ifdef QADC_CORE_PACKED
+    if (first) acc_init(g, bound);
+    lut_quad(w, t, g, k);
+#else
+    if (first) lut_quad_t<true>(w, t, g, k, 0u - bound);
+    else lut_quad_t<false>(w, t, g, k, 0u);
+#endif
+}
+
 // Writes a warp's final sorted list (r keys, kEmptyKey padded) to global memory.
 __device__ __forceinline__ void store_list(const WarpList& list, uint64_t* dst, int r, int lane) {
     for (int i = lane; i < r; i += 32) dst[i] = list.keys[i];
@@ -226,7 +238,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
                     const uint32_t bound = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
 #endif
                     GroupAcc g;
-                    acc_init(g, bound);
 #pragma unroll
                     for (int q = 0; q < Cfg::kQuads; ++q) {
                         uint4 tq[4];
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
                             if constexpr (Cfg::kRegTab) tq[i] = treg[4 * q + i];
                             else tq[i] = qtab[qi * M + 4 * q + i];
                         }
-                        lut_quad(w[q], tq, g, pk);
+                        scan_quad(q == 0, w[q], tq, g, pk, bound);
                     }
                     const bool mine = any_below(g);
                     if (__any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
