@@ -341,31 +341,46 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
     }
     if (record_events) QCK(cudaEventRecord(ctx->ev[1], ctx->stream));
     // 2+3. residual, rotation, float tables
-    tables_kernel<<<static_cast<unsigned>(nqa), 256, static_cast<size_t>(dim) * 8, ctx->stream>>>(
-        d_queries, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
-        ctx->b_tables.as<float>(), ctx->b_tmin.as<float>());
-    ctx->launches++;
-    QCK(cudaGetLastError());
+    {
+        dim3 tgrid((ma + 7) / 8, nq);
+        tables_kernel<<<tgrid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(
+            d_queries, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
+            ctx->b_tables.as<float>(), ctx->b_tmin.as<float>());
+        ctx->launches++;
+        QCK(cudaGetLastError());
+    }
     if (record_events) QCK(cudaEventRecord(ctx->ev[2], ctx->stream));
     // 4. keep-prefix float scan -> qmax
-    int nsplit = 1;
-    if (flat) nsplit = static_cast<int>(std::min<uint32_t>(128, std::max<uint32_t>(1, ctx->max_start / 4096)));
-    ENSURE(ctx->b_plists, static_cast<size_t>(nq) * nsplit * r * 8);
     PrefixArgs pa;
     pa.starts = ctx->d_starts; pa.start_off = ctx->d_start_off; pa.start_size = ctx->d_start_size;
-    pa.assign = d_assign; pa.tables = ctx->b_tables.as<float>(); pa.ma = ma; pa.r = r; pa.M = M; pa.nsplit = nsplit;
-    pa.lists = ctx->b_plists.as<uint64_t>();
-    dim3 pgrid(nsplit, nq);
-    if (M == 16) prefix_scan_kernel<16><<<pgrid, kSelThreads, 0, ctx->stream>>>(pa);
-    else prefix_scan_kernel<32><<<pgrid, kSelThreads, 0, ctx->stream>>>(pa);
-    ctx->launches++;
-    QCK(cudaGetLastError());
-    MergeArgs mg{};
-    mg.in_keys = pa.lists; mg.L = nsplit; mg.r = r; mg.nq = nq; mg.out_rth_value = ctx->b_qmax.as<float>();
-    int rc = run_merge(ctx, mg);
-    if (rc) return rc;
+    pa.assign = d_assign; pa.tables = ctx->b_tables.as<float>(); pa.ma = ma; pa.r = r; pa.M = M;
+    pa.qmax = ctx->b_qmax.as<float>();
+    if (!flat && ctx->max_start <= 128) {
+        // inverted lists with short prefixes: one warp per probe
+        pa.nsplit = 1; pa.lists = nullptr;
+        if (M == 16) prefix_scan_probes_kernel<16><<<nq, kSelThreads, 0, ctx->stream>>>(pa);
+        else prefix_scan_probes_kernel<32><<<nq, kSelThreads, 0, ctx->stream>>>(pa);
+        ctx->launches++;
+        QCK(cudaGetLastError());
+    } else {
+        int nsplit = 1;
+        if (flat) nsplit = static_cast<int>(std::min<uint32_t>(128, std::max<uint32_t>(1, ctx->max_start / 4096)));
+        ENSURE(ctx->b_plists, static_cast<size_t>(nq) * nsplit * r * 8);
+        pa.nsplit = nsplit; pa.lists = ctx->b_plists.as<uint64_t>();
+        dim3 pgrid(nsplit, nq);
+        if (M == 16) prefix_scan_kernel<16><<<pgrid, kSelThreads, 0, ctx->stream>>>(pa);
+        else prefix_scan_kernel<32><<<pgrid, kSelThreads, 0, ctx->stream>>>(pa);
+        ctx->launches++;
+        QCK(cudaGetLastError());
+        if (nsplit > 1) {
+            MergeArgs mg{};
+            mg.in_keys = pa.lists; mg.L = nsplit; mg.r = r; mg.nq = nq; mg.out_rth_value = ctx->b_qmax.as<float>();
+            int rc = run_merge(ctx, mg);
+            if (rc) return rc;
+        }
+    }
     // 5. bounds + int8 tables
-    quantize_kernel<<<static_cast<unsigned>(nqa), 256, 0, ctx->stream>>>(
+    quantize_kernel<<<nq, 256, 0, ctx->stream>>>(
         ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), ctx->b_qmax.as<float>(), ma, M,
         ctx->b_qtables.as<int8_t>(), ctx->b_qmin.as<float>(), ctx->d_err);
     ctx->launches++;

@@ -111,37 +111,40 @@ __global__ void __launch_bounds__(kSelThreads) coarse_select_kernel(const float*
         out_assign[static_cast<size_t>(q) * ma + a] = (a < count) ? static_cast<int32_t>(static_cast<uint32_t>(keys[a])) : 0;
 }
 
-// ---- residual -> rotation -> float tables: one CTA per (query, probe) --------------------
-// tables[(q*ma + a)*M*16 + j*16 + c];  tmin[q*ma + a] = min entry of that table.
+// ---- residual -> rotation -> float tables: one WARP per (query, probe) ----------------------
+// grid = (ceil(ma/8), nq), 8 warps per CTA.  tables[(q*ma + a)*M*16 + j*16 + c];
+// tmin[q*ma + a] = min entry of that table.
 __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ queries, int dim, int M,
                                                      const float* __restrict__ codebooks,
                                                      const float* __restrict__ rotation,    // or null
                                                      const float* __restrict__ centroids,   // or null (flat)
                                                      const int32_t* __restrict__ assign, int ma,
                                                      float* __restrict__ tables, float* __restrict__ tmin) {
-    extern __shared__ __align__(16) float sm[];
-    float* res = sm;          // dim
-    float* rot = sm + dim;    // dim
-    __shared__ float red[8];
-    const int qa = blockIdx.x, q = qa / ma, tid = threadIdx.x;
+    extern __shared__ __align__(16) float sm[];   // 8 warps x 2 x dim
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.y, a_i = blockIdx.x * 8 + warp;
+    if (a_i >= ma) return;
+    const size_t qa = static_cast<size_t>(q) * ma + a_i;
+    float* res = sm + static_cast<size_t>(warp) * 2 * dim;
+    float* rot = res + dim;
     const float* query = queries + static_cast<size_t>(q) * dim;
     const float* cent = centroids ? centroids + static_cast<size_t>(assign[qa]) * dim : nullptr;
-    for (int i = tid; i < dim; i += blockDim.x) res[i] = cent ? __fsub_rn(query[i], cent[i]) : query[i];
-    __syncthreads();
+    for (int i = lane; i < dim; i += 32) res[i] = cent ? __fsub_rn(query[i], __ldg(cent + i)) : query[i];
+    __syncwarp();
     const float* x = res;
     if (rotation) {
-        for (int j = tid; j < dim; j += blockDim.x) {
+        for (int j = lane; j < dim; j += 32) {
             const float* row = rotation + static_cast<size_t>(j) * dim;
             float s = 0.f;
             for (int k = 0; k < dim; ++k) s = __fmaf_rn(res[k], __ldg(row + k), s);
             rot[j] = s;
         }
-        __syncthreads();
+        __syncwarp();
         x = rot;
     }
     const int dsq = dim / M, blocks = dsq / 8, rem = dsq % 8;
     float local_min = 3.402823466e+38f;
-    for (int e = tid; e < M * 16; e += blockDim.x) {
+    for (int e = lane; e < M * 16; e += 32) {
         const int j = e >> 4;
         const float* a = x + j * dsq;
         const float* b = codebooks + static_cast<size_t>(e) * dsq;   // (j*16 + c) * dsq
@@ -163,17 +166,11 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ q
             const float diff = __fsub_rn(__ldg(b + blocks * 8 + i), a[blocks * 8 + i]);
             norm = __fmaf_rn(diff, diff, norm);
         }
-        tables[static_cast<size_t>(qa) * M * 16 + e] = norm;
+        tables[qa * M * 16 + e] = norm;
         local_min = fminf(local_min, norm);
     }
     for (int o = 16; o > 0; o >>= 1) local_min = fminf(local_min, __shfl_xor_sync(0xffffffffu, local_min, o));
-    if ((tid & 31) == 0) red[tid >> 5] = local_min;
-    __syncthreads();
-    if (tid == 0) {
-        float mn = red[0];
-        for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) mn = fminf(mn, red[w]);
-        tmin[qa] = mn;
-    }
+    if (lane == 0) tmin[qa] = local_min;
 }
 
 // ---- keep-prefix float ADC: grid = (splits, queries) --------------------------------------
@@ -188,6 +185,7 @@ struct PrefixArgs {
     const float* tables;            // [nq][ma][M*16]
     int ma, r, M, nsplit;
     uint64_t* lists;                // [nq][nsplit][r]
+    float* qmax;                    // [nq], written directly when nsplit == 1
 };
 
 template <int M>
@@ -234,9 +232,56 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixAr
     top.maybe_compact(a.r, tid, true);
     uint64_t* dst = a.lists + (static_cast<size_t>(q) * a.nsplit + split) * a.r;
     for (int i = tid; i < a.r; i += kSelThreads) dst[i] = keys[i];
+    // a single split needs no merge: the r-th key is qmax (FLT_MAX when the prefix is too short)
+    if (a.nsplit == 1 && tid == 0)
+        a.qmax[q] = (count == a.r) ? __uint_as_float(static_cast<uint32_t>(keys[a.r - 1] >> 32)) : 3.402823466e+38f;
 }
 
-// ---- bounds + quantisation: one CTA per (query, probe) ------------------------------------
+// Short prefixes (inverted lists): one warp per probe, lanes over the few prefix vectors; the
+// CTA keeps one top-r buffer.  grid = queries.
+template <int M>
+__global__ void __launch_bounds__(kSelThreads) prefix_scan_probes_kernel(const PrefixArgs a) {
+    constexpr int CS = M / 2;
+    __shared__ uint64_t keys[kSelCap];
+    __shared__ float tab[8][M * 16];
+    __shared__ int count;
+    __shared__ unsigned long long bound_key;
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    BlockTopK top{keys, &count, &bound_key};
+    top.init(tid);
+    // rounds of 8 probes; every probe contributes at most kSelCap/16 = 128 prefix vectors per round
+    for (int a0 = 0; a0 < a.ma; a0 += 8) {
+        const int ar = a0 + warp;
+        uint32_t n = 0;
+        const uint8_t* codes = nullptr;
+        if (ar < a.ma) {
+            const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
+            n = a.start_size[p];
+            codes = a.starts + a.start_off[p] * CS;
+            for (int i = lane; i < M * 16; i += 32) tab[warp][i] = a.tables[(static_cast<size_t>(q) * a.ma + ar) * M * 16 + i];
+        }
+        __syncwarp();
+        for (uint32_t v = lane; v < n; v += 32) {   // n <= 128 (host guarantees max_start <= 128 for this kernel)
+            uint32_t w[CS / 4];
+            if constexpr (CS == 8) {
+                const uint2 c = *reinterpret_cast<const uint2*>(codes + static_cast<size_t>(v) * CS);
+                w[0] = c.x; w[1] = c.y;
+            } else {
+                const uint4 c = *reinterpret_cast<const uint4*>(codes + static_cast<size_t>(v) * CS);
+                w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w;
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < M; ++j) s = __fadd_rn(s, tab[warp][j * 16 + ((w[j >> 3] >> (4 * (j & 7))) & 15u)]);
+            top.push((static_cast<uint64_t>(__float_as_uint(s)) << 32) | (static_cast<uint32_t>(ar) << 8) | v);
+        }
+        top.maybe_compact(a.r, tid, a0 + 8 >= a.ma);
+    }
+    if (tid == 0)
+        a.qmax[q] = (count == a.r) ? __uint_as_float(static_cast<uint32_t>(keys[a.r - 1] >> 32)) : 3.402823466e+38f;
+}
+
+// ---- bounds + quantisation: one CTA per query ------------------------------------------------
 // qmin = min over all ma tables (negatives clamped to 0, also in `tables`), qmax from the
 // prefix scan; q(v) = 127 if v >= qmax else (int8) trunc((v - qmin) / delta),
 // delta = (qmax - qmin) / 127.  err[0] is set when qmax > 1e30 (db_query_4.cpp:271-274).
@@ -244,25 +289,40 @@ __global__ void __launch_bounds__(256) quantize_kernel(float* __restrict__ table
                                                        const float* __restrict__ qmax_in, int ma, int M,
                                                        int8_t* __restrict__ qtables, float* __restrict__ qmin_out,
                                                        int* __restrict__ err) {
-    const int qa = blockIdx.x, q = qa / ma, tid = threadIdx.x;
-    float qmin = tmin[static_cast<size_t>(q) * ma];
-    for (int a = 1; a < ma; ++a) qmin = fminf(qmin, tmin[static_cast<size_t>(q) * ma + a]);
+    __shared__ float red[8];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    float mn = 3.402823466e+38f;
+    for (int a = tid; a < ma; a += 256) mn = fminf(mn, tmin[static_cast<size_t>(q) * ma + a]);
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mn;
+    __syncthreads();
+    float qmin = red[0];
+    for (int w = 1; w < 8; ++w) qmin = fminf(qmin, red[w]);
     const bool clamp = qmin < 0.f;
     if (clamp) qmin = 0.f;
     const float qmax = qmax_in[q];
-    if (tid == 0 && qa == q * ma) {
+    if (tid == 0) {
         qmin_out[q] = qmin;
         if (qmax > 1e30f) atomicExch(err, 1);
     }
     const float delta = __fdiv_rn(__fsub_rn(qmax, qmin), 127.0f);
-    for (int e = tid; e < M * 16; e += blockDim.x) {
-        const size_t i = static_cast<size_t>(qa) * M * 16 + e;
-        float v = tables[i];
-        if (clamp && v < 0.f) { v = 0.f; tables[i] = 0.f; }
-        int8_t qv;
-        if (v >= qmax) qv = 127;
-        else qv = static_cast<int8_t>(static_cast<int>(__fdiv_rn(__fsub_rn(v, qmin), delta)));
-        qtables[i] = qv;
+    const size_t base = static_cast<size_t>(q) * ma * M * 16;
+    const int total = ma * M * 16;
+    for (int e = tid * 4; e < total; e += 256 * 4) {   // M*16 is a multiple of 4
+        float4 v = *reinterpret_cast<float4*>(tables + base + e);
+        float vv[4] = {v.x, v.y, v.z, v.w};
+        char4 out;
+        int8_t qv[4];
+        bool wrote = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (clamp && vv[i] < 0.f) { vv[i] = 0.f; wrote = true; }
+            qv[i] = (vv[i] >= qmax) ? static_cast<int8_t>(127)
+                                    : static_cast<int8_t>(static_cast<int>(__fdiv_rn(__fsub_rn(vv[i], qmin), delta)));
+        }
+        if (wrote) *reinterpret_cast<float4*>(tables + base + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        out.x = qv[0]; out.y = qv[1]; out.z = qv[2]; out.w = qv[3];
+        *reinterpret_cast<char4*>(qtables + base + e) = out;
     }
 }
 
