@@ -154,6 +154,17 @@ int qadc_dump_distances(qadc_ctx* ctx, int part_i, const int8_t* qtable, int8_t*
 /* The device layout read back as row-major codes (layout round-trip test). */
 int qadc_download_codes(qadc_ctx* ctx, int part_i, uint8_t* out_codes);
 
+/* ---- "next" row N1: PQ encoder -------------------------------------------------------------- */
+/* Replaces base_pq::encode_multiple_vectors + multiple_set_bits_4 (quantizers.hpp:49-68,
+ * :222-245) and, with a coarse quantiser set, index_db::assign_single_compute_residuals
+ * (databases.hpp:252-268): rotates (OPQ, flat only) and encodes `count` host vectors
+ * (count*dim floats) into row-major 4-bit codes (count*m/2 bytes).  out_assign (count, may be
+ * NULL) receives the coarse cell of every vector when the context has a coarse quantiser; the
+ * code is then that of the residual.  Nearest centroid by direct squared distance, first minimum
+ * on ties. */
+int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* out_assign,
+                uint8_t* out_codes);
+
 /* ---- tuning knobs (bench / tests) ------------------------------------------------------ */
 /* key: "flat_qb" (queries per pass of the flat scan: 1,2,4,8), "flat_chunks" (CTAs along
  * the database, 0 = auto), "time_scan" (1: record CUDA events around the scan kernel for

@@ -72,6 +72,7 @@ class Oracle:
         L.qo_scan_with_tables.restype = C.c_int
         L.qo_scan_with_tables.argtypes = [u8p, C.c_void_p, i64p, C.c_int, i32p, C.c_int, i8p, C.c_int,
                                           C.c_uint, u32p, i8p, C.c_void_p]
+        L.qo_encode.argtypes = [f32p, C.c_long, C.c_int, C.c_int, f32p, u8p]
         L.qo_search.restype = C.c_int
         L.qo_search.argtypes = [C.c_int, C.c_int, f32p, C.c_void_p, C.c_int, C.c_void_p, u8p, C.c_void_p,
                                 i64p, C.c_float, f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, u32p, i8p,
@@ -140,6 +141,12 @@ class Oracle:
         self.lib.qo_coarse_assign(queries, nq, dim, np.ascontiguousarray(centroids), centroids.shape[0], ma,
                                   assign.reshape(-1), _opt(dists))
         return assign, dists
+
+    def encode(self, vectors, m, codebooks):
+        v = np.ascontiguousarray(vectors, np.float32)
+        codes = np.zeros((v.shape[0], m // 2), np.uint8)
+        self.lib.qo_encode(v, v.shape[0], v.shape[1], m, np.ascontiguousarray(codebooks.reshape(-1)), codes.reshape(-1))
+        return codes
 
     def start_size(self, size, keep):
         return self.lib.qo_start_size(size, np.float32(keep))

@@ -78,11 +78,12 @@ def load_library(build_if_missing=True):
     L.qadc_dump_distances.argtypes = [vp, i32, vp, vp]
     L.qadc_download_codes.argtypes = [vp, i32, vp]
     L.qadc_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.qadc_encode.argtypes = [vp, vp, u32, vp, vp]
     for name in ("qadc_create", "qadc_set_pq", "qadc_set_coarse", "qadc_begin_database", "qadc_upload_codes",
                  "qadc_set_position_base", "qadc_set_prefix", "qadc_finalize", "qadc_search", "qadc_search_device",
                  "qadc_synchronize", "qadc_last_launch_count", "qadc_last_scan_ms", "qadc_merge_shards_device",
                  "qadc_build_tables", "qadc_scan_with_tables", "qadc_dump_distances", "qadc_download_codes",
-                 "qadc_set_option"):
+                 "qadc_set_option", "qadc_encode"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -182,6 +183,14 @@ class Index:
             if sizes[p]:
                 self.upload_codes(p, 0, codes[offsets[p]:offsets[p + 1]], labels[offsets[p]:offsets[p + 1]])
         self.finalize(keep)
+
+    def encode(self, vectors):
+        """PQ-encode float vectors (and, for an IVF context, assign them to coarse cells)."""
+        v = np.ascontiguousarray(vectors, np.float32)
+        codes = np.empty((v.shape[0], self.m // 2), np.uint8)
+        assign = np.empty(v.shape[0], np.int32) if self.K else None
+        self._ck(self.lib.qadc_encode(self.h, _ptr(v), v.shape[0], _ptr(assign), _ptr(codes)))
+        return (codes, assign) if self.K else codes
 
     # ---- search -------------------------------------------------------------------------
     def search(self, queries, ma, r, want_metrics=False):

@@ -818,6 +818,60 @@ int qadc_download_codes(qadc_ctx* ctx, int part_i, uint8_t* out_codes) {
     return QADC_OK;
 }
 
+int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* out_assign, uint8_t* out_codes) {
+    if (!ctx || !vectors || !out_codes) return fail(ctx, QADC_EINVAL, "null buffer");
+    if (ctx->m == 0) return fail(ctx, QADC_ESTATE, "qadc_set_pq must be called first");
+    if (count == 0) return QADC_OK;
+    QCK(cudaSetDevice(ctx->device));
+    const int dim = ctx->dim, M = ctx->m, CS = M / 2;
+    const bool ivf = ctx->K > 0;
+    const uint32_t kChunk = 1u << 20;
+    ENSURE(ctx->b_queries, static_cast<size_t>(std::min(count, kChunk)) * dim * 4);
+    ENSURE(ctx->b_tables, static_cast<size_t>(std::min(count, kChunk)) * dim * 4);   // rotated copy
+    ENSURE(ctx->b_assign, static_cast<size_t>(std::min(count, kChunk)) * 4);
+    ENSURE(ctx->b_dump, static_cast<size_t>(std::min(count, kChunk)) * CS);
+    for (uint32_t off = 0; off < count; off += kChunk) {
+        const uint32_t n = std::min(kChunk, count - off);
+        float* d_x = ctx->b_queries.as<float>();
+        QCK(cudaMemcpyAsync(d_x, vectors + static_cast<size_t>(off) * dim, static_cast<size_t>(n) * dim * 4,
+                            cudaMemcpyHostToDevice, ctx->stream));
+        int32_t* d_assign = nullptr;
+        if (ivf) {
+            // index_db::assign_single_compute_residuals (databases.hpp:252-268): nearest cell, k = 1
+            d_assign = ctx->b_assign.as<int32_t>();
+            const int chunk_q = std::max(1, static_cast<int>(std::min<size_t>(n, (size_t(1) << 28) / ctx->K)));
+            ENSURE(ctx->b_cdist, static_cast<size_t>(chunk_q) * ctx->K * 4);
+            for (uint32_t q0 = 0; q0 < n; q0 += chunk_q) {
+                const int nn = static_cast<int>(std::min<uint32_t>(chunk_q, n - q0));
+                dim3 grid((nn + kCoarseTQ - 1) / kCoarseTQ, (ctx->K + kCoarseTC - 1) / kCoarseTC);
+                coarse_dist_kernel<<<grid, 256, 0, ctx->stream>>>(d_x + static_cast<size_t>(q0) * dim, nn, dim, ctx->d_centroids,
+                                                                  ctx->K, ctx->b_cdist.as<float>());
+                coarse_select_kernel<<<nn, kSelThreads, 0, ctx->stream>>>(ctx->b_cdist.as<float>(), ctx->K, 1, d_assign + q0);
+                QCK(cudaGetLastError());
+            }
+            if (out_assign)
+                QCK(cudaMemcpyAsync(out_assign + off, d_assign, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        const float* d_in = d_x;
+        if (ctx->d_rotation) {
+            if (ivf) return fail(ctx, QADC_EINVAL, "OPQ + inverted lists: rotate residuals is not implemented in qadc_encode");
+            const size_t tot = static_cast<size_t>(n) * dim;
+            rotate_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ctx->stream>>>(d_x, n, dim, ctx->d_rotation,
+                                                                                          ctx->b_tables.as<float>());
+            QCK(cudaGetLastError());
+            d_in = ctx->b_tables.as<float>();
+        }
+        const size_t threads = static_cast<size_t>(n) * CS;
+        encode_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(
+            d_in, n, dim, M, ctx->d_codebooks, ivf ? ctx->d_centroids : nullptr, d_assign, ctx->b_dump.as<uint8_t>());
+        QCK(cudaGetLastError());
+        QCK(cudaMemcpyAsync(out_codes + static_cast<size_t>(off) * CS, ctx->b_dump.p, static_cast<size_t>(n) * CS,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+        QCK(cudaStreamSynchronize(ctx->stream));
+    }
+    return QADC_OK;
+}
+
 int qadc_set_option(qadc_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return QADC_EINVAL;
     if (!strcmp(key, "flat_qb")) ctx->opt_flat_qb = value;

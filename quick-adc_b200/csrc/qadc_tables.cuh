@@ -281,6 +281,56 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_probes_kernel(const P
         a.qmax[q] = (count == a.r) ? __uint_as_float(static_cast<uint32_t>(keys[a.r - 1] >> 32)) : 3.402823466e+38f;
 }
 
+// ---- PQ encoder ("next" row N1) ---------------------------------------------------------------
+// base_pq::encode_multiple_vectors + multiple_set_bits_4 (quantizers.hpp:49-68, :222-245): one
+// thread per (vector, code byte) finds the nearest of 16 centroids for sub-quantisers 2b and 2b+1
+// (direct squared distance, first minimum wins like the k=1 heap) and writes idx[2b] | idx[2b+1]<<4.
+// `centroids`/`assign` given: encode the residual x - centroid[assign[v]] (index_db::add_vectors).
+__global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ vectors, uint32_t count, int dim, int M,
+                                                     const float* __restrict__ codebooks,
+                                                     const float* __restrict__ centroids,
+                                                     const int32_t* __restrict__ assign, uint8_t* __restrict__ codes) {
+    const int CS = M / 2, dsq = dim / M;
+    const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= static_cast<size_t>(count) * CS) return;
+    const uint32_t v = static_cast<uint32_t>(t / CS);
+    const int b = static_cast<int>(t % CS);
+    const float* x = vectors + static_cast<size_t>(v) * dim;
+    const float* cent = centroids ? centroids + static_cast<size_t>(assign[v]) * dim : nullptr;
+    uint32_t code = 0;
+    for (int h = 0; h < 2; ++h) {
+        const int j = 2 * b + h;
+        int best = 0;
+        float bd = 0.f;
+        for (int c = 0; c < 16; ++c) {
+            const float* cb = codebooks + (static_cast<size_t>(j) * 16 + c) * dsq;
+            float s = 0.f;
+            for (int i = 0; i < dsq; ++i) {
+                const float xi = cent ? __fsub_rn(x[j * dsq + i], __ldg(cent + j * dsq + i)) : x[j * dsq + i];
+                const float diff = __fsub_rn(xi, __ldg(cb + i));
+                s = __fmaf_rn(diff, diff, s);
+            }
+            if (c == 0 || s < bd) { bd = s; best = c; }
+        }
+        code |= static_cast<uint32_t>(best) << (4 * h);
+    }
+    codes[t] = static_cast<uint8_t>(code);
+}
+
+// opq::rotate_multiple_vectors (quantizers.hpp:289-301): out = X * R^T, sequential fma over k.
+__global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ vectors, uint32_t count, int dim,
+                                                     const float* __restrict__ rotation, float* __restrict__ out) {
+    const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= static_cast<size_t>(count) * dim) return;
+    const size_t v = t / dim;
+    const int j = static_cast<int>(t % dim);
+    const float* x = vectors + v * dim;
+    const float* row = rotation + static_cast<size_t>(j) * dim;
+    float s = 0.f;
+    for (int k = 0; k < dim; ++k) s = __fmaf_rn(x[k], __ldg(row + k), s);
+    out[t] = s;
+}
+
 // ---- bounds + quantisation: one CTA per query ------------------------------------------------
 // qmin = min over all ma tables (negatives clamped to 0, also in `tables`), qmax from the
 // prefix scan; q(v) = 127 if v >= qmax else (int8) trunc((v - qmin) / delta),

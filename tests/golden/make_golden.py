@@ -82,8 +82,20 @@ def ivf_case(ref, name, seed, dim, m, n, K, ma, nq, r, keep, empty=()):
     print(name, "heap sizes", res["sizes"])
 
 
+def encode_case(ref, name, seed, dim, m, n):
+    """base_pq::encode_multiple_vectors (quantizers.hpp:222-245) on seeded vectors."""
+    rng = np.random.default_rng(seed)
+    cb = synth.make_pq(rng, dim, m)
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), dim=dim, m=m, codebooks=cb, vectors=x,
+                        ref_codes=ref.encode(x, m, cb))
+    print(name, "encoded", n)
+
+
 def main():
     ref = Ref()
+    encode_case(ref, "encode_m16", seed=105, dim=128, m=16, n=400)
+    encode_case(ref, "encode_m32", seed=106, dim=256, m=32, n=200)
     # n = 3003: not a multiple of 16 -> exercises the pad-lane duplicate quirk (SURVEY F5b)
     flat_case(ref, "flat_m16", seed=101, dim=128, m=16, n=3003, nq=8, r=20, keep=0.05)
     # 96-d, m=32 -> sq_dim 3 (SURVEY F7: only reachable by direct template instantiation)

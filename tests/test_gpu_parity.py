@@ -443,3 +443,104 @@ def test_large_flat_planted_neighbours_and_dump_cross_check(qadc):
         assert np.array_equal(ids[s][:len(order)], pos[order].astype(np.uint32))
         assert np.array_equal(d[s][:len(order)], dist[pos[order]])
     ix.close()
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_virtual_ivf_shards_merge_equals_single(qadc, oracle, G):
+    """Sharded inverted lists: every shard owns whole lists (greedy by size), holds a
+    replica of ALL keep-prefixes, and returns its local top-r with labels resolved locally; the
+    merged result equals the unsharded one (and the oracle)."""
+    import torch
+    from qadc_b200 import sharding
+    rng = np.random.default_rng(40 + G)
+    dim, m, n, K, ma, nq, r, keep = 96, 16, 60000, 48, 10, 11, 50, 0.05
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(9,))
+    q = synth.make_queries(rng, nq, dim)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=keep,
+                             offsets=offsets), q, ma, r, want_tables=False)
+    sizes = np.diff(offsets)
+    owner = sharding.ivf_list_owner(sizes, G)
+    dq = torch.from_numpy(q).cuda()
+    keys = torch.empty((G, nq, r), dtype=torch.int64, device="cuda")
+    ids = torch.empty((G, nq, r), dtype=torch.int32, device="cuda")
+    for g in range(G):
+        ix = qadc.Index(0)
+        ix.set_pq(dim, m, cb)
+        ix.set_coarse(cents)
+        local = np.where(owner == g, sizes, 0).astype(np.uint32)
+        ix.begin_database(local, True)
+        for p in range(K):
+            if sizes[p] == 0:
+                continue
+            if owner[p] == g:
+                ix.upload_codes(p, 0, codes[offsets[p]:offsets[p + 1]], labels[offsets[p]:offsets[p + 1]])
+            ix.set_prefix(p, codes[offsets[p]:offsets[p] + sharding.start_size(int(sizes[p]), keep)])
+        ix.finalize(keep)
+        d_tmp = torch.empty((nq, r), dtype=torch.int8, device="cuda")
+        c_tmp = torch.empty(nq, dtype=torch.int32, device="cuda")
+        ix.search_device(dq.data_ptr(), nq, ma, r, ids[g].data_ptr(), d_tmp.data_ptr(), c_tmp.data_ptr(), keys[g].data_ptr())
+        ix.synchronize()
+        ix.close()
+    mi = qadc.Index(0)
+    o_ids = torch.empty((nq, r), dtype=torch.int32, device="cuda")
+    o_d = torch.empty((nq, r), dtype=torch.int8, device="cuda")
+    o_c = torch.empty(nq, dtype=torch.int32, device="cuda")
+    mi.merge_shards_device(keys.data_ptr(), ids.data_ptr(), G, nq, r, o_ids.data_ptr(), o_d.data_ptr(), o_c.data_ptr())
+    mi.synchronize()
+    assert np.array_equal(o_ids.cpu().numpy().view(np.uint32), exp["ids"])
+    assert np.array_equal(o_d.cpu().numpy(), exp["d"])
+    assert np.array_equal(o_c.cpu().numpy(), exp["count"])
+    mi.close()
+
+
+# ---- "next" row N1: PQ encoder on the GPU ----------------------------------------------------
+@pytest.mark.parametrize("name", ["encode_m16", "encode_m32"])
+def test_gpu_encoder_matches_reference_and_oracle(qadc, oracle, name):
+    g = load(name)
+    ix = qadc.Index(0)
+    ix.set_pq(int(g["dim"]), int(g["m"]), g["codebooks"])
+    codes = ix.encode(g["vectors"])
+    assert np.array_equal(codes, g["ref_codes"])                                   # reference encoder output
+    assert np.array_equal(codes, oracle.encode(g["vectors"], int(g["m"]), g["codebooks"]))
+    ix.close()
+
+
+def test_gpu_encode_search_recall(qadc, oracle):
+    """floats -> GPU encoder -> database -> search: queries that are small perturbations of database
+    vectors find them (Recall@100 with t=1 as recall.hpp:45-54 defines it), OPQ rotation included."""
+    rng = np.random.default_rng(9)
+    dim, m, n, nq, r = 64, 16, 50000, 50, 100
+    rot = np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32)
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    cb = np.stack([rng.permutation(base @ rot.T)[:16, j * 4:(j + 1) * 4] for j in range(m)]).astype(np.float32)
+    ix = qadc.Index(0)
+    ix.set_pq(dim, m, cb, rotation=rot)
+    codes = ix.encode(base)
+    assert np.array_equal(codes, oracle.encode(oracle.rotate(base, rot), m, cb))
+    ix.load_flat(codes, 0.02)
+    truth = rng.integers(0, n, nq)
+    q = base[truth] + 0.01 * rng.standard_normal((nq, dim)).astype(np.float32)
+    ids, d, cnt = ix.search(q, 1, r)
+    recall = np.mean([truth[i] in ids[i] for i in range(nq)])
+    assert recall >= 0.9, recall
+    ix.close()
+
+
+def test_gpu_ivf_assign_encode(qadc, oracle):
+    """index_db::add_vectors path: nearest coarse cell (k=1) + code of the residual."""
+    rng = np.random.default_rng(10)
+    dim, m, n, K = 128, 16, 5000, 300
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    ix = qadc.Index(0)
+    ix.set_pq(dim, m, cb)
+    ix.set_coarse(cents)
+    codes, assign = ix.encode(x)
+    e_assign, _ = oracle.coarse_assign(x, cents, 1)
+    assert np.array_equal(assign, e_assign[:, 0])
+    resid = (x - cents[assign]).astype(np.float32)
+    assert np.array_equal(codes, oracle.encode(resid, m, cb))
+    ix.close()
