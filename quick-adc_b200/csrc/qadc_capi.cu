@@ -248,7 +248,10 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         FlatPlan pl;
         rc = plan_flat(ctx, nq, r, pl);
         if (rc) return rc;
-        n_lists = pl.chunks * pl.nw;
+        // the NW warp lists of a CTA are merged inside the kernel when they fit a CTA-wide sort in the tile ring
+        const size_t ring_keys = static_cast<size_t>(4) * pl.nw * sb_bytes(M) / 8;
+        const bool cta_merge = static_cast<size_t>(next_pow2(pl.nw * r)) <= std::min<size_t>(ring_keys, 4096);
+        n_lists = cta_merge ? pl.chunks : pl.chunks * pl.nw;
         ENSURE(ctx->b_lists, static_cast<size_t>(nq) * n_lists * r * 8);
         FlatScanArgs a;
         a.codes = ctx->d_codes; a.n_sb = static_cast<uint32_t>(ctx->total_sb); a.size = ctx->h_size[0];

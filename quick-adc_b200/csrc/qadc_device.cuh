@@ -278,6 +278,10 @@ __device__ __forceinline__ void bitonic_sort_u64_u32(uint64_t* keys, uint32_t* v
 struct WarpSync {
     __device__ __forceinline__ void operator()() const { __syncwarp(); }
 };
+struct NamedSync {   // a subset of the CTA's warps (bar.sync id, nthreads)
+    int id, nthreads;
+    __device__ __forceinline__ void operator()() const { named_bar_sync(id, nthreads); }
+};
 struct BlockSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };

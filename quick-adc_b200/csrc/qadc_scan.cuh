@@ -275,19 +275,36 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
         if (++stage == NS) { stage = 0; phase ^= 1; }
     }
 
-    // ---- final: sort and publish one list per (warp, query) ----
+    // ---- final: one sorted list per (CTA, query) when the NW warp lists fit a CTA-wide sort in
+    // the (now idle) tile ring, else one list per (warp, query) ----
+    const bool cta_merge = a.n_lists == static_cast<int>(gridDim.x);
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(tiles);
+    const int ctid = threadIdx.x;   // consumer thread index (consumer warps are 0..NW-1)
 #pragma unroll
     for (int qi = 0; qi < QB; ++qi) {
-        if (qi < nqb) {
-            wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
-            store_list(wl[qi],
-                       a.lists + (static_cast<size_t>(qbase + qi) * a.n_lists + blockIdx.x * NW + warp) * a.r,
-                       a.r, lane);
-        }
+        if (qi < nqb) wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
     }
-#ifdef QADC_FINAL_SYNC
-    __syncthreads();
-#endif
+    if (!cta_merge) {
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi)
+            if (qi < nqb)
+                store_list(wl[qi], a.lists + (static_cast<size_t>(qbase + qi) * a.n_lists + blockIdx.x * NW + warp) * a.r,
+                           a.r, lane);
+        return;
+    }
+    int n_sort = 64;
+    while (n_sort < NW * a.r) n_sort <<= 1;
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) {
+        if (qi >= nqb) break;   // CTA-uniform
+        named_bar_sync(1, NW * 32);   // scratch is free (all tiles consumed / previous query stored)
+        for (int i = lane; i < a.r; i += 32) scratch[warp * a.r + i] = wl[qi].keys[i];
+        for (int i = NW * a.r + ctid; i < n_sort; i += NW * 32) scratch[i] = kEmptyKey;
+        named_bar_sync(1, NW * 32);
+        bitonic_sort_u64(scratch, n_sort, ctid, NW * 32, NamedSync{1, NW * 32});
+        uint64_t* dst = a.lists + (static_cast<size_t>(qbase + qi) * a.n_lists + blockIdx.x) * a.r;
+        for (int i = ctid; i < a.r; i += NW * 32) dst[i] = scratch[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------

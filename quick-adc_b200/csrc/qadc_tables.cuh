@@ -36,9 +36,11 @@ struct BlockTopK {
         const int c = *count;
         __syncthreads();   // every thread has read the count before anyone pushes again (uniform decision)
         if (c > kSelCap / 2 || force) {
-            bitonic_sort_u64(keys, kSelCap, tid, kSelThreads, BlockSync());
+            int n_sort = 64;   // only the occupied power-of-two prefix needs sorting (the rest is empty)
+            while (n_sort < c) n_sort <<= 1;
+            bitonic_sort_u64(keys, n_sort, tid, kSelThreads, BlockSync());
             const int n = min(c, k);
-            for (int i = k + tid; i < kSelCap; i += kSelThreads) keys[i] = kEmptyKey;
+            for (int i = k + tid; i < n_sort; i += kSelThreads) keys[i] = kEmptyKey;
             if (tid == 0) { *count = n; *bound_key = (n == k) ? keys[k - 1] : kEmptyKey; }
             __syncthreads();
         }
