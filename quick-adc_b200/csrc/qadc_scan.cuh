@@ -88,6 +88,26 @@ __device__ __forceinline__ void scan_quad(bool first, const uint4& w, const uint
 #endif
 }
 
+// Early abandon (skip the last sub-quantisers once every vector of a superblock has reached the
+// bound) is exact but measured SLOWER on B200 for the 1e9 x 16x4 bench (643 vs 680 G vectors/s):
+// the extra vote/branch splits the unrolled lookup chain.  Off unless -DQADC_EARLY_ABANDON.
+#ifdef QADC_EARLY_ABANDON
+constexpr bool kEarlyAbandon = true;
+#else
+constexpr bool kEarlyAbandon = false;
+#endif
+// One pair of sub-quantisers; the first pair of a vector starts the accumulators at -bound.
+__device__ __forceinline__ void scan_pair(bool first, uint32_t w0, uint32_t w1, const uint4& t0, const uint4& t1,
+                                          GroupAcc& g, const PipeK& k, uint32_t bound) {
+#ifdef QADC_CORE_PACKED
+    if (first) acc_init(g, bound);
+    lut_pair(w0, w1, t0, t1, g, k);
+#else
+    if (first) lut_pair<true>(w0, w1, t0, t1, g, k, 0u - bound);
+    else lut_pair<false>(w0, w1, t0, t1, g, k, 0u);
+#endif
+}
+
 // Writes a warp's final sorted list (r keys, kEmptyKey padded) to global memory.
 __device__ __forceinline__ void store_list(const WarpList& list, uint64_t* dst, int r, int lane) {
     for (int i = lane; i < r; i += 32) dst[i] = list.keys[i];
@@ -238,18 +258,24 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
                     const uint32_t bound = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
 #endif
                     GroupAcc g;
+                    // Early abandon: table entries are >= 0, so partial sums only grow.  Once every vector
+                    // of the superblock has reached the bound after kCheck sub-quantisers, the rest of the
+                    // lookups cannot produce a candidate and are skipped (exact; data dependent).
+                    bool alive = true;
 #pragma unroll
-                    for (int q = 0; q < Cfg::kQuads; ++q) {
-                        uint4 tq[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if constexpr (Cfg::kRegTab) tq[i] = treg[4 * q + i];
-                            else tq[i] = qtab[qi * M + 4 * q + i];
+                    for (int p = 0; p < M / 2; ++p) {   // pairs of sub-quantisers
+                        if (alive) {
+                            uint4 t0, t1;
+                            if constexpr (Cfg::kRegTab) { t0 = treg[2 * p]; t1 = treg[2 * p + 1]; }
+                            else { t0 = qtab[qi * M + 2 * p]; t1 = qtab[qi * M + 2 * p + 1]; }
+                            const uint4& wq = w[p >> 1];
+                            scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, t0, t1, g, pk, bound);
+                            if (kEarlyAbandon && ((M == 16 && p == 5) || (M == 32 && (p == 9 || p == 12))))
+                                alive = __any_sync(0xffffffffu, any_below(g));
                         }
-                        scan_quad(q == 0, w[q], tq, g, pk, bound);
                     }
-                    const bool mine = any_below(g);
-                    if (__any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
+                    const bool mine = alive && any_below(g);
+                    if (alive && __any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
                         if (mine) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi]);
                         __syncwarp();
                         if (*wl[qi].count >= compact_at) {
