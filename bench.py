@@ -311,7 +311,7 @@ def run_ours(args):
     ix.synchronize()
 
     # roofline of the dominant kernel (the 4-bit scan): algorithmic bytes = passes x N_local x 8
-    qb_used = args.qb if args.qb else (4 if nq >= 4 else (2 if nq >= 2 else 1))
+    qb_used = args.qb if args.qb else (2 if nq >= 2 else 1)
     passes = -(-nq // qb_used)
     t_scan = float(np.mean(scan_ms)) * 1e-3
     achieved = passes * n_local * CODE_BYTES / t_scan / 1e9

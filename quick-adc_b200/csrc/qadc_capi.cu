@@ -164,32 +164,42 @@ int launch_flat(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
     return QADC_OK;
 }
 
-struct FlatPlan { int qb, nw, chunks, cap; uint32_t sb_per_chunk; };
+struct FlatVariant {
+    int m, qb, nw, ns;
+    int (*launch)(qadc_ctx*, FlatScanArgs, int);
+    size_t (*smem)(int cap);
+};
+#define QADC_FLAT_VARIANT(M, QB, NW, NS) {M, QB, NW, NS, launch_flat<M, QB, NW, NS>, FlatCfg<M, QB, NW, NS>::smem_bytes}
+// in order of preference per (m, qb): 15 consumer warps when the lists fit, else 8
+const FlatVariant kFlatVariants[] = {
+    QADC_FLAT_VARIANT(16, 1, QADC_NW1, QADC_NS1), QADC_FLAT_VARIANT(16, 1, 8, 4),
+    QADC_FLAT_VARIANT(16, 2, 15, 3), QADC_FLAT_VARIANT(16, 2, 8, 4),
+    QADC_FLAT_VARIANT(16, 4, 15, 3), QADC_FLAT_VARIANT(16, 4, 8, 4),
+    QADC_FLAT_VARIANT(32, 1, 15, 3), QADC_FLAT_VARIANT(32, 1, 8, 4),
+    QADC_FLAT_VARIANT(32, 2, 8, 4),
+};
 
-size_t flat_smem(int M, int qb, int nw, int cap) {
-    if (M == 16) {
-        if (qb == 1) return nw == QADC_NW1 ? FlatCfg<16, 1, QADC_NW1, QADC_NS1>::smem_bytes(cap) : FlatCfg<16, 1, 8, 4>::smem_bytes(cap);
-        return qb == 2 ? FlatCfg<16, 2, 8, 4>::smem_bytes(cap) : FlatCfg<16, 4, 8, 4>::smem_bytes(cap);
-    }
-    return qb == 1 ? FlatCfg<32, 1, 8, 4>::smem_bytes(cap) : FlatCfg<32, 2, 8, 4>::smem_bytes(cap);
-}
+struct FlatPlan { const FlatVariant* v; int qb, nw, chunks, cap; uint32_t sb_per_chunk; };
 
-// Chooses queries-per-pass, warps per CTA and chunk count for the flat scan.
+// Chooses queries-per-pass, kernel variant, list capacity and chunk count for the flat scan.
 int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     const int M = ctx->m;
     int qb = static_cast<int>(ctx->opt_flat_qb);
-    if (qb <= 0) qb = (nq >= 4) ? ((M == 16) ? 4 : 2) : ((nq >= 2) ? 2 : 1);
+    if (qb <= 0) qb = (nq >= 2) ? 2 : 1;   // measured best for batches (config 1: 676 vs 563 (1) / 502 (4) G pairs/s)
     if (M == 32 && qb > 2) qb = 2;
     if (qb > 4) qb = 4;
     if (qb == 3) qb = 2;
     while (qb > nq && qb > 1) qb >>= 1;
-    const int cap = next_pow2(r + kSbVec);
-    while (qb > 1 && flat_smem(M, qb, 8, cap) > kMaxSmem) qb >>= 1;
-    int nw = (M == 16 && qb == 1) ? QADC_NW1 : 8;
-    if (flat_smem(M, qb, nw, cap) > kMaxSmem) nw = 8;
-    if (flat_smem(M, qb, nw, cap) > kMaxSmem)
-        return fail(ctx, QADC_EINVAL, "r too large for the scan kernel's shared-memory lists");
-    pl.qb = qb; pl.cap = cap; pl.nw = nw;
+    // list capacity: one superblock of candidates on top of r (one pass) or half a superblock (two passes)
+    const int caps[2] = {next_pow2(r + kSbVec), next_pow2(r + kSbVec / 2)};
+    pl.v = nullptr;
+    for (; qb >= 1 && !pl.v; qb >>= 1)
+        for (const FlatVariant& v : kFlatVariants) {
+            if (v.m != M || v.qb != qb || pl.v) continue;
+            for (int cap : caps)
+                if (!pl.v && v.smem(cap) <= static_cast<size_t>(kMaxSmem)) { pl.v = &v; pl.cap = cap; pl.qb = qb; pl.nw = v.nw; }
+        }
+    if (!pl.v) return fail(ctx, QADC_EINVAL, "r too large for the scan kernel's shared-memory lists");
     const uint32_t n_sb = static_cast<uint32_t>(ctx->total_sb);
     const int tile_sb = pl.nw;
     const int qgroups = (nq + pl.qb - 1) / pl.qb;
@@ -249,7 +259,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         rc = plan_flat(ctx, nq, r, pl);
         if (rc) return rc;
         // the NW warp lists of a CTA are merged inside the kernel when they fit a CTA-wide sort in the tile ring
-        const size_t ring_keys = static_cast<size_t>(4) * pl.nw * sb_bytes(M) / 8;
+        const size_t ring_keys = static_cast<size_t>(pl.v->ns) * pl.nw * sb_bytes(M) / 8;
         const bool cta_merge = static_cast<size_t>(next_pow2(pl.nw * r)) <= std::min<size_t>(ring_keys, 4096);
         n_lists = cta_merge ? pl.chunks : pl.chunks * pl.nw;
         ENSURE(ctx->b_lists, static_cast<size_t>(nq) * n_lists * r * 8);
@@ -258,15 +268,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         a.pos_base = ctx->h_pos_base[0]; a.sb_per_chunk = pl.sb_per_chunk; a.qtabs = d_qtables; a.nq = nq;
         a.r = r; a.cap = pl.cap; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
         a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk;
-        if (M == 16) {
-            if (pl.qb == 1 && pl.nw == QADC_NW1) rc = launch_flat<16, 1, QADC_NW1, QADC_NS1>(ctx, a, pl.chunks);
-            else if (pl.qb == 1) rc = launch_flat<16, 1, 8, 4>(ctx, a, pl.chunks);
-            else if (pl.qb == 2) rc = launch_flat<16, 2, 8, 4>(ctx, a, pl.chunks);
-            else rc = launch_flat<16, 4, 8, 4>(ctx, a, pl.chunks);
-        } else {
-            if (pl.qb == 1) rc = launch_flat<32, 1, 8, 4>(ctx, a, pl.chunks);
-            else rc = launch_flat<32, 2, 8, 4>(ctx, a, pl.chunks);
-        }
+        rc = pl.v->launch(ctx, a, pl.chunks);
         if (rc) return rc == QADC_ENOMEM ? fail(ctx, rc, "scan kernel shared memory exceeds 227 KB") : rc;
     } else {
         const int cap = next_pow2(r + kSbVec);

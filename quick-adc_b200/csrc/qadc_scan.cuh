@@ -68,12 +68,45 @@ __global__ void __launch_bounds__(256) untranspose_codes_kernel(const uint8_t* _
 // Append every vector of a group whose sum is below the bound.  pos0 = position of vector
 // k=0 inside the (local) partition.
 __device__ __forceinline__ void emit_candidates(const GroupAcc& g, uint32_t bound, uint32_t pos0, uint32_t size,
-                                                uint32_t pos_base, uint32_t probe_rank, WarpList& list) {
+                                                uint32_t pos_base, uint32_t probe_rank, WarpList& list,
+                                                int* hist = nullptr) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t v = lane_raw(g, k);
-        if (!(v & 0x8000u) && pos0 + k < size) list.push(make_key(v + bound - 0x8000u, probe_rank, pos_base + pos0 + k));
+        if (!(v & 0x8000u) && pos0 + k < size) {
+            const uint32_t d = v + bound - 0x8000u;
+            list.push(make_key(d, probe_rank, pos_base + pos0 + k));
+            if (hist) atomicAdd(hist + d, 1);
+        }
     }
+}
+
+// CTA-wide candidate histogram (128 bins per query): every candidate ever pushed by any warp of the
+// CTA is counted, so the smallest distance whose cumulative count reaches r is a valid value for
+// the query's shared bound long before any single warp has collected r candidates of its own.
+// Called by a whole warp; returns the bound (or 127 if fewer than r candidates were counted).
+__device__ __forceinline__ int hist_bound(const int* hist, int r, int lane) {
+    const int4 c = *reinterpret_cast<const int4*>(hist + lane * 4);
+    const int mine = c.x + c.y + c.z + c.w;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const unsigned reached = __ballot_sync(0xffffffffu, incl >= r);
+    if (!reached) return 127;
+    const int src = __ffs(reached) - 1;
+    int b = 127;
+    if (lane == src) {
+        int cum = incl - mine;
+        const int v[4] = {c.x, c.y, c.z, c.w};
+        for (int i = 0; i < 4; ++i) {
+            cum += v[i];
+            if (cum >= r) { b = lane * 4 + i; break; }
+        }
+    }
+    return __shfl_sync(0xffffffffu, b, src);
 }
 
 // One quad of the scan; the first quad of a vector starts the accumulators at -bound.
@@ -147,7 +180,8 @@ struct FlatCfg {
     static constexpr int kThreads = (NW + 1) * 32;
     static size_t smem_bytes(int cap) {
         return static_cast<size_t>(NS) * kTileBytes + static_cast<size_t>(QB) * M * 16 +
-               static_cast<size_t>(NW) * QB * cap * 8 + static_cast<size_t>(NW) * QB * 8 + 2 * NS * 8 + 128;
+               static_cast<size_t>(NW) * QB * cap * 8 + static_cast<size_t>(NW) * QB * 8 + 2 * NS * 8 +
+               static_cast<size_t>(QB) * (128 + 2) * 4 + 128;
     }
 };
 
@@ -162,6 +196,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
     int* bnd = cnt + NW * QB;
     uint64_t* full = reinterpret_cast<uint64_t*>(bnd + NW * QB);
     uint64_t* empty = full + NS;
+    int* hist = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(empty + NS) + 15) & ~uintptr_t(15));   // [QB][128]
+    int* hist_total = hist + QB * 128;                // [QB] candidates counted
+    int* hist_next = hist_total + QB;                 // [QB] count at which the bound is recomputed
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sb0 = min(blockIdx.x * a.sb_per_chunk, a.n_sb);
@@ -183,6 +220,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
     }
     for (int i = threadIdx.x; i < NW * QB * a.cap; i += blockDim.x) lists[i] = kEmptyKey;
     for (int i = threadIdx.x; i < NW * QB; i += blockDim.x) { cnt[i] = 0; bnd[i] = 127; }
+    for (int i = threadIdx.x; i < QB * 128; i += blockDim.x) hist[i] = 0;
+    for (int i = threadIdx.x; i < QB; i += blockDim.x) { hist_total[i] = 0; hist_next[i] = a.r; }
     __syncthreads();
 
     if (warp == NW) {
@@ -217,7 +256,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 #pragma unroll
         for (int j = 0; j < M; ++j) treg[j] = qtab[j];
     }
-    const int compact_at = min(a.cap - kSbVec, 2 * a.r);
+    const int halves = (a.cap < a.r + kSbVec) ? 2 : 1;
+    const int compact_at = min(a.cap - kSbVec / halves, 2 * a.r);
 
     // loop state kept in registers: this warp's superblock, its slot inside a stage, ring position
     uint32_t sb = sb0 + warp;
@@ -276,11 +316,37 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
                     }
                     const bool mine = alive && any_below(g);
                     if (alive && __any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
-                        if (mine) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi]);
+                        // small lists (cap < r + 256) take the superblock in two position-ordered halves
+                        const int before = *wl[qi].count;
                         __syncwarp();
-                        if (*wl[qi].count >= compact_at) {
-                            wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
-                            lbound[qi] = *wl[qi].bound;
+                        for (int half = 0; half < halves; ++half) {
+                            const bool my_turn = halves == 1 || (lane >> 4) == half;
+                            if (mine && my_turn)
+                                emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi], hist + qi * 128);
+                            __syncwarp();
+                            const int now = *wl[qi].count;
+                            if (half == halves - 1 || now >= compact_at) {
+                                // CTA-wide count of candidates; when it passes the next threshold this warp
+                                // re-derives the query's shared bound from the CTA histogram
+                                int total = 0;
+                                if (lane == 0) {
+                                    total = atomicAdd(hist_total + qi, now - before) + (now - before);
+                                    if (total < hist_next[qi]) total = -1;   // lane 0 alone decides (warp-uniform)
+                                }
+                                total = __shfl_sync(0xffffffffu, total, 0);
+                                if (total >= 0) {
+                                    const int hb = hist_bound(hist + qi * 128, a.r, lane);
+                                    if (lane == 0) {
+                                        hist_next[qi] = total + max(a.r / 4, 8);
+                                        if (hb < 127) atomicMin(a.shared_bound + qbase + qi, hb);
+                                    }
+                                    if (hb < gb[qi]) gb[qi] = hb;
+                                }
+                            }
+                            if (now >= compact_at) {
+                                wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
+                                lbound[qi] = *wl[qi].bound;
+                            }
                         }
                     }
                 }

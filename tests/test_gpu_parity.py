@@ -129,11 +129,14 @@ def test_flat_scan_degenerate_ties(qadc, oracle):
     n, m, r = 10000, 16, 100
     codes = np.zeros((n, m // 2), np.uint8)
     ix = flat_index(qadc, 128, m, synth.make_pq(np.random.default_rng(0), 128, m), codes, 1.0)
-    for val in (0, 5):
-        qt = np.full((2, 1, m, 16), val, np.int8)
-        ids, d, cnt = ix.scan_with_tables(np.zeros((2, 1), np.int32), qt, r)
-        assert np.all(cnt == r) and np.all(d == min(127, val * m))
-        assert np.array_equal(ids[0], np.arange(r, dtype=np.uint32))
+    for qb in (1, 2, 4):   # 4 queries per pass uses half-superblock candidate lists (two-pass emit)
+        ix.set_option("flat_qb", qb)
+        for val in (0, 5):
+            qt = np.full((5, 1, m, 16), val, np.int8)
+            ids, d, cnt = ix.scan_with_tables(np.zeros((5, 1), np.int32), qt, r)
+            assert np.all(cnt == r) and np.all(d == min(127, val * m))
+            for q in range(5):
+                assert np.array_equal(ids[q], np.arange(r, dtype=np.uint32))
     # nothing below 127 -> sentinels only (db_query_4.cpp:276)
     qt = np.full((1, 1, m, 16), 127, np.int8)
     ids, d, cnt = ix.scan_with_tables(np.zeros((1, 1), np.int32), qt, r)
