@@ -272,7 +272,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         if (rc) return rc == QADC_ENOMEM ? fail(ctx, rc, "scan kernel shared memory exceeds 227 KB") : rc;
     } else {
         const int cap = next_pow2(r + kSbVec);
-        const size_t smem = static_cast<size_t>(kNW) * cap * 8 + kNW * 8;
+        const size_t smem = static_cast<size_t>(kNW) * cap * 8 + kNW * 8 + (128 + 2) * 4 + 16;
         if (smem > kMaxSmem) return fail(ctx, QADC_EINVAL, "r too large for the IVF scan kernel");
         int chunks = std::max(1, std::min((ma + kNW - 1) / kNW, (2 * ctx->sm_count + nq - 1) / nq));
         const int ppc = (ma + chunks - 1) / chunks;

@@ -151,6 +151,26 @@ __device__ __forceinline__ void store_list(const WarpList& list, uint64_t* dst, 
 // the top r if d <= v.  Read with a volatile load so every tile sees recent updates.
 __device__ __forceinline__ int load_shared_bound(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
+// After a warp pushed `added` candidates: count them CTA-wide and, when the count passes the next
+// threshold, re-derive the query's shared bound from the CTA histogram.  Whole warp calls it;
+// returns the new bound (or 127 when nothing changed).
+__device__ __forceinline__ int hist_update(int* hist, int* hist_total, int* hist_next, int added, int r, int lane,
+                                           int* shared_bound) {
+    int total = 0;
+    if (lane == 0) {
+        total = atomicAdd(hist_total, added) + added;
+        if (total < *hist_next) total = -1;   // lane 0 alone decides (warp-uniform)
+    }
+    total = __shfl_sync(0xffffffffu, total, 0);
+    if (total < 0) return 127;
+    const int hb = hist_bound(hist, r, lane);
+    if (lane == 0) {
+        *hist_next = total + max(r / 4, 8);
+        if (hb < 127) atomicMin(shared_bound, hb);
+    }
+    return hb;
+}
+
 // ------------------------------------------------------------------------------------------
 // Flat scan: grid = (chunks along the database, query groups of QB).  NW consumer warps +
 // one producer warp per CTA; the producer streams tiles of NW superblocks through an NS-stage
@@ -317,31 +337,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
                     const bool mine = alive && any_below(g);
                     if (alive && __any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
                         // small lists (cap < r + 256) take the superblock in two position-ordered halves
-                        const int before = *wl[qi].count;
-                        __syncwarp();
                         for (int half = 0; half < halves; ++half) {
+                            const int before = *wl[qi].count;
+                            __syncwarp();
                             const bool my_turn = halves == 1 || (lane >> 4) == half;
                             if (mine && my_turn)
                                 emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi], hist + qi * 128);
                             __syncwarp();
                             const int now = *wl[qi].count;
-                            if (half == halves - 1 || now >= compact_at) {
+                            {
                                 // CTA-wide count of candidates; when it passes the next threshold this warp
                                 // re-derives the query's shared bound from the CTA histogram
-                                int total = 0;
-                                if (lane == 0) {
-                                    total = atomicAdd(hist_total + qi, now - before) + (now - before);
-                                    if (total < hist_next[qi]) total = -1;   // lane 0 alone decides (warp-uniform)
-                                }
-                                total = __shfl_sync(0xffffffffu, total, 0);
-                                if (total >= 0) {
-                                    const int hb = hist_bound(hist + qi * 128, a.r, lane);
-                                    if (lane == 0) {
-                                        hist_next[qi] = total + max(a.r / 4, 8);
-                                        if (hb < 127) atomicMin(a.shared_bound + qbase + qi, hb);
-                                    }
-                                    if (hb < gb[qi]) gb[qi] = hb;
-                                }
+                                const int hb = hist_update(hist + qi * 128, hist_total + qi, hist_next + qi, now - before,
+                                                           a.r, lane, a.shared_bound + qbase + qi);
+                                if (hb < gb[qi]) gb[qi] = hb;
                             }
                             if (now >= compact_at) {
                                 wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
@@ -430,10 +439,15 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
     const int a0 = blockIdx.x * a.probes_per_chunk, a1 = min(a0 + a.probes_per_chunk, a.ma);
     const PipeK pk = a.k;
 
+    int* hist = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(bnd + NW) + 15) & ~uintptr_t(15));   // [128]
+    int* hist_total = hist + 128;
+    int* hist_next = hist_total + 1;
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x == 0) { *hist_total = 0; *hist_next = a.r; }
     WarpList wl{lists + static_cast<size_t>(warp) * a.cap, cnt + warp, bnd + warp};
     for (int i = lane; i < a.cap; i += 32) wl.keys[i] = kEmptyKey;
     if (lane == 0) { *wl.count = 0; *wl.bound = 127; }
-    __syncwarp();
+    __syncthreads();
     const int compact_at = min(a.cap - kSbVec, 2 * a.r);
     int* sbound = a.shared_bound + q;
 
@@ -461,9 +475,16 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
                 const uint4 tq[4] = {treg[4 * qd], treg[4 * qd + 1], treg[4 * qd + 2], treg[4 * qd + 3]};
                 lut_quad(w[qd], tq, g, pk);
             }
-            if (any_below(g)) emit_candidates(g, bound, sb * kSbVec + lane * 8, size, pos_base, ar, wl);
-            __syncwarp();
-            if (*wl.count >= compact_at) wl.compact(a.cap, a.r, lane, sbound);
+            const bool mine = any_below(g);
+            if (__any_sync(0xffffffffu, mine)) {
+                const int before = *wl.count;
+                __syncwarp();
+                if (mine) emit_candidates(g, bound, sb * kSbVec + lane * 8, size, pos_base, ar, wl, hist);
+                __syncwarp();
+                const int now = *wl.count;
+                hist_update(hist, hist_total, hist_next, now - before, a.r, lane, sbound);
+                if (now >= compact_at) wl.compact(a.cap, a.r, lane, sbound);
+            }
         }
     }
     wl.compact(a.cap, a.r, lane, sbound);
