@@ -204,8 +204,15 @@ int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     const int tile_sb = pl.nw;
     const int qgroups = (nq + pl.qb - 1) / pl.qb;
     long chunks = ctx->opt_flat_chunks;
-    // ~16 waves of CTAs: the tail of the last wave costs at most a few percent
-    if (chunks <= 0) chunks = std::max(1, (16 * ctx->sm_count + qgroups - 1) / qgroups);
+    // up to ~16 waves of CTAs (the tail of the last wave then costs a few percent), fewer for small
+    // shards so that a CTA still streams >= ~600 tiles and its ~20 us of setup/merge stays small
+    if (chunks <= 0) {
+        const long n_tiles = (n_sb + tile_sb - 1) / tile_sb;
+        int waves = 16;
+        while (waves > 1 && n_tiles / std::max<long>(1, (static_cast<long>(waves) * ctx->sm_count + qgroups - 1) / qgroups) < 600)
+            waves >>= 1;
+        chunks = std::max<long>(1, (static_cast<long>(waves) * ctx->sm_count + qgroups - 1) / qgroups);
+    }
     const long max_chunks = std::max<long>(1, (n_sb + tile_sb - 1) / tile_sb);
     chunks = std::min(chunks, max_chunks);
     uint32_t spc = static_cast<uint32_t>((n_sb + chunks - 1) / chunks);
