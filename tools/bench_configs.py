@@ -78,7 +78,27 @@ def config3(nq=10000):
     ix.close()
 
 
+def config5(nq=2000, n=20 * 10 ** 6):
+    """Deep1B-shaped IVF-65536, 96-d, 16x4 (sq_dim 6), nprobe 128 — at 20M vectors on one GPU."""
+    rng = np.random.default_rng(1239)
+    dim, m, K, ma = 96, 16, 65536, 128
+    cb = rng.standard_normal((m, 16, dim // m)).astype(np.float32)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    sizes = rng.multinomial(n, np.ones(K) / K)
+    offsets = np.zeros(K + 1, np.int64); offsets[1:] = np.cumsum(sizes)
+    labels = rng.permutation(n).astype(np.uint32)
+    codes = rng.integers(0, 256, (n, m // 2), dtype=np.uint8)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    t0 = time.perf_counter()
+    ix = qadc_b200.Index(0); ix.set_pq(dim, m, cb); ix.set_coarse(cents); ix.load_ivf(codes, labels, offsets, 0.01)
+    print("load_ivf seconds", time.perf_counter() - t0, flush=True)
+    db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=0.01, offsets=offsets,
+              scanned_per_query=float(ma * n / K))
+    run("5 (scaled to 20M): Deep1B-shaped IVF-65536 16x4, nprobe 128", ix, db, q, ma, check=3)
+    ix.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["1", "2", "3"]
     for w in which:
-        {"1": config1, "2": config2, "3": config3}[w]()
+        {"1": config1, "2": config2, "3": config3, "5": config5}[w]()
