@@ -99,12 +99,8 @@ __device__ __forceinline__ int hist_bound(const int* hist, int r, int lane) {
     const int src = __ffs(reached) - 1;
     int b = 127;
     if (lane == src) {
-        int cum = incl - mine;
-        const int v[4] = {c.x, c.y, c.z, c.w};
-        for (int i = 0; i < 4; ++i) {
-            cum += v[i];
-            if (cum >= r) { b = lane * 4 + i; break; }
-        }
+        const int c0 = incl - mine + c.x, c1 = c0 + c.y, c2 = c1 + c.z;
+        b = lane * 4 + (c0 >= r ? 0 : (c1 >= r ? 1 : (c2 >= r ? 2 : 3)));
     }
     return __shfl_sync(0xffffffffu, b, src);
 }
@@ -198,27 +194,28 @@ struct FlatCfg {
     static constexpr int kTileBytes = NW * kSbBytes;
     static constexpr bool kRegTab = (QB == 1 && M == 16);
     static constexpr int kThreads = (NW + 1) * 32;
-    static size_t smem_bytes(int cap) {
-        return static_cast<size_t>(NS) * kTileBytes + static_cast<size_t>(QB) * M * 16 +
-               static_cast<size_t>(NW) * QB * cap * 8 + static_cast<size_t>(NW) * QB * 8 + 2 * NS * 8 +
-               static_cast<size_t>(QB) * (128 + 2) * 4 + 128;
-    }
+    // tiles | tables | full/empty barriers | histogram + counters | list counts/bounds, rounded to 16 bytes
+    static constexpr int kFixedBytes =
+        ((NS * kTileBytes + QB * M * 16 + 2 * NS * 8 + QB * (128 + 2) * 4 + NW * QB * 8) + 15) / 16 * 16;
+    static size_t smem_bytes(int cap) { return static_cast<size_t>(kFixedBytes) + static_cast<size_t>(NW) * QB * cap * 8; }
 };
 
 template <int M, int QB, int NW, int NS>
 __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatScanArgs a) {
     using Cfg = FlatCfg<M, QB, NW, NS>;
     extern __shared__ __align__(128) uint8_t smem[];
+    // every small array sits at a compile-time offset (no address registers live across the
+    // lookup loop); only the candidate lists, whose size depends on `cap`, come last
     uint8_t* tiles = smem;
     uint4* qtab = reinterpret_cast<uint4*>(tiles + static_cast<size_t>(NS) * Cfg::kTileBytes);   // [QB][M]
-    uint64_t* lists = reinterpret_cast<uint64_t*>(qtab + QB * M);                                 // [NW][QB][cap]
-    int* cnt = reinterpret_cast<int*>(lists + static_cast<size_t>(NW) * QB * a.cap);              // [NW][QB]
-    int* bnd = cnt + NW * QB;
-    uint64_t* full = reinterpret_cast<uint64_t*>(bnd + NW * QB);
+    uint64_t* full = reinterpret_cast<uint64_t*>(qtab + QB * M);
     uint64_t* empty = full + NS;
-    int* hist = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(empty + NS) + 15) & ~uintptr_t(15));   // [QB][128]
+    int* hist = reinterpret_cast<int*>(empty + NS);   // [QB][128] candidate histogram (16-byte aligned)
     int* hist_total = hist + QB * 128;                // [QB] candidates counted
     int* hist_next = hist_total + QB;                 // [QB] count at which the bound is recomputed
+    int* cnt = hist_next + QB;                        // [NW][QB]
+    int* bnd = cnt + NW * QB;
+    uint64_t* lists = reinterpret_cast<uint64_t*>(tiles + Cfg::kFixedBytes);                     // [NW][QB][cap]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sb0 = min(blockIdx.x * a.sb_per_chunk, a.n_sb);
@@ -284,7 +281,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
     uint32_t n_left = (sb < sb1) ? (sb1 - sb + NW - 1) / NW : 0;   // tiles in which this warp has a superblock
     uint32_t slot = smem_u32(tiles) + warp * Cfg::kSbBytes + lane * 16;
     uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
-    pin(slot); pin(full_a); pin(empty_a); pin(sb); pin(n_left);
+    pin(slot); pin(sb); pin(n_left);   // full_a / empty_a are compile-time offsets from the shared-memory base
     uint32_t stage = 0, phase = 0;
     int lbound[QB], gb[QB];   // strict local bound, shared bound (refreshed once per ring revolution)
 #pragma unroll
@@ -356,6 +353,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
                                 wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
                                 lbound[qi] = *wl[qi].bound;
                             }
+                        }
+                        if constexpr (Cfg::kRegTab) {
+                            // the 64 table registers are re-read from shared memory here, so they need not
+                            // stay live (or be spilled) across the rare path above
+#pragma unroll
+                            for (int j = 0; j < M; ++j) treg[j] = qtab[j];
                         }
                     }
                 }
