@@ -127,6 +127,24 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_per_launch(n_local, nq, qb):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch from the committed `ncu --set full`
+    capture (profiles/r01_scan_flat_16x4_1B_ncu_full.txt), which was taken on exactly the default workload
+    (1e9 local vectors, 16 queries per step, 1 query per pass); None for any other configuration."""
+    if (n_local, nq, qb) != (10 ** 9, 16, 1):
+        return None
+    p = os.path.join(ROOT, "profiles", "r01_scan_flat_16x4_1B_ncu_full.txt")
+    try:
+        vals = {}
+        for line in open(p):
+            t = line.split()
+            if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                vals[t[0]] = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[t[2]]
+        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(n_cpu, nq, threads, steps, warmup, log=None):
     """The reference's own CPU path (oracle/_ref) on vectors [0, n_cpu) of the same database."""
@@ -348,7 +366,7 @@ def run_ours(args):
             "verify": verify,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "scan_flat_kernel",
+                         "traffic": ncu_traffic_per_launch(n_local, nq, qb_used), "peak_source": peak_src, "kernel": "scan_flat_kernel",
                          "kernel_ms": t_scan * 1e3, "kernel_share_of_step": t_scan * 1e3 / ms_step,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": passes * n_local * CODE_BYTES},
