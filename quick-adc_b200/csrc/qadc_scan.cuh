@@ -514,26 +514,32 @@ template <int M>
 __global__ void __launch_bounds__(256) prefix_hist_kernel(const PrefixBoundArgs a) {
     constexpr int CS = M / 2;
     __shared__ unsigned int hist[128];
-    __shared__ int8_t tab[M * 16];
-    const int split = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+    __shared__ __align__(16) int8_t tab[8][M * 16];   // one table per warp
+    const int split = blockIdx.x, q = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 128) hist[tid] = 0;
-    for (int ar = 0; ar < a.ma; ++ar) {
+    __syncthreads();
+    // inverted lists: warps take probes round-robin and lanes stride over that probe's short prefix;
+    // a flat database (one probe) is strided by the whole CTA
+    const bool single = a.ma == 1;
+    const uint32_t vstep = single ? 256u : 32u, vfirst = single ? tid : lane;
+    for (int ar = single ? 0 : warp; ar < a.ma; ar += single ? 1 : 8) {
         const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
         const uint32_t n = a.start_size[p];
         const uint32_t v0 = static_cast<uint32_t>(static_cast<uint64_t>(n) * split / a.nsplit);
         const uint32_t v1 = static_cast<uint32_t>(static_cast<uint64_t>(n) * (split + 1) / a.nsplit);
-        if (v1 == v0) continue;
-        __syncthreads();
-        for (int i = tid; i < M * 16; i += 256) tab[i] = a.qtabs[(static_cast<size_t>(q) * a.ma + ar) * M * 16 + i];
-        __syncthreads();
+        if (v1 == v0) continue;   // warp-uniform
+        __syncwarp();
+        const uint4* tsrc = reinterpret_cast<const uint4*>(a.qtabs + (static_cast<size_t>(q) * a.ma + ar) * M * 16);
+        for (int i = lane; i < M; i += 32) reinterpret_cast<uint4*>(tab[warp])[i] = __ldg(tsrc + i);
+        __syncwarp();
         const uint8_t* codes = a.starts + a.start_off[p] * CS;
-        for (uint32_t v = v0 + tid; v < v1; v += 256) {
+        for (uint32_t v = v0 + vfirst; v < v1; v += vstep) {
             const uint8_t* c = codes + static_cast<size_t>(v) * CS;
             int sum = 0;
 #pragma unroll
             for (int b = 0; b < CS; ++b) {
                 const uint32_t byte = c[b];
-                sum += tab[(2 * b) * 16 + (byte & 15u)] + tab[(2 * b + 1) * 16 + (byte >> 4)];
+                sum += tab[warp][(2 * b) * 16 + (byte & 15u)] + tab[warp][(2 * b + 1) * 16 + (byte >> 4)];
             }
             atomicAdd(&hist[min(sum, 127)], 1u);
         }

@@ -152,9 +152,19 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ q
         const float* b = codebooks + static_cast<size_t>(e) * dsq;   // (j*16 + c) * dsq
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int bl = 0; bl < blocks; ++bl) {
+            float av[8], bv[8];
+            if ((dsq & 3) == 0) {   // 16-byte aligned rows: two 128-bit loads each (same values, same order)
+                const float4 a0 = *reinterpret_cast<const float4*>(a + bl * 8), a1 = *reinterpret_cast<const float4*>(a + bl * 8 + 4);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + bl * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + bl * 8 + 4));
+                av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+                bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+            } else {
+#pragma unroll
+                for (int l = 0; l < 8; ++l) { av[l] = a[bl * 8 + l]; bv[l] = __ldg(b + bl * 8 + l); }
+            }
 #pragma unroll
             for (int l = 0; l < 8; ++l) {
-                const float diff = __fsub_rn(a[bl * 8 + l], __ldg(b + bl * 8 + l));
+                const float diff = __fsub_rn(av[l], bv[l]);
                 acc[l] = __fmaf_rn(diff, diff, acc[l]);
             }
         }
