@@ -376,7 +376,7 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         QCK(cudaGetLastError());
     } else {
         int nsplit = 1;
-        if (flat) nsplit = static_cast<int>(std::min<uint32_t>(128, std::max<uint32_t>(1, ctx->max_start / 4096)));
+        if (flat) nsplit = static_cast<int>(std::min<uint32_t>(64, std::max<uint32_t>(1, ctx->max_start / 16384)));
         ENSURE(ctx->b_plists, static_cast<size_t>(nq) * nsplit * r * 8);
         pa.nsplit = nsplit; pa.lists = ctx->b_plists.as<uint64_t>();
         dim3 pgrid(nsplit, nq);
