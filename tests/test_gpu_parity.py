@@ -547,3 +547,31 @@ def test_gpu_ivf_assign_encode(qadc, oracle):
     resid = (x - cents[assign]).astype(np.float32)
     assert np.array_equal(codes, oracle.encode(resid, m, cb))
     ix.close()
+
+
+@pytest.mark.parametrize("r", [1, 2, 1024])
+def test_extreme_r(qadc, oracle, r):
+    """r = 1 and the largest supported r (1024), flat and IVF, against the oracle."""
+    rng = np.random.default_rng(500 + r)
+    dim, m, n, nq = 128, 16, 40000, 5
+    cb = synth.make_pq(rng, dim, m)
+    codes = synth.make_codes(rng, n, m)
+    q = synth.make_queries(rng, nq, dim)
+    keep = 0.1
+    ix = flat_index(qadc, dim, m, cb, codes, keep)
+    ids, d, cnt = ix.search(q, 1, r)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=keep, offsets=np.array([0, n], np.int64)),
+                        q, 1, r, want_tables=False)
+    assert np.array_equal(ids, exp["ids"]) and np.array_equal(d, exp["d"]) and np.array_equal(cnt, exp["count"])
+    ix.close()
+    K, ma = 16, 6
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m)
+    ix = ivf_index(qadc, dim, m, cb, cents, codes, labels, offsets, keep)
+    ids, d, cnt = ix.search(q, ma, r)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=keep,
+                             offsets=offsets), q, ma, r, want_tables=False)
+    assert np.array_equal(ids, exp["ids"]) and np.array_equal(d, exp["d"]) and np.array_equal(cnt, exp["count"])
+    with pytest.raises(qadc.QadcError):
+        ix.search(q, ma, 1025)   # r > 1024 is refused
+    ix.close()
