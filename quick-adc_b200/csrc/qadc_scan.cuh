@@ -192,7 +192,7 @@ struct FlatCfg {
     static constexpr int kQuads = M / 4;
     static constexpr int kSbBytes = M * 128;
     static constexpr int kTileBytes = NW * kSbBytes;
-    static constexpr bool kRegTab = (QB == 1 && M == 16);
+    static constexpr bool kRegTab = (QB == 1 && M == 16 && NW <= 16);   // more warps: tables stay in shared memory
     static constexpr int kThreads = (NW + 1) * 32;
     // tiles | tables | full/empty barriers | histogram + counters | list counts/bounds, rounded to 16 bytes
     static constexpr int kFixedBytes =
