@@ -15,11 +15,17 @@
 
 #include <cstring>
 
+#include "../../include/qadc_b200.h"
 #include "quantizers.hpp"
 
 struct base_db {
     std::unique_ptr<base_pq> pq;
     virtual ~base_db() = default;
+    // base_db::add_vectors (databases.hpp:57-58): encode `count` vectors and store them with ids
+    // labels_offset.. ; the PQ encoding (and, for inverted lists, the coarse assignment) runs on
+    // the GPU through `enc`, a context prepared with qadc_set_pq (+ qadc_set_coarse).
+    virtual void add_vectors(qadc_ctx* enc, const float* vectors, unsigned count, unsigned labels_offset) = 0;
+    virtual void save(std::ostream& os) const = 0;
     virtual int partition_count() const = 0;
     virtual void get_partition(int part_i, const std::uint8_t*& codes, unsigned*& labels, unsigned& size) const = 0;
     virtual void free_partition(int part_i) = 0;
@@ -41,6 +47,19 @@ struct flat_db : base_db {
         codes_count = 0;
     }
     void print(std::ostream& os) const override { os << "Flat DB" << std::endl; pq->print(os); }
+    // flat_db::add_vectors (databases.hpp:136-156): codes are stored at positions labels_offset..
+    void add_vectors(qadc_ctx* enc, const float* vectors, unsigned count, unsigned labels_offset) override {
+        const size_t cs = pq->code_size();
+        if (labels_offset + count > codes_count) {
+            codes_count = labels_offset + count;
+            codes.resize(static_cast<size_t>(codes_count) * cs);
+        }
+        if (qadc_encode(enc, vectors, count, nullptr, codes.data() + static_cast<size_t>(labels_offset) * cs)) {
+            std::cerr << "qadc_encode: " << qadc_last_error(enc) << std::endl;
+            std::exit(1);
+        }
+    }
+    void save(std::ostream& os) const override;
 };
 
 struct index_db : base_db {
@@ -63,7 +82,53 @@ struct index_db : base_db {
         os << "Indexed DB (partitions=" << part_count << ")" << std::endl;
         pq->print(os);
     }
+    // index_db::add_vectors (databases.hpp:270-298): nearest cell, code of the residual, dispatch
+    // into the cell's list with label vec_i + labels_offset.
+    void add_vectors(qadc_ctx* enc, const float* vectors, unsigned count, unsigned labels_offset) override {
+        const size_t cs = pq->code_size();
+        std::vector<std::int32_t> assign(count);
+        std::vector<std::uint8_t> buf(static_cast<size_t>(count) * cs);
+        if (qadc_encode(enc, vectors, count, assign.data(), buf.data())) {
+            std::cerr << "qadc_encode: " << qadc_last_error(enc) << std::endl;
+            std::exit(1);
+        }
+        for (unsigned v = 0; v < count; ++v) {
+            const int p = assign[v];
+            partitions[p].insert(partitions[p].end(), buf.begin() + v * cs, buf.begin() + (v + 1) * cs);
+            labels[p].push_back(v + labels_offset);
+        }
+    }
+    void save(std::ostream& os) const override;
 };
+
+inline void qdb_write_header(std::ostream& os, const base_pq& pq, int kind, int K) {
+    const opq* o = dynamic_cast<const opq*>(&pq);
+    const std::int32_t h[6] = {kind, o ? 1 : 0, pq.dim, pq.sq_count, pq.sq_bits, K};
+    os.write("QADCDB1\0", 8);
+    os.write(reinterpret_cast<const char*>(h), sizeof(h));
+    os.write(reinterpret_cast<const char*>(pq.centroids_flat.data()), pq.centroids_flat.size() * sizeof(float));
+    if (o) os.write(reinterpret_cast<const char*>(o->rotation.data()), o->rotation.size() * sizeof(float));
+}
+
+inline void flat_db::save(std::ostream& os) const {
+    qdb_write_header(os, *pq, 0, 1);
+    const std::uint64_t n = codes_count;
+    os.write(reinterpret_cast<const char*>(&n), 8);
+    os.write(reinterpret_cast<const char*>(codes.data()), codes.size());
+}
+
+inline void index_db::save(std::ostream& os) const {
+    qdb_write_header(os, *pq, 1, part_count);
+    os.write(reinterpret_cast<const char*>(centroids.data()), centroids.size() * sizeof(float));
+    for (int p = 0; p < part_count; ++p) {
+        const std::uint64_t n = labels[p].size();
+        os.write(reinterpret_cast<const char*>(&n), 8);
+    }
+    for (int p = 0; p < part_count; ++p) {
+        os.write(reinterpret_cast<const char*>(partitions[p].data()), partitions[p].size());
+        os.write(reinterpret_cast<const char*>(labels[p].data()), labels[p].size() * 4);
+    }
+}
 
 inline std::unique_ptr<base_db> load_qdb(const char* filename) {
     std::ifstream in(filename, std::ios::binary);

@@ -107,3 +107,57 @@ def test_cli_ivf_matches_oracle(cli, oracle, tmp_path):
     for qi in range(nq):
         for v in np.unique(d[qi]):
             assert set(ids[qi][d[qi] == v].tolist()) == set(exp["ids"][qi][exp["d"][qi] == v].tolist())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ivf", [False, True])
+def test_db_build_then_query(cli, oracle, tmp_path, ivf):
+    """floats -> db_build (GPU encoder, the reference's flatdb_create/db_add chain) -> db_query_4:
+    same results as the oracle's encoder + search on the same inputs."""
+    from qadc_b200 import dbfile
+    rng = np.random.default_rng(33 + ivf)
+    dim, m, n, nq, r, K, ma = 64, 16, 12000, 10, 20, 20, 4
+    cb = synth.make_pq(rng, dim, m)
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    q = synth.make_queries(rng, nq, dim)
+    dbfile.write_pq_data(tmp_path / "q.pq.data", dim, m, cb)
+    dbfile.write_vecs(tmp_path / "base.fvecs", base)
+    dbfile.write_vecs(tmp_path / "q.fvecs", q)
+    cmd = [os.path.join(HOST, "db_build")]
+    if ivf:
+        cents = base[rng.permutation(n)[:K]].copy()
+        dbfile.write_vecs(tmp_path / "cents.fvecs", cents)
+        cmd += ["-c", str(tmp_path / "cents.fvecs")]
+    cmd += [str(tmp_path / "q.pq.data"), str(tmp_path / "base.fvecs"), str(tmp_path / "db.qdb")]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert ("Indexed DB (partitions=20)" if ivf else "Flat DB") in p.stderr and "pq (dim=64, sq=16x4)" in p.stderr
+    # expected database built with the oracle: assignment, residual codes, insertion order per cell
+    keep = np.float32(10 * 0.01)
+    if ivf:
+        assign, _ = oracle.coarse_assign(base, cents, 1)
+        assign = assign[:, 0]
+        codes_all = oracle.encode((base - cents[assign]).astype(np.float32), m, cb)
+        order = np.argsort(assign, kind="stable")
+        offsets = np.zeros(K + 1, np.int64)
+        offsets[1:] = np.cumsum(np.bincount(assign, minlength=K))
+        db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes_all[order], labels=order.astype(np.uint32),
+                  keep=keep, offsets=offsets)
+        exp = oracle.search(db, q, ma, r, want_tables=False)
+    else:
+        db = dict(dim=dim, m=m, codebooks=cb, codes=oracle.encode(base, m, cb), keep=keep, offsets=np.array([0, n], np.int64))
+        exp = oracle.search(db, q, 1, r, want_tables=False)
+    gt = exp["ids"][:, :1].astype(np.int32).copy()
+    dbfile.write_vecs(tmp_path / "gt.ivecs", gt)
+    out = tmp_path / "res.bin"
+    p = subprocess.run([cli, "-r", str(r), "-m", str(ma if ivf else 1), "-k", "10", "-b", "0", "-o", str(out),
+                        str(tmp_path / "db.qdb"), str(tmp_path / "q.fvecs"), str(tmp_path / "gt.ivecs")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert float(p.stdout.strip().splitlines()[1].split(",")[1]) == 1.0
+    raw = np.fromfile(out, np.uint8).reshape(nq, r * 5)
+    ids, d = raw[:, :4 * r].copy().view(np.uint32), raw[:, 4 * r:].view(np.int8)
+    assert np.array_equal(d, exp["d"])
+    for qi in range(nq):
+        for v in np.unique(d[qi]):
+            assert set(ids[qi][d[qi] == v].tolist()) == set(exp["ids"][qi][exp["d"][qi] == v].tolist())
