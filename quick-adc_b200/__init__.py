@@ -41,12 +41,14 @@ def load_library(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing and os.path.exists("/usr/local/cuda/bin/nvcc"):
+    # Build only when the library is absent (never when merely older than the sources: several
+    # ranks may import concurrently, and file times do not survive a copy to the GPU box);
+    # __graft_entry__.build() / quick-adc_b200/build.py rebuild explicitly.
+    if build_if_missing and not os.path.exists(LIB_PATH) and os.path.exists(_build.NVCC):
         try:
-            _build.build()
-        except Exception as e:  # a stale .so is still better than none; a missing one is fatal below
-            if not os.path.exists(LIB_PATH):
-                raise RuntimeError(f"cannot build libqadc_b200.so: {e}")
+            _build.build(force=True)
+        except Exception as e:
+            raise RuntimeError(f"cannot build libqadc_b200.so: {e}")
     path = os.environ.get("QADC_LIB", LIB_PATH)   # development knob: an alternative build of the same library
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
