@@ -25,6 +25,7 @@ struct DevBuf {
 
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kNW = 8;
+constexpr int kMaxBatch = 32768;   // queries per internal sub-batch of a search call
 #ifndef QADC_NW1
 #define QADC_NW1 15  // consumer warps of the single-query 16x4 flat kernel
 #endif
@@ -655,12 +656,17 @@ int qadc_search_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, in
     if (rc) return rc;
     QCK(cudaSetDevice(ctx->device));
     ctx->launches = 0;
-    rc = tables_device(ctx, d_queries, nq, ma, r, nullptr, true);
-    if (rc) return rc;
-    QCK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    rc = scan_device(ctx, ctx->b_assign.as<int32_t>(), ctx->b_qtables.as<int8_t>(), nq, ma, r, d_ids, d_dists,
-                     d_counts, d_keys);
-    if (rc) return rc;
+    // sub-batches keep every grid dimension below 65 536 and the per-batch scratch bounded
+    for (int q0 = 0; q0 < nq; q0 += kMaxBatch) {
+        const int n = std::min(kMaxBatch, nq - q0);
+        rc = tables_device(ctx, d_queries + static_cast<size_t>(q0) * ctx->dim, n, ma, r, nullptr, q0 == 0);
+        if (rc) return rc;
+        if (q0 == 0) QCK(cudaEventRecord(ctx->ev[3], ctx->stream));
+        rc = scan_device(ctx, ctx->b_assign.as<int32_t>(), ctx->b_qtables.as<int8_t>(), n, ma, r,
+                         d_ids + static_cast<size_t>(q0) * r, d_dists + static_cast<size_t>(q0) * r, d_counts + q0,
+                         d_keys ? d_keys + static_cast<size_t>(q0) * r : nullptr);
+        if (rc) return rc;
+    }
     QCK(cudaEventRecord(ctx->ev[4], ctx->stream));
     QCK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return QADC_OK;
@@ -741,6 +747,7 @@ int qadc_build_tables(qadc_ctx* ctx, const float* queries, int nq, int ma, int r
                       int32_t* out_assign, float* out_tables, float* out_qmin, float* out_qmax, int8_t* out_qtables) {
     int rc = check_search_args(ctx, nq, ma, r);
     if (rc) return rc;
+    if (nq > kMaxBatch) return fail(ctx, QADC_EINVAL, "parity entry points take at most 32768 queries per call");
     if (!queries) return fail(ctx, QADC_EINVAL, "queries is null");
     QCK(cudaSetDevice(ctx->device));
     const size_t nqa = static_cast<size_t>(nq) * ma, td = static_cast<size_t>(ctx->m) * 16;
@@ -768,6 +775,7 @@ int qadc_scan_with_tables(qadc_ctx* ctx, const int32_t* assign, const int8_t* qt
                           uint32_t* out_ids, int8_t* out_dists, int32_t* out_counts) {
     int rc = check_search_args(ctx, nq, ma, r);
     if (rc) return rc;
+    if (nq > kMaxBatch) return fail(ctx, QADC_EINVAL, "parity entry points take at most 32768 queries per call");
     if (!assign || !qtables || !out_ids || !out_dists) return fail(ctx, QADC_EINVAL, "null buffer");
     const size_t nqa = static_cast<size_t>(nq) * ma, td = static_cast<size_t>(ctx->m) * 16, nr = static_cast<size_t>(nq) * r;
     for (size_t i = 0; i < nqa * td; ++i)

@@ -575,3 +575,19 @@ def test_extreme_r(qadc, oracle, r):
     with pytest.raises(qadc.QadcError):
         ix.search(q, ma, 1025)   # r > 1024 is refused
     ix.close()
+
+
+def test_search_more_queries_than_one_sub_batch(qadc, oracle):
+    """40 000 queries in one call (internally split into sub-batches of 32 768)."""
+    rng = np.random.default_rng(4242)
+    dim, m, n, nq, r = 128, 16, 20000, 40000, 10
+    cb = synth.make_pq(rng, dim, m)
+    codes = synth.make_codes(rng, n, m)
+    q = synth.make_queries(rng, nq, dim)
+    ix = flat_index(qadc, dim, m, cb, codes, 0.05)
+    ids, d, cnt = ix.search(q, 1, r)
+    sel = np.array([0, 1, 32767, 32768, 32769, 39999])
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=0.05, offsets=np.array([0, n], np.int64)),
+                        q[sel], 1, r, want_tables=False)
+    assert np.array_equal(ids[sel], exp["ids"]) and np.array_equal(d[sel], exp["d"]) and np.array_equal(cnt[sel], exp["count"])
+    ix.close()
