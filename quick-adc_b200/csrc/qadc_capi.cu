@@ -177,7 +177,7 @@ const FlatVariant kFlatVariants[] = {
     QADC_FLAT_VARIANT(16, 2, 15, 3), QADC_FLAT_VARIANT(16, 2, 8, 4),
     QADC_FLAT_VARIANT(16, 4, 15, 3), QADC_FLAT_VARIANT(16, 4, 8, 4),
     QADC_FLAT_VARIANT(32, 1, 15, 3), QADC_FLAT_VARIANT(32, 1, 8, 4),
-    QADC_FLAT_VARIANT(32, 2, 8, 4),
+    QADC_FLAT_VARIANT(32, 2, 15, 2), QADC_FLAT_VARIANT(32, 2, 8, 4),
 };
 
 struct FlatPlan { const FlatVariant* v; int qb, nw, chunks, cap; uint32_t sb_per_chunk; };
