@@ -591,3 +591,38 @@ def test_search_more_queries_than_one_sub_batch(qadc, oracle):
                         q[sel], 1, r, want_tables=False)
     assert np.array_equal(ids[sel], exp["ids"]) and np.array_equal(d[sel], exp["d"]) and np.array_equal(cnt[sel], exp["count"])
     ix.close()
+
+
+def test_recall_at_100_matches_reference(qadc, oracle, ref):
+    """Recall@100 (recall.hpp:45-54 with t = 1: the true nearest neighbour is among the returned
+    ids) of the CUDA path vs the unmodified reference on the same encoded IVF database."""
+    rng = np.random.default_rng(77)
+    dim, m, n, K, ma, nq, r = 128, 16, 30000, 64, 8, 200, 100
+    base = rng.standard_normal((n, dim)).astype(np.float32)
+    cents = base[rng.permutation(n)[:K]].copy()
+    # codebooks drawn from residual sub-vectors so that codes are meaningful
+    assign, _ = oracle.coarse_assign(base, cents, 1)
+    resid = (base - cents[assign[:, 0]]).astype(np.float32)
+    cb = np.stack([resid[rng.permutation(n)[:16], j * 8:(j + 1) * 8] for j in range(m)]).astype(np.float32)
+    ix = qadc.Index(0)
+    ix.set_pq(dim, m, cb)
+    ix.set_coarse(cents)
+    codes, a = ix.encode(base)                                   # GPU encoder == reference encoder (golden test)
+    order = np.argsort(a, kind="stable")
+    offsets = np.zeros(K + 1, np.int64)
+    offsets[1:] = np.cumsum(np.bincount(a, minlength=K))
+    codes_s, labels = codes[order], order.astype(np.uint32)
+    truth = rng.integers(0, n, nq)
+    q = (base[truth] + 0.05 * rng.standard_normal((nq, dim))).astype(np.float32)
+    gt = np.argmin(((q[:, None, :] - base[None, :, :]) ** 2).sum(-1), axis=1) if n * nq * dim < 2e9 else truth
+    keep = 0.05
+    ix.load_ivf(codes_s, labels, offsets, keep)
+    ids, d, cnt = ix.search(q, ma, r)
+    h = ref.ivf(dim, m, cb, cents, codes_s, labels, offsets)
+    h.prepare(keep)
+    res = h.search(q, ma, r, nthreads=4)
+    h.close()
+    rec_gpu = np.mean([gt[i] in ids[i][:cnt[i]] for i in range(nq)])
+    rec_ref = np.mean([gt[i] in res["keys"][i][:res["sizes"][i]] for i in range(nq)])
+    assert rec_gpu >= 0.5 and abs(rec_gpu - rec_ref) <= 0.02, (rec_gpu, rec_ref)
+    ix.close()
