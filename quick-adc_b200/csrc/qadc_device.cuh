@@ -191,8 +191,10 @@ struct PipeK {
 // selector of vectors 4..7 = upper half of the word.  With QADC_SHIFT_FMA the shift is a
 // multiply-high by 2^16 (s2) on the FMA pipe instead of SHF on the ALU pipe.
 __device__ __forceinline__ uint32_t hi16(uint32_t w, const PipeK& k) {
-#ifdef QADC_SHIFT_FMA
+#if defined(QADC_SHIFT_FMA)
     return __umulhi(w, k.s2);
+#elif defined(QADC_SHIFT_WIDE)
+    return static_cast<uint32_t>((static_cast<uint64_t>(w) * k.s2) >> 32);   // IMAD.WIDE.U32, upper word
 #else
     return w >> 16;
 #endif
