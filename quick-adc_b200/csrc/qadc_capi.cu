@@ -436,16 +436,25 @@ int qadc_create(int device, void* stream, qadc_ctx** out) {
     qadc_ctx* c = new qadc_ctx;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    ctx = c;
-    if (stream) c->stream = static_cast<cudaStream_t>(stream);
-    else { QCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-    for (auto& ev : c->ev) QCK(cudaEventCreate(&ev));
-    for (auto& ev : c->ev_scan0) QCK(cudaEventCreate(&ev));
-    for (auto& ev : c->ev_scan1) QCK(cudaEventCreate(&ev));
-    QCK(cudaMalloc(&c->d_err, sizeof(int)));
-    QCK(cudaMemset(c->d_err, 0, sizeof(int)));
-    QCK(cudaMallocHost(&c->h_err, sizeof(int)));
-    *c->h_err = 0;
+    auto init = [&]() -> int {
+        qadc_ctx* ctx = c;   // errors are reported on the new context, copied out below
+        if (stream) c->stream = static_cast<cudaStream_t>(stream);
+        else { QCK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+        for (auto& ev : c->ev) QCK(cudaEventCreate(&ev));
+        for (auto& ev : c->ev_scan0) QCK(cudaEventCreate(&ev));
+        for (auto& ev : c->ev_scan1) QCK(cudaEventCreate(&ev));
+        QCK(cudaMalloc(&c->d_err, sizeof(int)));
+        QCK(cudaMemset(c->d_err, 0, sizeof(int)));
+        QCK(cudaMallocHost(&c->h_err, sizeof(int)));
+        *c->h_err = 0;
+        return QADC_OK;
+    };
+    const int rc = init();
+    if (rc != QADC_OK) {
+        g_create_error = c->err;
+        qadc_destroy(c);
+        return rc;
+    }
     *out = c;
     return QADC_OK;
 }
@@ -453,7 +462,7 @@ int qadc_create(int device, void* stream, qadc_ctx** out) {
 void qadc_destroy(qadc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     free_db(c);
     cudaFree(c->d_codebooks); cudaFree(c->d_rotation); cudaFree(c->d_centroids);
     for (DevBuf* b : {&c->staging, &c->b_queries, &c->b_assign, &c->b_tables, &c->b_tmin, &c->b_qmax, &c->b_qmin,
@@ -461,11 +470,11 @@ void qadc_destroy(qadc_ctx* c) {
                       &c->b_dump, &c->b_hist, &c->b_sbound, &c->b_cdist})
         cudaFree(b->p);
     cudaFree(c->d_err);
-    cudaFreeHost(c->h_err);
-    for (auto& ev : c->ev) cudaEventDestroy(ev);
-    for (auto& ev : c->ev_scan0) cudaEventDestroy(ev);
-    for (auto& ev : c->ev_scan1) cudaEventDestroy(ev);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->h_err) cudaFreeHost(c->h_err);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_scan0) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_scan1) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -629,8 +638,8 @@ int qadc_finalize(qadc_ctx* ctx, float keep) {
     QCK(cudaMemcpy(ctx->d_start_off, ctx->h_start_off.data(), P * 8, cudaMemcpyHostToDevice));
     QCK(cudaMemcpy(ctx->d_start_size, ctx->h_start_size.data(), P * 4, cudaMemcpyHostToDevice));
     QCK(cudaMemcpy(ctx->d_pos_base, ctx->h_pos_base.data(), P * 4, cudaMemcpyHostToDevice));
-    uint8_t* d_flags = nullptr;
-    QCK(cudaMalloc(&d_flags, P));
+    ENSURE(ctx->b_dump, static_cast<size_t>(P));
+    uint8_t* d_flags = ctx->b_dump.as<uint8_t>();
     QCK(cudaMemcpy(d_flags, has_explicit.data(), P, cudaMemcpyHostToDevice));
     dim3 grid(P, std::max(1u, std::min(64u, (ctx->max_start + 255) / 256)));
     if (M == 16)
@@ -645,7 +654,6 @@ int qadc_finalize(qadc_ctx* ctx, float keep) {
             QCK(cudaMemcpyAsync(ctx->d_starts + ctx->h_start_off[p] * CS, ctx->h_explicit_prefix[p],
                                 static_cast<size_t>(ctx->h_explicit_count[p]) * CS, cudaMemcpyDeviceToDevice, ctx->stream));
     QCK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_flags);
     ctx->finalized = true;
     return QADC_OK;
 }

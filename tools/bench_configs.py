@@ -98,7 +98,25 @@ def config5(nq=2000, n=20 * 10 ** 6):
     ix.close()
 
 
+def config6(nq=2000, n=20 * 10 ** 6):
+    """Long inverted lists (about 20k vectors each, like Deep1B / IVF-65536): IVF-1024, nprobe 16."""
+    rng = np.random.default_rng(1240)
+    dim, m, K, ma = 96, 16, 1024, 16
+    cb = rng.standard_normal((m, 16, dim // m)).astype(np.float32)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    sizes = rng.multinomial(n, np.ones(K) / K)
+    offsets = np.zeros(K + 1, np.int64); offsets[1:] = np.cumsum(sizes)
+    labels = rng.permutation(n).astype(np.uint32)
+    codes = rng.integers(0, 256, (n, m // 2), dtype=np.uint8)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    ix = qadc_b200.Index(0); ix.set_pq(dim, m, cb); ix.set_coarse(cents); ix.load_ivf(codes, labels, offsets, 0.001)
+    db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=0.001, offsets=offsets,
+              scanned_per_query=float(ma * n / K))
+    run("6: long lists, IVF-1024 x 20k vectors, nprobe 16", ix, db, q, ma, check=3)
+    ix.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["1", "2", "3"]
     for w in which:
-        {"1": config1, "2": config2, "3": config3, "5": config5}[w]()
+        {"1": config1, "2": config2, "3": config3, "5": config5, "6": config6}[w]()
