@@ -50,23 +50,29 @@ struct BlockTopK {
 // ---- coarse assignment ------------------------------------------------------------------------
 // d(q,c) = sum_i fma(diff_i, diff_i, .) sequentially over the dimension (the FIXED statement of
 // find_k_neighbors, neighbors.cpp:30-76 with the :64 stride bug removed); the ma smallest under
-// (d, c) ascending.  Two kernels: a shared-memory tiled distance kernel (32 queries x 64
-// centroids per CTA step, every (q,c) sum still strictly in dimension order, so results are
+// (d, c) ascending.  Two kernels: a shared-memory / register tiled distance kernel (64 queries x
+// 128 centroids per CTA, every (q,c) sum still strictly in dimension order, so results are
 // bit-identical to the oracle) and a per-query streaming selection.
-constexpr int kCoarseTQ = 32;   // queries per CTA
-constexpr int kCoarseTC = 64;   // centroids per tile
-constexpr int kCoarseTD = 32;   // dimensions per smem slab
+constexpr int kCoarseTQ = 64;    // queries per CTA
+constexpr int kCoarseTC = 128;   // centroids per CTA
+constexpr int kCoarseTD = 16;    // dimensions per shared-memory slab
 
+// 16 x 16 threads; thread (ty, tx) owns queries 4*ty..4*ty+3 and centroids tx, tx+16, ..., tx+112
+// (a 4 x 8 register tile: 12 shared loads per 64 sub+fma).  The slab row stride of 17 words keeps
+// both the query reads (two rows per warp, broadcast) and the centroid reads (17*tx mod 32 distinct)
+// free of bank conflicts.  Every (q, c) sum still runs strictly in dimension order.
 __global__ void __launch_bounds__(256) coarse_dist_kernel(const float* __restrict__ queries, int nq, int dim,
                                                           const float* __restrict__ centroids, int K,
                                                           float* __restrict__ dist) {   // [nq][K]
     __shared__ float sq[kCoarseTQ][kCoarseTD + 1];
     __shared__ float sc[kCoarseTC][kCoarseTD + 1];
-    const int tid = threadIdx.x;
-    const int tq = tid & 31;          // query inside the tile (lane)
-    const int tc0 = (tid >> 5) * 8;   // 8 centroids per thread, warp-uniform -> broadcast reads of sc
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int q0 = blockIdx.x * kCoarseTQ, c0 = blockIdx.y * kCoarseTC;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
     for (int d0 = 0; d0 < dim; d0 += kCoarseTD) {
         const int dn = min(kCoarseTD, dim - d0);
         __syncthreads();
@@ -79,19 +85,31 @@ __global__ void __launch_bounds__(256) coarse_dist_kernel(const float* __restric
             sc[r][c] = (c0 + r < K && c < dn) ? __ldg(centroids + static_cast<size_t>(c0 + r) * dim + d0 + c) : 0.f;
         }
         __syncthreads();
-        for (int i = 0; i < dn; ++i) {
-            const float x = sq[tq][i];
+        for (int d = 0; d < dn; ++d) {
+            float x[4], y[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float diff = __fsub_rn(x, sc[tc0 + k][i]);
-                acc[k] = __fmaf_rn(diff, diff, acc[k]);
-            }
+            for (int i = 0; i < 4; ++i) x[i] = sq[4 * ty + i][d];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[k] = sc[tx + 16 * k][d];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float diff = __fsub_rn(x[i], y[k]);
+                    acc[i][k] = __fmaf_rn(diff, diff, acc[i][k]);
+                }
         }
     }
-    if (q0 + tq < nq) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (c0 + tc0 + k < K) dist[static_cast<size_t>(q0 + tq) * K + c0 + tc0 + k] = acc[k];
+    for (int i = 0; i < 4; ++i) {
+        const int q = q0 + 4 * ty + i;
+        if (q < nq) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = c0 + tx + 16 * k;
+                if (c < K) dist[static_cast<size_t>(q) * K + c] = acc[i][k];
+            }
+        }
     }
 }
 
