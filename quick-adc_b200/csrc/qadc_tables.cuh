@@ -122,7 +122,13 @@ __global__ void __launch_bounds__(kSelThreads) coarse_select_kernel(const float*
     const float* d = dist + static_cast<size_t>(q) * K;
     BlockTopK top{keys, &count, &bound_key};
     top.init(tid);
-    for (int base = 0; base < K; base += kSelCap / 2) {
+    // first round: nothing to filter against yet, so the keys are stored directly (no shared atomics)
+    const int first = min(kSelCap / 2, K);
+    for (int c = tid; c < first; c += kSelThreads)
+        keys[c] = (static_cast<uint64_t>(__float_as_uint(d[c])) << 32) | static_cast<uint32_t>(c);
+    if (tid == 0) count = first;
+    top.maybe_compact(ma, tid, first >= K);
+    for (int base = first; base < K; base += kSelCap / 2) {
         for (int c = base + tid; c < min(base + kSelCap / 2, K); c += kSelThreads)
             top.push((static_cast<uint64_t>(__float_as_uint(d[c])) << 32) | static_cast<uint32_t>(c));
         top.maybe_compact(ma, tid, base + kSelCap / 2 >= K);

@@ -29,7 +29,7 @@ for r in rows[2:]:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]; ia = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[2:] if len(r) == len(hdr)]
+data = [r for r in rows[2:] if len(r) == len(hdr) and r[ia["# Samples"]].isdigit()]   # several kernels: headers repeat
 tot = sum(int(r[ia["# Samples"]]) for r in data); texec = sum(int(r[ia["Instructions Executed"]]) for r in data)
 print(f"source page: {tot} samples, {texec} warp instructions", file=out)
 c = Counter()
