@@ -253,6 +253,12 @@ class Ref:
         L.ref_search.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u32p, i8p,
                                  i32p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_encode.argtypes = [C.c_int, C.c_int, f32p, f32p, C.c_int, u8p]
+        L.ref_set_rotation.argtypes = [C.c_void_p, f32p]
+        L.ref_save_db.restype = C.c_int
+        L.ref_save_db.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_load_db.restype = C.c_void_p
+        L.ref_load_db.argtypes = [C.c_char_p]
+        L.ref_db_info.argtypes = [C.c_void_p, i32p]
 
     def interleave(self, codes):
         n, cs = codes.shape
@@ -344,10 +350,34 @@ class Ref:
                                     _opt(times))
             return dict(keys=keys, vals=vals, sizes=sizes, assign=assign, tables=tables, times_us=times)
 
+        def set_rotation(self, rotation):
+            """OPQ (quantizers.hpp:248-301); call before prepare()."""
+            self.ref.lib.ref_set_rotation(self.ptr, np.ascontiguousarray(rotation, np.float32).reshape(-1))
+
+        def save(self, path):
+            """flatdb_create.cpp:49-53 over oracle/shims/cereal."""
+            if self.ref.lib.ref_save_db(self.ptr, str(path).encode()) != 0:
+                raise IOError("ref_save_db failed")
+
+        def info(self):
+            out = np.zeros(6, np.int32)
+            self.ref.lib.ref_db_info(self.ptr, out)
+            return dict(zip(("index", "opq", "dim", "m", "bits", "partitions"), (int(v) for v in out)))
+
         def close(self):
             if self.ptr:
                 self.ref.lib.ref_destroy(self.ptr)
                 self.ptr = None
+
+    def load(self, path):
+        """query_common.hpp:321-328 (load_database) over oracle/shims/cereal."""
+        p = self.lib.ref_load_db(str(path).encode())
+        if not p:
+            raise IOError("ref_load_db failed")
+        h = Ref.Handle(self, p, 0, 0)
+        i = h.info()
+        h.m, h.dim = i["m"], i["dim"]
+        return h
 
     def flat(self, dim, m, codebooks, codes):
         p = self.lib.ref_flat_create(dim, m, np.ascontiguousarray(codebooks.reshape(-1)),

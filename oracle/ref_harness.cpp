@@ -218,6 +218,49 @@ __attribute__((visibility("default"))) void* ref_ivf_create(
     return h;
 }
 
+// OPQ: replaces the handle's quantiser by an opq with the same codebooks and the given rotation
+// (quantizers.hpp:248-301), before ref_prepare.
+__attribute__((visibility("default"))) void ref_set_rotation(void* handle, const float* rotation) {
+    auto h = static_cast<ref_handle*>(handle);
+    base_pq& old = *h->db->pq;
+    h->db->pq.reset(new opq(old.sq_count, old.sq_bits, old.dim, old.centroids_flat.get(),
+                            const_cast<float*>(rotation)));
+}
+
+// Database files: exactly the calls of flatdb_create.cpp:49-53 (save) and query_common.hpp:321-328
+// (load).  Field order comes from the reference's save()/load() members; the bytes of each field
+// from shims/cereal (a restatement of cereal 1.2.2's binary archive, see its header).
+__attribute__((visibility("default"))) int ref_save_db(void* handle, const char* path) {
+    auto h = static_cast<ref_handle*>(handle);
+    std::ofstream out_file(path);
+    if (!out_file) return -1;
+    cereal::BinaryOutputArchive out_archive(out_file);
+    out_archive(h->db);
+    return out_file ? 0 : -1;
+}
+__attribute__((visibility("default"))) void* ref_load_db(const char* path) {
+    query_args args{};
+    args.db_file = path;
+    auto h = new ref_handle;
+    try {
+        h->db = load_database(args);
+    } catch (const std::exception& e) {
+        std::cerr << e.what() << std::endl;
+    }
+    if (!h->db) { delete h; return nullptr; }
+    return h;
+}
+// What a loaded database holds: kind 0 flat / 1 index, opq flag, dim, m, bits, partitions.
+__attribute__((visibility("default"))) void ref_db_info(void* handle, int* out6) {
+    auto h = static_cast<ref_handle*>(handle);
+    out6[0] = dynamic_cast<index_db*>(h->db.get()) ? 1 : 0;
+    out6[1] = dynamic_cast<opq*>(h->db->pq.get()) ? 1 : 0;
+    out6[2] = h->db->pq->dim;
+    out6[3] = h->db->pq->sq_count;
+    out6[4] = h->db->pq->sq_bits;
+    out6[5] = h->db->partition_count();
+}
+
 // scanner_4::prepare_database (db_query_4.cpp:210-228). Frees the db's copy of the codes.
 __attribute__((visibility("default"))) void ref_prepare(void* handle, float keep) {
     auto h = static_cast<ref_handle*>(handle);

@@ -1,9 +1,13 @@
 // base_db / flat_db / index_db — the database API the scanner consumes (databases.hpp:34-63,
 // :77-134, :176-250): partition_count / get_partition / free_partition, row-major 4-bit codes,
 // uint32 labels for inverted lists.  Query-time assignment and residuals run on the GPU, so
-// assign_compute_residuals* are not needed here.  Files: the reference serialises with cereal
-// (absent here, layout unverifiable), so databases are stored in the small documented ".qdb"
-// container below (writer: quick-adc_b200/dbfile.py).
+// assign_compute_residuals* are not needed here.
+//
+// Files.  load_database() reads two formats, told apart by their first bytes:
+//  * the reference's own database files (cereal 1.2.2 BinaryOutputArchive of a
+//    std::unique_ptr<base_db>, flatdb_create.cpp:49-53 / query_common.hpp:321-328) — layout in
+//    the "cereal archive" section below;
+//  * the ".qdb" container (writer: quick-adc_b200/dbfile.py), a plain header + arrays:
 //
 //   char  magic[8] = "QADCDB1\0"
 //   int32 kind (0 flat, 1 index), pq_kind (0 pq, 1 opq), dim, m, bits, K (partitions; 1 if flat)
@@ -25,7 +29,8 @@ struct base_db {
     // labels_offset.. ; the PQ encoding (and, for inverted lists, the coarse assignment) runs on
     // the GPU through `enc`, a context prepared with qadc_set_pq (+ qadc_set_coarse).
     virtual void add_vectors(qadc_ctx* enc, const float* vectors, unsigned count, unsigned labels_offset) = 0;
-    virtual void save(std::ostream& os) const = 0;
+    virtual void save(std::ostream& os) const = 0;          // .qdb container
+    virtual void save_archive(std::ostream& os) const = 0;  // the reference's cereal layout
     virtual int partition_count() const = 0;
     virtual void get_partition(int part_i, const std::uint8_t*& codes, unsigned*& labels, unsigned& size) const = 0;
     virtual void free_partition(int part_i) = 0;
@@ -60,6 +65,7 @@ struct flat_db : base_db {
         }
     }
     void save(std::ostream& os) const override;
+    void save_archive(std::ostream& os) const override;
 };
 
 struct index_db : base_db {
@@ -99,6 +105,7 @@ struct index_db : base_db {
         }
     }
     void save(std::ostream& os) const override;
+    void save_archive(std::ostream& os) const override;
 };
 
 inline void qdb_write_header(std::ostream& os, const base_pq& pq, int kind, int K) {
@@ -130,19 +137,13 @@ inline void index_db::save(std::ostream& os) const {
     }
 }
 
-inline std::unique_ptr<base_db> load_qdb(const char* filename) {
-    std::ifstream in(filename, std::ios::binary);
-    if (!in) {
-        std::cerr << "Could not open database " << filename << std::endl;
-        std::exit(1);
-    }
+inline std::unique_ptr<base_db> load_qdb(std::istream& in, const char* filename) {
     char magic[8];
     std::int32_t h[6];
     in.read(magic, 8);
     in.read(reinterpret_cast<char*>(h), sizeof(h));
     if (!in || std::memcmp(magic, "QADCDB1", 8) != 0) {
-        std::cerr << filename << " is not a .qdb database (cereal archives of the reference are not readable "
-                  << "here: convert with quick-adc_b200/dbfile.py)" << std::endl;
+        std::cerr << filename << " is not a .qdb database" << std::endl;
         std::exit(1);
     }
     const int kind = h[0], pq_kind = h[1], dim = h[2], m = h[3], bits = h[4], K = h[5];
@@ -184,6 +185,174 @@ inline std::unique_ptr<base_db> load_qdb(const char* filename) {
     }
     db->pq = std::move(pq);
     return db;
+}
+
+// ---- cereal archive -------------------------------------------------------------------------
+// The reference writes `std::unique_ptr<base_db>` through cereal::BinaryOutputArchive (cereal
+// 1.2.2: native little-endian values, no header).  Bytes, in order:
+//   uint32 0x80000001; uint64 len; "flat_db" | "index_db"        first registered polymorphic type
+//   uint8  1                                                      pointer is not null
+//   flat_db  (databases.hpp:158-161):  <pq>; uint32 codes_count; uint64 n; uint8 codes[n]
+//   index_db (databases.hpp:300-313):  int32 part_count; <pq>; float centroids[part_count*dim];
+//                                      per partition uint64 n; uint8 codes[n];
+//                                      per partition uint64 n; uint32 labels[n]
+//   <pq> = std::unique_ptr<base_pq>:
+//     base_pq: uint32 0x40000000; uint8 1; int32 sq_count, sq_bits, dim; float codebooks[dim*2^bits]
+//     opq:     uint32 0x80000002; uint64 3; "opq"; uint8 1; the base_pq fields; float rotation[dim*dim]
+// (quantizers.hpp:170-178, :303-312).  cereal is not available in this build environment: the
+// layout is restated from its published format and checked against the reference's own
+// save()/load() code running over a restatement of the archive classes (oracle/shims/cereal),
+// not against files written by the real library.
+namespace qadc_archive {
+const std::uint32_t kFirstUse = 0x80000000u, kSameType = 0x40000000u;
+
+template <typename T> inline void put(std::ostream& os, const T& v) { os.write(reinterpret_cast<const char*>(&v), sizeof(T)); }
+template <typename T> inline T get(std::istream& in) {
+    T v = T();
+    in.read(reinterpret_cast<char*>(&v), sizeof(T));
+    return v;
+}
+inline void put_name(std::ostream& os, std::uint32_t id, const char* name) {
+    put<std::uint32_t>(os, kFirstUse | id);
+    put<std::uint64_t>(os, std::strlen(name));
+    os.write(name, static_cast<std::streamsize>(std::strlen(name)));
+    put<std::uint8_t>(os, 1);
+}
+template <typename T> inline void put_vector(std::ostream& os, const std::vector<T>& v) {
+    put<std::uint64_t>(os, v.size());
+    os.write(reinterpret_cast<const char*>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
+}
+template <typename T> inline bool get_vector(std::istream& in, std::vector<T>& v, std::uint64_t max_bytes) {
+    const std::uint64_t n = get<std::uint64_t>(in);
+    if (!in || n * sizeof(T) > max_bytes) return false;
+    v.resize(n);
+    in.read(reinterpret_cast<char*>(v.data()), static_cast<std::streamsize>(n * sizeof(T)));
+    return static_cast<bool>(in);
+}
+inline std::string get_name(std::istream& in) {
+    const std::uint64_t n = get<std::uint64_t>(in);
+    if (!in || n > 64) return std::string();
+    std::string s(n, '\0');
+    in.read(&s[0], static_cast<std::streamsize>(n));
+    return s;
+}
+inline void put_pq(std::ostream& os, const base_pq& pq, std::uint32_t next_id) {
+    const opq* o = dynamic_cast<const opq*>(&pq);
+    if (o) put_name(os, next_id, "opq");
+    else { put<std::uint32_t>(os, kSameType); put<std::uint8_t>(os, 1); }
+    put<std::int32_t>(os, pq.sq_count);
+    put<std::int32_t>(os, pq.sq_bits);
+    put<std::int32_t>(os, pq.dim);
+    os.write(reinterpret_cast<const char*>(pq.centroids_flat.data()), static_cast<std::streamsize>(pq.centroids_flat.size() * sizeof(float)));
+    if (o) os.write(reinterpret_cast<const char*>(o->rotation.data()), static_cast<std::streamsize>(o->rotation.size() * sizeof(float)));
+}
+inline std::unique_ptr<base_pq> get_pq(std::istream& in) {
+    const std::uint32_t id = get<std::uint32_t>(in);
+    bool is_opq = false;
+    if (id & kFirstUse) {
+        if (get_name(in) != "opq") return nullptr;
+        is_opq = true;
+    } else if (!(id & kSameType)) {
+        return nullptr;
+    }
+    if (get<std::uint8_t>(in) != 1) return nullptr;
+    const int m = get<std::int32_t>(in), bits = get<std::int32_t>(in), dim = get<std::int32_t>(in);
+    if (!in || m <= 0 || bits <= 0 || bits > 16 || dim <= 0 || dim > (1 << 20) || dim % m) return nullptr;
+    std::unique_ptr<base_pq> pq;
+    if (is_opq) pq.reset(new opq(m, bits, dim));
+    else pq.reset(new base_pq(m, bits, dim));
+    in.read(reinterpret_cast<char*>(pq->centroids_flat.data()), static_cast<std::streamsize>(pq->centroids_flat.size() * sizeof(float)));
+    if (auto* o = dynamic_cast<opq*>(pq.get()))
+        in.read(reinterpret_cast<char*>(o->rotation.data()), static_cast<std::streamsize>(o->rotation.size() * sizeof(float)));
+    if (!in) return nullptr;
+    return pq;
+}
+}  // namespace qadc_archive
+
+inline void flat_db::save_archive(std::ostream& os) const {
+    qadc_archive::put_name(os, 1, "flat_db");
+    qadc_archive::put_pq(os, *pq, 2);
+    qadc_archive::put<std::uint32_t>(os, codes_count);
+    qadc_archive::put_vector(os, codes);
+}
+
+inline void index_db::save_archive(std::ostream& os) const {
+    qadc_archive::put_name(os, 1, "index_db");
+    qadc_archive::put<std::int32_t>(os, part_count);
+    qadc_archive::put_pq(os, *pq, 2);
+    os.write(reinterpret_cast<const char*>(centroids.data()), static_cast<std::streamsize>(centroids.size() * sizeof(float)));
+    for (int p = 0; p < part_count; ++p) qadc_archive::put_vector(os, partitions[p]);
+    for (int p = 0; p < part_count; ++p) qadc_archive::put_vector(os, labels[p]);
+}
+
+// `file_bytes` bounds every length field, so a corrupt file cannot ask for absurd allocations.
+inline std::unique_ptr<base_db> load_archive(std::istream& in, std::uint64_t file_bytes) {
+    using namespace qadc_archive;
+    const std::uint32_t id = get<std::uint32_t>(in);
+    if (!in || !(id & kFirstUse)) return nullptr;
+    const std::string name = get_name(in);
+    if (get<std::uint8_t>(in) != 1) return nullptr;
+    std::unique_ptr<base_db> db;
+    if (name == "flat_db") {
+        auto* f = new flat_db;
+        db.reset(f);
+        f->pq = get_pq(in);
+        if (!f->pq) return nullptr;
+        f->codes_count = get<std::uint32_t>(in);
+        if (!get_vector(in, f->codes, file_bytes)) return nullptr;
+        if (f->codes.size() != static_cast<size_t>(f->codes_count) * f->pq->code_size()) return nullptr;
+    } else if (name == "index_db") {
+        auto* x = new index_db;
+        db.reset(x);
+        x->part_count = get<std::int32_t>(in);
+        x->pq = get_pq(in);
+        if (!x->pq || x->part_count <= 0 || static_cast<std::uint64_t>(x->part_count) * x->pq->dim * 4 > file_bytes) return nullptr;
+        x->centroids.resize(static_cast<size_t>(x->part_count) * x->pq->dim);
+        in.read(reinterpret_cast<char*>(x->centroids.data()), static_cast<std::streamsize>(x->centroids.size() * sizeof(float)));
+        x->partitions.resize(x->part_count);
+        x->labels.resize(x->part_count);
+        for (int p = 0; p < x->part_count; ++p)
+            if (!get_vector(in, x->partitions[p], file_bytes)) return nullptr;
+        for (int p = 0; p < x->part_count; ++p) {
+            if (!get_vector(in, x->labels[p], file_bytes)) return nullptr;
+            if (x->partitions[p].size() != x->labels[p].size() * x->pq->code_size()) return nullptr;
+        }
+    } else {
+        return nullptr;
+    }
+    return db;
+}
+
+// query_common.hpp:321-328 — accepts the reference's archives and .qdb containers.
+inline std::unique_ptr<base_db> load_database(const char* filename) {
+    std::ifstream in(filename, std::ios::binary);
+    if (!in) {
+        std::cerr << "Could not open database " << filename << std::endl;
+        std::exit(1);
+    }
+    in.seekg(0, std::ios::end);
+    const std::uint64_t file_bytes = static_cast<std::uint64_t>(in.tellg());
+    in.seekg(0);
+    char magic[8] = {0};
+    in.read(magic, 8);
+    in.clear();
+    in.seekg(0);
+    if (std::memcmp(magic, "QADCDB1", 8) == 0) return load_qdb(in, filename);
+    std::unique_ptr<base_db> db = load_archive(in, file_bytes);
+    if (!db) {
+        std::cerr << filename << " is not a database file (neither a flat_db/index_db cereal archive nor a .qdb container)" << std::endl;
+        std::exit(1);
+    }
+    return db;
+}
+
+// Writes `.qdb` when the name ends so, the reference's archive layout otherwise.
+inline bool save_database(const base_db& db, const char* filename) {
+    std::ofstream out(filename, std::ios::binary);
+    if (!out) return false;
+    if (qadc_ends_with(filename, ".qdb")) db.save(out);
+    else db.save_archive(out);
+    return static_cast<bool>(out);
 }
 
 #endif

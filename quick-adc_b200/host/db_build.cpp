@@ -1,7 +1,9 @@
 // db_build — creates a database file from a quantiser and a base-vector file, the job of the
 // reference's flatdb_create / indexdb_create2 + db_add chain (flatdb_create.cpp, db_add.cpp) with
 // the encoding done on the GPU:
-//     db_build [-c coarse_centroids.fvecs] [-g GPU] quantizer.(o)pq.data base.(f|b)vecs out.qdb
+//     db_build [-c coarse_centroids.fvecs] [-g GPU] quantizer.(o)pq.data base.(f|b)vecs out_db
+// out_db ending in ".qdb" is written as a .qdb container, any other name in the reference's own
+// archive layout (host/databases.hpp), which the reference's tools read.
 // Without -c a flat database is written, with -c an inverted-list database over those centroids
 // (training the centroids — k-means, indexdb_create1.cpp — is out of scope).  Vectors are added
 // in chunks of one million like db_add (db_add.cpp:52-77), ids = position in the base file.
@@ -16,9 +18,9 @@ int main(int argc, char* argv[]) {
     while ((opt = getopt(argc, argv, "c:g:")) != -1) {
         if (opt == 'c') coarse = optarg;
         else if (opt == 'g') gpu = std::atoi(optarg);
-        else { std::cerr << "Usage: db_build [-c centroids.fvecs] [-g GPU] pq_file base_file out.qdb" << std::endl; return 1; }
+        else { std::cerr << "Usage: db_build [-c centroids.fvecs] [-g GPU] pq_file base_file out_db" << std::endl; return 1; }
     }
-    if (argc - optind < 3) { std::cerr << "Usage: db_build [-c centroids.fvecs] [-g GPU] pq_file base_file out.qdb" << std::endl; return 1; }
+    if (argc - optind < 3) { std::cerr << "Usage: db_build [-c centroids.fvecs] [-g GPU] pq_file base_file out_db" << std::endl; return 1; }
     std::unique_ptr<base_pq> pq = pq_from_data_file(argv[optind]);
     if (pq->sq_bits != 4) { std::cerr << "Quantizer must have  sq_bits=4" << std::endl; return 1; }
     vectors_owner<float> base = load_vectors_by_extension(argv[optind + 1]);
@@ -52,9 +54,7 @@ int main(int argc, char* argv[]) {
     std::cerr << std::endl;
     db->print(std::cerr);
     std::cerr << std::endl;
-    std::ofstream out(argv[optind + 2], std::ios::binary);
-    if (!out) { std::cerr << "Could not write " << argv[optind + 2] << std::endl; return 1; }
-    db->save(out);
+    if (!save_database(*db, argv[optind + 2])) { std::cerr << "Could not write " << argv[optind + 2] << std::endl; return 1; }
     qadc_destroy(enc);
     return 0;
 }

@@ -53,7 +53,7 @@ int main(int argc, char* argv[]) {
     cmdargs args;
     parse_args(args, argc, argv);
     std::cerr << "Database file: " << args.db_file << std::endl;
-    std::unique_ptr<base_db> db = load_qdb(args.db_file);
+    std::unique_ptr<base_db> db = load_database(args.db_file);
     if (db->pq->sq_bits != 4) {
         std::cerr << "Quantizer must have  sq_bits=4" << std::endl;   // load_database_check, db_query_4.cpp:393-402
         return 1;

@@ -52,7 +52,7 @@ def flat_case(ref, name, seed, dim, m, n, nq, r, keep):
     print(name, "heap sizes", res["sizes"], "d<127 per query", (dist < 127).sum(1))
 
 
-def ivf_case(ref, name, seed, dim, m, n, K, ma, nq, r, keep, empty=()):
+def ivf_case(ref, name, seed, dim, m, n, K, ma, nq, r, keep, empty=(), opq=False):
     rng = np.random.default_rng(seed)
     cb = synth.make_pq(rng, dim, m)
     cents = (2.0 * rng.standard_normal((K, dim))).astype(np.float32)
@@ -61,6 +61,10 @@ def ivf_case(ref, name, seed, dim, m, n, K, ma, nq, r, keep, empty=()):
     out = dict(dim=dim, m=m, r=r, ma=ma, keep=np.float32(keep), codebooks=cb, centroids=cents, codes=codes,
                labels=labels, offsets=offsets, queries=queries)
     h = ref.ivf(dim, m, cb, cents, codes, labels, offsets)
+    if opq:
+        # opq::rotate_multiple_vectors (quantizers.hpp:286-301) rotates the residuals before the tables
+        out["rotation"] = np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32)
+        h.set_rotation(out["rotation"])
     h.prepare(keep)
     out["ref_start_size"] = np.array([h.starts_size(p) for p in range(K)], np.uint32)
     # K <= 256, so find_k_neighbors is correct as shipped
@@ -92,16 +96,59 @@ def encode_case(ref, name, seed, dim, m, n):
     print(name, "encoded", n)
 
 
+def archive_case(ref, name, seed, dim, m, n, K):
+    """Database files as the reference writes them (flatdb_create.cpp:49-53): flat/index x pq/opq.
+    Field order = the reference's save() members; field bytes = oracle/shims/cereal (cereal 1.2.2's
+    binary archive restated; the real library is not in this image)."""
+    import tempfile
+    rng = np.random.default_rng(seed)
+    cb = synth.make_pq(rng, dim, m)
+    codes = synth.make_codes(rng, n, m)
+    rot = np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32)
+    cents = rng.standard_normal((K, dim)).astype(np.float32)
+    icodes, labels, offsets = synth.make_ivf(rng, n, K, m, (1,))
+    out = dict(dim=dim, m=m, codebooks=cb, codes=codes, rotation=rot, centroids=cents, ivf_codes=icodes, labels=labels,
+               offsets=offsets)
+    with tempfile.TemporaryDirectory() as tmp:
+        for ivf in (False, True):
+            for opq in (False, True):
+                h = ref.ivf(dim, m, cb, cents, icodes, labels, offsets) if ivf else ref.flat(dim, m, cb, codes)
+                if opq:
+                    h.set_rotation(rot)
+                path = os.path.join(tmp, "db")
+                h.save(path)
+                h.close()
+                out["ref_%s_%s" % ("index" if ivf else "flat", "opq" if opq else "pq")] = np.fromfile(path, np.uint8)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: v.size for k, v in out.items() if k.startswith("ref_")})
+
+
 def main():
+    """python tests/golden/make_golden.py [name ...]  (no names: every fixture)"""
     ref = Ref()
-    encode_case(ref, "encode_m16", seed=105, dim=128, m=16, n=400)
-    encode_case(ref, "encode_m32", seed=106, dim=256, m=32, n=200)
+    only = set(sys.argv[1:])
+
+    def want(name):
+        return not only or name in only
+
+    for name, kw in (("encode_m16", dict(seed=105, dim=128, m=16, n=400)), ("encode_m32", dict(seed=106, dim=256, m=32, n=200))):
+        if want(name):
+            encode_case(ref, name, **kw)
     # n = 3003: not a multiple of 16 -> exercises the pad-lane duplicate quirk (SURVEY F5b)
-    flat_case(ref, "flat_m16", seed=101, dim=128, m=16, n=3003, nq=8, r=20, keep=0.05)
+    if want("flat_m16"):
+        flat_case(ref, "flat_m16", seed=101, dim=128, m=16, n=3003, nq=8, r=20, keep=0.05)
     # 96-d, m=32 -> sq_dim 3 (SURVEY F7: only reachable by direct template instantiation)
-    flat_case(ref, "flat_m32", seed=102, dim=96, m=32, n=2048, nq=6, r=16, keep=0.05)
-    ivf_case(ref, "ivf_m16", seed=103, dim=128, m=16, n=6000, K=24, ma=5, nq=8, r=20, keep=0.08, empty=(3,))
-    ivf_case(ref, "ivf_m32", seed=104, dim=96, m=32, n=4000, K=12, ma=3, nq=6, r=10, keep=0.1)
+    if want("flat_m32"):
+        flat_case(ref, "flat_m32", seed=102, dim=96, m=32, n=2048, nq=6, r=16, keep=0.05)
+    if want("ivf_m16"):
+        ivf_case(ref, "ivf_m16", seed=103, dim=128, m=16, n=6000, K=24, ma=5, nq=8, r=20, keep=0.08, empty=(3,))
+    if want("ivf_m32"):
+        ivf_case(ref, "ivf_m32", seed=104, dim=96, m=32, n=4000, K=12, ma=3, nq=6, r=10, keep=0.1)
+    if want("archives"):
+        archive_case(ref, "archives", seed=108, dim=32, m=16, n=300, K=6)
+    # OPQ: the rotation sits between the residuals and the tables
+    if want("ivf_opq_m16"):
+        ivf_case(ref, "ivf_opq_m16", seed=107, dim=64, m=16, n=5000, K=16, ma=4, nq=8, r=20, keep=0.08, empty=(9,), opq=True)
 
 
 if __name__ == "__main__":

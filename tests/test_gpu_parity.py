@@ -11,24 +11,33 @@ import numpy as np
 import pytest
 
 import synth
-from test_oracle import FLAT, IVF, FLOAT_RTOL, load, rel_err, blas_scale, tie_class_check
+from test_oracle import FLAT, IVF, OPQ, FLOAT_RTOL, load, rel_err, blas_scale, tie_class_check, golden_db, rotated
 
 pytestmark = pytest.mark.gpu
 
 
-def flat_index(qadc, dim, m, cb, codes, keep):
+def flat_index(qadc, dim, m, cb, codes, keep, rotation=None):
     ix = qadc.Index(0)
-    ix.set_pq(dim, m, cb)
+    ix.set_pq(dim, m, cb, rotation=rotation)
     ix.load_flat(codes, keep)
     return ix
 
 
-def ivf_index(qadc, dim, m, cb, cents, codes, labels, offsets, keep):
+def ivf_index(qadc, dim, m, cb, cents, codes, labels, offsets, keep, rotation=None):
     ix = qadc.Index(0)
-    ix.set_pq(dim, m, cb)
+    ix.set_pq(dim, m, cb, rotation=rotation)
     ix.set_coarse(cents)
     ix.load_ivf(codes, labels, offsets, keep)
     return ix
+
+
+def golden_index(qadc, g):
+    """Device index of a golden fixture (flat / inverted lists, with its OPQ rotation if any)."""
+    rot = g["rotation"] if "rotation" in g else None
+    if "centroids" in g:
+        return ivf_index(qadc, int(g["dim"]), int(g["m"]), g["codebooks"], g["centroids"], g["codes"], g["labels"],
+                         g["offsets"], float(g["keep"]), rot)
+    return flat_index(qadc, int(g["dim"]), int(g["m"]), g["codebooks"], g["codes"], float(g["keep"]), rot)
 
 
 # ---- layout ------------------------------------------------------------------------------
@@ -144,14 +153,14 @@ def test_flat_scan_degenerate_ties(qadc, oracle):
     ix.close()
 
 
-@pytest.mark.parametrize("name", IVF)
+@pytest.mark.parametrize("name", IVF + OPQ)
 def test_ivf_scan_with_reference_tables(qadc, oracle, name):
     """Injected assign + the reference's own int8 tables: canonical result bit-exact vs the
     oracle, tie-class equivalent to the raw reference heap (Stage R)."""
     g = load(name)
     r, m, ma = int(g["r"]), int(g["m"]), int(g["ma"])
     codes, labels, offsets = g["codes"], g["labels"], g["offsets"]
-    ix = ivf_index(qadc, int(g["dim"]), m, g["codebooks"], g["centroids"], codes, labels, offsets, float(g["keep"]))
+    ix = golden_index(qadc, g)
     ids, d, cnt = ix.scan_with_tables(g["ref_assign"], g["ref_qtables"], r)
     checked = 0
     for q in range(g["queries"].shape[0]):
@@ -198,25 +207,16 @@ def test_ivf_random_large(qadc, oracle):
 
 
 # ---- Stage T: tables, bounds, int8 tables ---------------------------------------------------
-@pytest.mark.parametrize("name", FLAT + IVF)
+@pytest.mark.parametrize("name", FLAT + IVF + OPQ)
 def test_table_pipeline_vs_oracle_and_reference(qadc, oracle, name):
     g = load(name)
     r, m = int(g["r"]), int(g["m"])
     ivf = "centroids" in g
     ma = int(g["ma"]) if ivf else 1
-    n = g["codes"].shape[0]
-    if ivf:
-        ix = ivf_index(qadc, int(g["dim"]), m, g["codebooks"], g["centroids"], g["codes"], g["labels"], g["offsets"],
-                       float(g["keep"]))
-    else:
-        ix = flat_index(qadc, int(g["dim"]), m, g["codebooks"], g["codes"], float(g["keep"]))
+    ix = golden_index(qadc, g)
     out = ix.build_tables(g["queries"], ma, r)
     assert out["rc"] == 0
-    db = dict(dim=int(g["dim"]), m=m, codebooks=g["codebooks"], codes=g["codes"], keep=float(g["keep"]),
-              offsets=g["offsets"] if ivf else np.array([0, n], np.int64))
-    if ivf:
-        db.update(centroids=g["centroids"], labels=g["labels"])
-    exp = oracle.search(db, g["queries"], ma, r)
+    exp = oracle.search(golden_db(g), g["queries"], ma, r)
     # the device uses the oracle's explicit float operations: expect bit equality
     assert np.array_equal(out["assign"], exp["assign"])
     assert np.array_equal(out["tables"], exp["tables"])
@@ -226,7 +226,7 @@ def test_table_pipeline_vs_oracle_and_reference(qadc, oracle, name):
     if ivf:
         assert np.array_equal(out["assign"], g["ref_assign"])
         for q in range(g["queries"].shape[0]):
-            resid = g["queries"][q][None, :] - g["centroids"][out["assign"][q]]
+            resid = rotated(g, g["queries"][q][None, :] - g["centroids"][out["assign"][q]])
             assert rel_err(out["tables"][q], g["ref_tables_used"][q], blas_scale(resid, g["codebooks"], m)) <= FLOAT_RTOL
     else:
         assert rel_err(out["tables"][:, 0], g["ref_tables_direct"], 1e-30) <= FLOAT_RTOL
@@ -273,20 +273,14 @@ def test_coarse_assignment_large_k(qadc, oracle):
 
 
 # ---- end to end ----------------------------------------------------------------------------
-@pytest.mark.parametrize("name", FLAT + IVF)
+@pytest.mark.parametrize("name", FLAT + IVF + OPQ)
 def test_search_end_to_end_golden_inputs(qadc, oracle, name):
     g = load(name)
     r, m = int(g["r"]), int(g["m"])
     ivf = "centroids" in g
     ma = int(g["ma"]) if ivf else 1
-    n = g["codes"].shape[0]
-    db = dict(dim=int(g["dim"]), m=m, codebooks=g["codebooks"], codes=g["codes"], keep=float(g["keep"]),
-              offsets=g["offsets"] if ivf else np.array([0, n], np.int64))
-    if ivf:
-        db.update(centroids=g["centroids"], labels=g["labels"])
-        ix = ivf_index(qadc, db["dim"], m, g["codebooks"], g["centroids"], g["codes"], g["labels"], g["offsets"], db["keep"])
-    else:
-        ix = flat_index(qadc, db["dim"], m, g["codebooks"], g["codes"], db["keep"])
+    db = golden_db(g)
+    ix = golden_index(qadc, g)
     ids, d, cnt = ix.search(g["queries"], ma, r)
     exp = oracle.search(db, g["queries"], ma, r)
     assert np.array_equal(cnt, exp["count"]) and np.array_equal(d, exp["d"]) and np.array_equal(ids, exp["ids"])

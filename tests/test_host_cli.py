@@ -30,7 +30,92 @@ def test_cli_rejects_non_database(cli, tmp_path):
     f = tmp_path / "x.qdb"
     f.write_bytes(b"not a database at all, just bytes" * 4)
     p = subprocess.run([cli, str(f), str(f), str(f)], capture_output=True, text=True)
-    assert p.returncode == 1 and "not a .qdb database" in p.stderr
+    assert p.returncode == 1 and "is not a database file" in p.stderr
+
+
+# ---- database files: the reference's archive layout and the .qdb container --------------------
+ARCHIVE_KINDS = [(ivf, opq) for ivf in (False, True) for opq in (False, True)]
+
+
+def archive_kwargs(g, ivf, opq):
+    kw = dict(dim=int(g["dim"]), m=int(g["m"]), codebooks=g["codebooks"], codes=g["ivf_codes"] if ivf else g["codes"],
+              rotation=g["rotation"] if opq else None)
+    if ivf:
+        kw.update(centroids=g["centroids"], labels=g["labels"], offsets=g["offsets"])
+    return kw
+
+
+def archive_key(ivf, opq):
+    return "ref_%s_%s" % ("index" if ivf else "flat", "opq" if opq else "pq")
+
+
+@pytest.mark.parametrize("ivf,opq", ARCHIVE_KINDS)
+def test_archive_writer_matches_reference_files(qadc, tmp_path, ivf, opq):
+    """dbfile.write_archive_db == the bytes the reference's save() members produced
+    (tests/golden/archives.npz), and read_db gets the arrays back."""
+    from qadc_b200 import dbfile
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "archives.npz")))
+    kw = archive_kwargs(g, ivf, opq)
+    dbfile.write_archive_db(tmp_path / "a.db", **kw)
+    assert (tmp_path / "a.db").read_bytes() == g[archive_key(ivf, opq)].tobytes()
+    back = dbfile.read_db(tmp_path / "a.db")
+    for k, v in kw.items():
+        if v is None:
+            assert k not in back
+        else:
+            assert np.array_equal(back[k], v), k
+
+
+@pytest.mark.parametrize("ivf,opq", ARCHIVE_KINDS)
+def test_db_convert_reads_and_writes_reference_files(cli, qadc, tmp_path, ivf, opq):
+    """C++ host loader/saver (host/databases.hpp): reference archive -> .qdb -> archive, byte exact."""
+    from qadc_b200 import dbfile
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "archives.npz")))
+    ref_bytes = g[archive_key(ivf, opq)].tobytes()
+    (tmp_path / "ref.db").write_bytes(ref_bytes)
+    conv = os.path.join(HOST, "db_convert")
+    p = subprocess.run([conv, str(tmp_path / "ref.db"), str(tmp_path / "x.qdb")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert ("Indexed DB (partitions=6)" if ivf else "Flat DB") in p.stderr and ("opq" if opq else "pq") + " (dim=32" in p.stderr
+    assert "Vectors: 300" in p.stderr
+    dbfile.write_qdb(tmp_path / "y.qdb", **archive_kwargs(g, ivf, opq))
+    assert (tmp_path / "x.qdb").read_bytes() == (tmp_path / "y.qdb").read_bytes()
+    p = subprocess.run([conv, str(tmp_path / "x.qdb"), str(tmp_path / "back.db")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert (tmp_path / "back.db").read_bytes() == ref_bytes
+    # a truncated archive is rejected, not half-read
+    (tmp_path / "cut.db").write_bytes(ref_bytes[:len(ref_bytes) // 2])
+    p = subprocess.run([conv, str(tmp_path / "cut.db"), str(tmp_path / "z.qdb")], capture_output=True, text=True)
+    assert p.returncode == 1 and "is not a database file" in p.stderr
+
+
+@pytest.mark.parametrize("ivf,opq", ARCHIVE_KINDS)
+def test_reference_loads_our_files(ref, qadc, tmp_path, ivf, opq):
+    """The reference's load_database (query_common.hpp:321-328) reads a file written by this repo
+    and searches it exactly like the database it was built from in memory."""
+    from qadc_b200 import dbfile
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "archives.npz")))
+    kw = archive_kwargs(g, ivf, opq)
+    dbfile.write_archive_db(tmp_path / "ours.db", **kw)
+    loaded = ref.load(tmp_path / "ours.db")
+    assert loaded.info() == dict(index=int(ivf), opq=int(opq), dim=32, m=16, bits=4, partitions=6 if ivf else 1)
+    if ivf:
+        mem = ref.ivf(kw["dim"], kw["m"], kw["codebooks"], kw["centroids"], kw["codes"], kw["labels"], kw["offsets"])
+    else:
+        mem = ref.flat(kw["dim"], kw["m"], kw["codebooks"], kw["codes"])
+    if opq:
+        mem.set_rotation(kw["rotation"])
+    # the live reference writes the same bytes as the committed fixture
+    mem.save(tmp_path / "theirs.db")
+    assert (tmp_path / "theirs.db").read_bytes() == g[archive_key(ivf, opq)].tobytes()
+    q = synth.make_queries(np.random.default_rng(3), 5, kw["dim"])
+    res = []
+    for h in (loaded, mem):
+        h.prepare(0.2)
+        res.append(h.search(q, 3 if ivf else 1, 10, nthreads=1, blas_tables=False))
+        h.close()
+    for k in ("keys", "vals", "sizes"):
+        assert np.array_equal(res[0][k], res[1][k])
 
 
 def test_pq_data_round_trip(qadc, tmp_path):
@@ -48,9 +133,9 @@ def test_pq_data_round_trip(qadc, tmp_path):
     assert np.array_equal(np.frombuffer(raw[12:12 + 4 * 64 * 16], np.float32), cb.reshape(-1))
 
 
-def run_cli(cli, tmp_path, db_kwargs, queries, gt, r, ma, keep_percent, batch):
+def run_cli(cli, tmp_path, db_kwargs, queries, gt, r, ma, keep_percent, batch, archive=False):
     from qadc_b200 import dbfile
-    dbfile.write_qdb(tmp_path / "db.qdb", **db_kwargs)
+    (dbfile.write_archive_db if archive else dbfile.write_qdb)(tmp_path / "db.qdb", **db_kwargs)
     dbfile.write_vecs(tmp_path / "q.fvecs", queries)
     dbfile.write_vecs(tmp_path / "gt.ivecs", gt)
     out = tmp_path / "res.bin"
@@ -90,18 +175,23 @@ def test_cli_flat_matches_oracle(cli, oracle, tmp_path, batch):
 
 
 @pytest.mark.gpu
-def test_cli_ivf_matches_oracle(cli, oracle, tmp_path):
+@pytest.mark.parametrize("archive", [False, True])
+def test_cli_ivf_matches_oracle(cli, oracle, tmp_path, archive):
+    """archive=True: the database is an OPQ index_db file in the reference's own layout."""
     rng = np.random.default_rng(32)
     dim, m, n, K, ma, nq, r = 96, 32, 20000, 40, 6, 9, 30
     cb = synth.make_pq(rng, dim, m)
     cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
     codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(7,))
     q = synth.make_queries(rng, nq, dim)
-    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels,
-                             keep=np.float32(5 * 0.01), offsets=offsets), q, ma, r, want_tables=False)
+    rot = np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32) if archive else None
+    db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=np.float32(5 * 0.01), offsets=offsets)
+    if archive:
+        db["rotation"] = rot
+    exp = oracle.search(db, q, ma, r, want_tables=False)
     gt = exp["ids"][:, :1].astype(np.int32).copy()
     fields, ids, d = run_cli(cli, tmp_path, dict(dim=dim, m=m, codebooks=cb, codes=codes, centroids=cents, labels=labels,
-                                                 offsets=offsets), q, gt, r, ma, 5, 4)
+                                                 offsets=offsets, rotation=rot), q, gt, r, ma, 5, 4, archive=archive)
     assert float(fields[1]) == 1.0 and fields[2] == str(ma)
     assert np.array_equal(d, exp["d"])
     for qi in range(nq):
@@ -113,10 +203,12 @@ def test_cli_ivf_matches_oracle(cli, oracle, tmp_path):
 @pytest.mark.parametrize("ivf", [False, True])
 def test_db_build_then_query(cli, oracle, tmp_path, ivf):
     """floats -> db_build (GPU encoder, the reference's flatdb_create/db_add chain) -> db_query_4:
-    same results as the oracle's encoder + search on the same inputs."""
+    same results as the oracle's encoder + search on the same inputs.  The inverted-list case goes
+    through a file in the reference's archive layout, the flat one through a .qdb container."""
     from qadc_b200 import dbfile
     rng = np.random.default_rng(33 + ivf)
     dim, m, n, nq, r, K, ma = 64, 16, 12000, 10, 20, 20, 4
+    dbname = str(tmp_path / ("db.index" if ivf else "db.qdb"))
     cb = synth.make_pq(rng, dim, m)
     base = rng.standard_normal((n, dim)).astype(np.float32)
     q = synth.make_queries(rng, nq, dim)
@@ -128,7 +220,7 @@ def test_db_build_then_query(cli, oracle, tmp_path, ivf):
         cents = base[rng.permutation(n)[:K]].copy()
         dbfile.write_vecs(tmp_path / "cents.fvecs", cents)
         cmd += ["-c", str(tmp_path / "cents.fvecs")]
-    cmd += [str(tmp_path / "q.pq.data"), str(tmp_path / "base.fvecs"), str(tmp_path / "db.qdb")]
+    cmd += [str(tmp_path / "q.pq.data"), str(tmp_path / "base.fvecs"), dbname]
     p = subprocess.run(cmd, capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert ("Indexed DB (partitions=20)" if ivf else "Flat DB") in p.stderr and "pq (dim=64, sq=16x4)" in p.stderr
@@ -151,7 +243,7 @@ def test_db_build_then_query(cli, oracle, tmp_path, ivf):
     dbfile.write_vecs(tmp_path / "gt.ivecs", gt)
     out = tmp_path / "res.bin"
     p = subprocess.run([cli, "-r", str(r), "-m", str(ma if ivf else 1), "-k", "10", "-b", "0", "-o", str(out),
-                        str(tmp_path / "db.qdb"), str(tmp_path / "q.fvecs"), str(tmp_path / "gt.ivecs")],
+                        dbname, str(tmp_path / "q.fvecs"), str(tmp_path / "gt.ivecs")],
                        capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert float(p.stdout.strip().splitlines()[1].split(",")[1]) == 1.0

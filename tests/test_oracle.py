@@ -11,11 +11,31 @@ import synth
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FLAT = ["flat_m16", "flat_m32"]
 IVF = ["ivf_m16", "ivf_m32"]
+OPQ = ["ivf_opq_m16"]   # inverted lists + OPQ rotation (quantizers.hpp:286-301)
 FLOAT_RTOL = 1e-5   # north_star: float tables within 1e-5 relative before quantisation
 
 
 def load(name):
     return dict(np.load(os.path.join(GOLD, name + ".npz")))
+
+
+def golden_db(g):
+    """Oracle database dict (oracle.search) of a golden fixture."""
+    ivf = "centroids" in g
+    db = dict(dim=int(g["dim"]), m=int(g["m"]), codebooks=g["codebooks"], codes=g["codes"], keep=float(g["keep"]),
+              offsets=g["offsets"] if ivf else np.array([0, g["codes"].shape[0]], np.int64))
+    if ivf:
+        db.update(centroids=g["centroids"], labels=g["labels"])
+    if "rotation" in g:
+        db["rotation"] = g["rotation"]
+    return db
+
+
+def rotated(g, vecs):
+    """X * R^T in float64 (the reference: sgemm NoTrans/Trans), identity without OPQ."""
+    if "rotation" not in g:
+        return vecs
+    return (vecs.astype(np.float64) @ g["rotation"].astype(np.float64).T).astype(np.float32)
 
 
 def rel_err(a, b, floor):
@@ -132,7 +152,7 @@ def test_canonical_rule_vs_reference_heap_flat(oracle, name):
     assert checked >= 1
 
 
-@pytest.mark.parametrize("name", IVF)
+@pytest.mark.parametrize("name", IVF + OPQ)
 def test_ivf_against_reference(oracle, name):
     g = load(name)
     r, m, ma = int(g["r"]), int(g["m"]), int(g["ma"])
@@ -148,7 +168,7 @@ def test_ivf_against_reference(oracle, name):
     for q in range(g["queries"].shape[0]):
         a = g["ref_assign"][q]
         # residual tables (direct form) vs the reference's blas-form tables
-        resid = g["queries"][q][None, :] - g["centroids"][a]
+        resid = rotated(g, g["queries"][q][None, :] - g["centroids"][a])
         mine = oracle.tables_direct(resid, m, g["codebooks"])
         assert rel_err(mine, g["ref_tables_used"][q], blas_scale(resid, g["codebooks"], m)) <= FLOAT_RTOL
         # bounds from the reference's tables
@@ -181,7 +201,7 @@ def test_ivf_against_reference(oracle, name):
     assert checked >= 1
 
 
-@pytest.mark.parametrize("name", FLAT + IVF)
+@pytest.mark.parametrize("name", FLAT + IVF + OPQ)
 def test_full_pipeline_self_consistent(oracle, name):
     """qo_search (the whole canonical pipeline) agrees with its own stages and stays within
     tolerance of the reference's float results."""
@@ -189,11 +209,7 @@ def test_full_pipeline_self_consistent(oracle, name):
     r, m = int(g["r"]), int(g["m"])
     ivf = "centroids" in g
     ma = int(g["ma"]) if ivf else 1
-    n = g["codes"].shape[0]
-    db = dict(dim=int(g["dim"]), m=m, codebooks=g["codebooks"], codes=g["codes"], keep=float(g["keep"]),
-              offsets=g["offsets"] if ivf else np.array([0, n], np.int64))
-    if ivf:
-        db.update(centroids=g["centroids"], labels=g["labels"])
+    db = golden_db(g)
     res = oracle.search(db, g["queries"], ma, r)
     assert res["rc"] == 0
     assert np.all(np.abs(res["qmax"] - g["ref_qmax"]) <= FLOAT_RTOL * g["ref_qmax"])
