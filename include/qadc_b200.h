@@ -118,6 +118,22 @@ int qadc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, uint
  * (distance << 48 | probe_rank << 32 | position) used to merge shards. */
 int qadc_search_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r,
                        uint32_t* d_ids, int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys);
+/* Same with the coarse assignment supplied by the caller (d_assign: nq*ma cell indices in probe
+ * order, on the device) instead of computed: the second half of a sharded search, after the
+ * ranks have exchanged their partial assignments (below). */
+int qadc_search_assigned_device(qadc_ctx* ctx, const float* d_queries, const int32_t* d_assign, int nq,
+                                int ma, int r, uint32_t* d_ids, int8_t* d_dists, int32_t* d_counts,
+                                uint64_t* d_keys);
+/* Sharded coarse assignment (index_db::assign_compute_residuals_mutiple -> find_k_neighbors,
+ * databases.hpp:213-231, neighbors.cpp:30-76, split over the GPUs of one box): every rank ranks
+ * the queries against the cells [c_first, c_first + c_count) only and returns its ma best as keys
+ * (float distance bits << 32 | global cell index), ascending, padded with ~0 when c_count < ma
+ * (d_out_keys: nq*ma).  After an all-gather, qadc_coarse_merge_device keeps the ma smallest of the
+ * G*ma keys of every query (d_keys laid out [G][nq][ma]) and writes their cell indices to d_assign
+ * (nq*ma) — the same assignment, bit for bit, as the unsharded search computes. */
+int qadc_coarse_partial_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int c_first,
+                               int c_count, uint64_t* d_out_keys);
+int qadc_coarse_merge_device(qadc_ctx* ctx, const uint64_t* d_keys, int G, int nq, int ma, int32_t* d_assign);
 /* Waits for the context's stream and reports deferred device-side conditions of earlier
  * asynchronous calls (QADC_EBOUND from qadc_search_device). */
 int qadc_synchronize(qadc_ctx* ctx);

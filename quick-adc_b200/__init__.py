@@ -69,6 +69,9 @@ def load_library(build_if_missing=True):
     L.qadc_finalize.argtypes = [vp, f32]
     L.qadc_search.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.qadc_search_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.qadc_search_assigned_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.qadc_coarse_partial_device.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.qadc_coarse_merge_device.argtypes = [vp, vp, i32, i32, i32, vp]
     L.qadc_synchronize.argtypes = [vp]
     L.qadc_last_launch_count.argtypes = [vp]
     L.qadc_last_scan_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -85,7 +88,8 @@ def load_library(build_if_missing=True):
                  "qadc_set_position_base", "qadc_set_prefix", "qadc_finalize", "qadc_search", "qadc_search_device",
                  "qadc_synchronize", "qadc_last_launch_count", "qadc_last_scan_ms", "qadc_merge_shards_device",
                  "qadc_build_tables", "qadc_scan_with_tables", "qadc_dump_distances", "qadc_download_codes",
-                 "qadc_set_option", "qadc_encode"):
+                 "qadc_set_option", "qadc_encode", "qadc_search_assigned_device", "qadc_coarse_partial_device",
+                 "qadc_coarse_merge_device"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -214,6 +218,21 @@ class Index:
         self._ck(self.lib.qadc_search_device(self.h, _ptr(int(d_queries)), nq, ma, r, _ptr(int(d_ids)),
                                              _ptr(int(d_dists)), _ptr(int(d_counts)),
                                              _ptr(None if d_keys is None else int(d_keys))))
+
+    def search_assigned_device(self, d_queries, d_assign, nq, ma, r, d_ids, d_dists, d_counts, d_keys=None):
+        """qadc_search_device with the coarse assignment (nq*ma int32 on the device) supplied."""
+        self._ck(self.lib.qadc_search_assigned_device(self.h, _ptr(int(d_queries)), _ptr(int(d_assign)), nq, ma, r,
+                                                      _ptr(int(d_ids)), _ptr(int(d_dists)), _ptr(int(d_counts)),
+                                                      _ptr(None if d_keys is None else int(d_keys))))
+
+    def coarse_partial_device(self, d_queries, nq, ma, c_first, c_count, d_out_keys):
+        """This rank's ma best cells among [c_first, c_first + c_count) as uint64 keys [nq][ma]."""
+        self._ck(self.lib.qadc_coarse_partial_device(self.h, _ptr(int(d_queries)), nq, ma, c_first, c_count,
+                                                     _ptr(int(d_out_keys))))
+
+    def coarse_merge_device(self, d_keys, G, nq, ma, d_assign):
+        """ma smallest of the gathered [G][nq][ma] keys per query -> assignment [nq][ma] int32."""
+        self._ck(self.lib.qadc_coarse_merge_device(self.h, _ptr(int(d_keys)), G, nq, ma, _ptr(int(d_assign))))
 
     def synchronize(self):
         self._ck(self.lib.qadc_synchronize(self.h))

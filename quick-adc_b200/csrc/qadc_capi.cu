@@ -347,7 +347,7 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
                                                               ctx->d_centroids, ctx->K, ctx->b_cdist.as<float>());
             QCK(cudaGetLastError());
             coarse_select_kernel<<<n, kSelThreads, 0, ctx->stream>>>(ctx->b_cdist.as<float>(), ctx->K, ma,
-                                                                    d_assign + static_cast<size_t>(q0) * ma);
+                                                                    d_assign + static_cast<size_t>(q0) * ma, nullptr, 0u);
             QCK(cudaGetLastError());
             ctx->launches += 2;
         }
@@ -658,8 +658,8 @@ int qadc_finalize(qadc_ctx* ctx, float keep) {
     return QADC_OK;
 }
 
-int qadc_search_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, uint32_t* d_ids,
-                       int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys) {
+static int search_device_impl(qadc_ctx* ctx, const float* d_queries, const int32_t* d_assign_in, int nq, int ma, int r,
+                              uint32_t* d_ids, int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys) {
     int rc = check_search_args(ctx, nq, ma, r);
     if (rc) return rc;
     QCK(cudaSetDevice(ctx->device));
@@ -667,7 +667,8 @@ int qadc_search_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, in
     // sub-batches keep every grid dimension below 65 536 and the per-batch scratch bounded
     for (int q0 = 0; q0 < nq; q0 += kMaxBatch) {
         const int n = std::min(kMaxBatch, nq - q0);
-        rc = tables_device(ctx, d_queries + static_cast<size_t>(q0) * ctx->dim, n, ma, r, nullptr, q0 == 0);
+        rc = tables_device(ctx, d_queries + static_cast<size_t>(q0) * ctx->dim, n, ma, r,
+                           d_assign_in ? d_assign_in + static_cast<size_t>(q0) * ma : nullptr, q0 == 0);
         if (rc) return rc;
         if (q0 == 0) QCK(cudaEventRecord(ctx->ev[3], ctx->stream));
         rc = scan_device(ctx, ctx->b_assign.as<int32_t>(), ctx->b_qtables.as<int8_t>(), n, ma, r,
@@ -677,6 +678,68 @@ int qadc_search_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, in
     }
     QCK(cudaEventRecord(ctx->ev[4], ctx->stream));
     QCK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return QADC_OK;
+}
+
+int qadc_search_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, uint32_t* d_ids,
+                       int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys) {
+    return search_device_impl(ctx, d_queries, nullptr, nq, ma, r, d_ids, d_dists, d_counts, d_keys);
+}
+
+int qadc_search_assigned_device(qadc_ctx* ctx, const float* d_queries, const int32_t* d_assign, int nq, int ma, int r,
+                                uint32_t* d_ids, int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys) {
+    if (!ctx) return QADC_EINVAL;
+    if (!d_assign) return fail(ctx, QADC_EINVAL, "null assignment");
+    return search_device_impl(ctx, d_queries, d_assign, nq, ma, r, d_ids, d_dists, d_counts, d_keys);
+}
+
+int qadc_coarse_partial_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int c_first, int c_count,
+                               uint64_t* d_out_keys) {
+    if (!ctx) return QADC_EINVAL;
+    if (ctx->K == 0) return fail(ctx, QADC_ESTATE, "no coarse quantizer (flat database)");
+    if (!d_queries || !d_out_keys) return fail(ctx, QADC_EINVAL, "null buffer");
+    if (nq <= 0 || ma <= 0 || ma > kSelCap / 2 || c_first < 0 || c_count < 0 || c_first + c_count > ctx->K)
+        return fail(ctx, QADC_EINVAL, "bad coarse range or ma");
+    QCK(cudaSetDevice(ctx->device));
+    const int dim = ctx->dim;
+    if (c_count == 0) {
+        QCK(cudaMemsetAsync(d_out_keys, 0xff, static_cast<size_t>(nq) * ma * 8, ctx->stream));
+        return QADC_OK;
+    }
+    const int chunk_q = std::max(1, static_cast<int>(std::min<size_t>(nq, (size_t(1) << 28) / c_count)));
+    ENSURE(ctx->b_cdist, static_cast<size_t>(chunk_q) * c_count * 4);
+    for (int q0 = 0; q0 < nq; q0 += chunk_q) {
+        const int n = std::min(chunk_q, nq - q0);
+        dim3 grid((n + kCoarseTQ - 1) / kCoarseTQ, (c_count + kCoarseTC - 1) / kCoarseTC);
+        coarse_dist_kernel<<<grid, 256, 0, ctx->stream>>>(d_queries + static_cast<size_t>(q0) * dim, n, dim,
+                                                          ctx->d_centroids + static_cast<size_t>(c_first) * dim, c_count,
+                                                          ctx->b_cdist.as<float>());
+        QCK(cudaGetLastError());
+        coarse_select_kernel<<<n, kSelThreads, 0, ctx->stream>>>(ctx->b_cdist.as<float>(), c_count, ma, nullptr,
+                                                                d_out_keys + static_cast<size_t>(q0) * ma,
+                                                                static_cast<uint32_t>(c_first));
+        QCK(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    return QADC_OK;
+}
+
+int qadc_coarse_merge_device(qadc_ctx* ctx, const uint64_t* d_keys, int G, int nq, int ma, int32_t* d_assign) {
+    if (!ctx) return QADC_EINVAL;
+    if (!d_keys || !d_assign) return fail(ctx, QADC_EINVAL, "null buffer");
+    if (G <= 0 || nq <= 0 || ma <= 0) return fail(ctx, QADC_EINVAL, "bad merge shape");
+    const int n_sort = next_pow2(std::max(G * ma, 2));
+    if (static_cast<size_t>(n_sort) * 8 > kMaxSmem) return fail(ctx, QADC_EINVAL, "G * ma too large for the coarse merge");
+    QCK(cudaSetDevice(ctx->device));
+    QCK(cudaFuncSetAttribute(coarse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n_sort * 8));
+    for (int q0 = 0; q0 < nq; q0 += kMaxBatch) {   // grid.x limit is not an issue; keep launches bounded like the search
+        const int n = std::min(kMaxBatch, nq - q0);
+        coarse_merge_kernel<<<n, 256, static_cast<size_t>(n_sort) * 8, ctx->stream>>>(d_keys + static_cast<size_t>(q0) * ma, G, nq,
+                                                                                       ma, n_sort,
+                                                                                       d_assign + static_cast<size_t>(q0) * ma);
+        QCK(cudaGetLastError());
+        ctx->launches++;
+    }
     return QADC_OK;
 }
 
@@ -874,7 +937,7 @@ int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* ou
                 dim3 grid((nn + kCoarseTQ - 1) / kCoarseTQ, (ctx->K + kCoarseTC - 1) / kCoarseTC);
                 coarse_dist_kernel<<<grid, 256, 0, ctx->stream>>>(d_x + static_cast<size_t>(q0) * dim, nn, dim, ctx->d_centroids,
                                                                   ctx->K, ctx->b_cdist.as<float>());
-                coarse_select_kernel<<<nn, kSelThreads, 0, ctx->stream>>>(ctx->b_cdist.as<float>(), ctx->K, 1, d_assign + q0);
+                coarse_select_kernel<<<nn, kSelThreads, 0, ctx->stream>>>(ctx->b_cdist.as<float>(), ctx->K, 1, d_assign + q0, nullptr, 0u);
                 QCK(cudaGetLastError());
             }
             if (out_assign)

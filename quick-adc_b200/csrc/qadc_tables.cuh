@@ -113,8 +113,10 @@ __global__ void __launch_bounds__(256) coarse_dist_kernel(const float* __restric
     }
 }
 
+// out_assign (cell indices) or out_keys (distance bits << 32 | index_base + cell, ~0 padded) is written.
 __global__ void __launch_bounds__(kSelThreads) coarse_select_kernel(const float* __restrict__ dist, int K, int ma,
-                                                                    int32_t* __restrict__ out_assign) {
+                                                                    int32_t* __restrict__ out_assign,
+                                                                    uint64_t* __restrict__ out_keys, uint32_t index_base) {
     __shared__ uint64_t keys[kSelCap];
     __shared__ int count;
     __shared__ unsigned long long bound_key;
@@ -133,8 +135,28 @@ __global__ void __launch_bounds__(kSelThreads) coarse_select_kernel(const float*
             top.push((static_cast<uint64_t>(__float_as_uint(d[c])) << 32) | static_cast<uint32_t>(c));
         top.maybe_compact(ma, tid, base + kSelCap / 2 >= K);
     }
-    for (int a = tid; a < ma; a += kSelThreads)
-        out_assign[static_cast<size_t>(q) * ma + a] = (a < count) ? static_cast<int32_t>(static_cast<uint32_t>(keys[a])) : 0;
+    for (int a = tid; a < ma; a += kSelThreads) {
+        if (out_assign) out_assign[static_cast<size_t>(q) * ma + a] = (a < count) ? static_cast<int32_t>(static_cast<uint32_t>(keys[a])) : 0;
+        if (out_keys) out_keys[static_cast<size_t>(q) * ma + a] = (a < count) ? keys[a] + index_base : ~0ull;
+    }
+}
+
+// Sharded coarse assignment, second half: the ma smallest of the G*ma keys of one query
+// (keys laid out [G][nq][ma]); one CTA per query, bitonic sort in shared memory.
+__global__ void __launch_bounds__(256) coarse_merge_kernel(const uint64_t* __restrict__ keys, int G, int nq, int ma,
+                                                           int n_sort, int32_t* __restrict__ out_assign) {
+    extern __shared__ __align__(16) uint64_t mk[];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < n_sort; i += 256) {
+        const int g = i / ma, a = i - g * ma;
+        mk[i] = (g < G) ? keys[(static_cast<size_t>(g) * nq + q) * ma + a] : ~0ull;
+    }
+    __syncthreads();
+    bitonic_sort_u64(mk, n_sort, tid, 256, BlockSync());
+    for (int a = tid; a < ma; a += 256) {
+        const uint64_t k = mk[a];
+        out_assign[static_cast<size_t>(q) * ma + a] = (k == ~0ull) ? 0 : static_cast<int32_t>(static_cast<uint32_t>(k));
+    }
 }
 
 // ---- residual -> rotation -> float tables: one WARP per (query, probe) ----------------------

@@ -4,7 +4,9 @@ Flat: contiguous ranges of whole 256-vector superblocks, so that global position
 shard offset + local position and the canonical order is preserved.  IVF: whole lists are
 assigned to GPUs (greedy by size); a list is never split.  Every shard keeps a replica of
 the keep-prefixes, so all shards derive identical quantisation bounds without a collective;
-the only exchange step is one all-gather of the per-shard top-r (key, id) lists.
+the exchange steps are one all-gather of the per-shard top-r (key, id) lists and, for inverted
+lists, one all-gather of the per-shard coarse candidates (the coarse quantizer's cells are split
+into contiguous ranges, so ranking the queries against K cells costs K/G per GPU).
 """
 import numpy as np
 
@@ -37,6 +39,35 @@ def ivf_list_owner(sizes, world):
         owner[p] = g
         load[g] += sizes[p]
     return owner
+
+
+def coarse_range(K, rank, world):
+    """[first, first + count) of the coarse cells rank `rank` ranks the queries against."""
+    base, extra = divmod(K, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def all_gather_keys(keys, group=None):
+    """All-gather of one int64 tensor [nq, k] -> [G, nq, k] in rank order (coarse candidates)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world * keys.shape[0],) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
+    dist.all_gather_into_tensor(out, keys.contiguous(), group=group)
+    return out.view((world,) + tuple(keys.shape))
+
+
+def sharded_coarse_assign(index, d_queries, nq, ma, K, rank, world, d_part_keys, d_assign, group=None):
+    """Coarse assignment with the cells split over the ranks: partial ranking on this GPU
+    (qadc_coarse_partial_device), one all-gather, merge (qadc_coarse_merge_device).  d_part_keys:
+    int64 CUDA tensor [nq, ma] (scratch), d_assign: int32 CUDA tensor [nq, ma] (result, identical on
+    every rank and identical to the unsharded assignment)."""
+    first, count = coarse_range(K, rank, world)
+    index.coarse_partial_device(d_queries.data_ptr(), nq, ma, first, count, d_part_keys.data_ptr())
+    gathered = all_gather_keys(d_part_keys, group) if world > 1 else d_part_keys.view((1,) + tuple(d_part_keys.shape))
+    index.coarse_merge_device(gathered.data_ptr(), world, nq, ma, d_assign.data_ptr())
+    return d_assign
 
 
 def all_gather_topk(keys, ids, group=None):

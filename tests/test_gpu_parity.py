@@ -492,6 +492,59 @@ def test_virtual_ivf_shards_merge_equals_single(qadc, oracle, G):
     mi.close()
 
 
+@pytest.mark.parametrize("G,K,ma", [(2, 48, 10), (8, 1500, 64), (3, 5, 4)])
+def test_sharded_coarse_assignment_equals_unsharded(qadc, oracle, G, K, ma):
+    """Cells split into G contiguous ranges: per-range top-ma keys (qadc_coarse_partial_device),
+    gathered [G][nq][ma], merged (qadc_coarse_merge_device) == the oracle's assignment; a search
+    with that assignment (qadc_search_assigned_device) == the plain search."""
+    import torch
+    from qadc_b200 import sharding
+    rng = np.random.default_rng(70 + G)
+    dim, m, n, nq, r, keep = 64, 16, 30000, 13, 20, 0.2
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    cents[K // 2] = cents[0]                       # duplicate cell: distance tie resolved by index
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m)
+    q = synth.make_queries(rng, nq, dim)
+    ix = ivf_index(qadc, dim, m, cb, cents, codes, labels, offsets, keep)
+    dq = torch.from_numpy(q).cuda()
+    gathered = torch.empty((G, nq, ma), dtype=torch.int64, device="cuda")
+    for g in range(G):
+        first, count = sharding.coarse_range(K, g, G)
+        ix.coarse_partial_device(dq.data_ptr(), nq, ma, first, count, gathered[g].data_ptr())
+    assign = torch.empty((nq, ma), dtype=torch.int32, device="cuda")
+    ix.coarse_merge_device(gathered.data_ptr(), G, nq, ma, assign.data_ptr())
+    ix.synchronize()
+    exp_assign, exp_dist = oracle.coarse_assign(q, cents, ma)
+    assert np.array_equal(assign.cpu().numpy(), exp_assign)
+    gk = gathered.cpu().numpy()
+    for g in range(G):                              # every partial list: ascending, inside its range, ~0 padded
+        first, count = sharding.coarse_range(K, g, G)
+        real = gk[g] != -1
+        assert np.all(real.sum(1) == min(ma, count))
+        assert np.all(np.diff(gk[g].view(np.uint64), axis=1) >= 0)
+        idx = (gk[g] & 0xffffffff)[real]
+        assert np.all((idx >= first) & (idx < first + count))
+    # search with the supplied assignment == search that computes it
+    outs = []
+    for supplied in (False, True):
+        ids = torch.empty((nq, r), dtype=torch.int32, device="cuda")
+        d = torch.empty((nq, r), dtype=torch.int8, device="cuda")
+        cnt = torch.empty(nq, dtype=torch.int32, device="cuda")
+        if supplied:
+            ix.search_assigned_device(dq.data_ptr(), assign.data_ptr(), nq, ma, r, ids.data_ptr(), d.data_ptr(), cnt.data_ptr())
+        else:
+            ix.search_device(dq.data_ptr(), nq, ma, r, ids.data_ptr(), d.data_ptr(), cnt.data_ptr())
+        ix.synchronize()
+        outs.append((ids.cpu().numpy(), d.cpu().numpy(), cnt.cpu().numpy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=keep,
+                             offsets=offsets), q, ma, r, want_tables=False)
+    assert np.array_equal(outs[1][0].view(np.uint32), exp["ids"]) and np.array_equal(outs[1][1], exp["d"])
+    ix.close()
+
+
 # ---- "next" row N1: PQ encoder on the GPU ----------------------------------------------------
 @pytest.mark.parametrize("name", ["encode_m16", "encode_m32"])
 def test_gpu_encoder_matches_reference_and_oracle(qadc, oracle, name):

@@ -133,6 +133,11 @@ def test_pq_data_round_trip(qadc, tmp_path):
     assert np.array_equal(np.frombuffer(raw[12:12 + 4 * 64 * 16], np.float32), cb.reshape(-1))
 
 
+def cli_keep(percent):
+    """`-k PERCENT` as db_query_4.cpp:342 computes it: atof(optarg) * ONE_PERCENT (double x float(0.01)) -> float."""
+    return np.float32(np.float64(percent) * np.float64(np.float32(0.01)))
+
+
 def run_cli(cli, tmp_path, db_kwargs, queries, gt, r, ma, keep_percent, batch, archive=False):
     from qadc_b200 import dbfile
     (dbfile.write_archive_db if archive else dbfile.write_qdb)(tmp_path / "db.qdb", **db_kwargs)
@@ -160,7 +165,7 @@ def test_cli_flat_matches_oracle(cli, oracle, tmp_path, batch):
     cb = synth.make_pq(rng, dim, m)
     codes = synth.make_codes(rng, n, m)
     q = synth.make_queries(rng, nq, dim)
-    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=np.float32(2 * 0.01), offsets=np.array([0, n], np.int64)),
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=cli_keep(2), offsets=np.array([0, n], np.int64)),
                         q, 1, r, want_tables=False)
     gt = exp["ids"][:, :1].astype(np.int32).copy()
     gt[::2] = n + 5   # half of the queries cannot be recalled
@@ -185,7 +190,7 @@ def test_cli_ivf_matches_oracle(cli, oracle, tmp_path, archive):
     codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(7,))
     q = synth.make_queries(rng, nq, dim)
     rot = np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32) if archive else None
-    db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=np.float32(5 * 0.01), offsets=offsets)
+    db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=cli_keep(5), offsets=offsets)
     if archive:
         db["rotation"] = rot
     exp = oracle.search(db, q, ma, r, want_tables=False)
@@ -225,7 +230,7 @@ def test_db_build_then_query(cli, oracle, tmp_path, ivf):
     assert p.returncode == 0, p.stderr
     assert ("Indexed DB (partitions=20)" if ivf else "Flat DB") in p.stderr and "pq (dim=64, sq=16x4)" in p.stderr
     # expected database built with the oracle: assignment, residual codes, insertion order per cell
-    keep = np.float32(10 * 0.01)
+    keep = cli_keep(10)
     if ivf:
         assign, _ = oracle.coarse_assign(base, cents, 1)
         assign = assign[:, 0]

@@ -43,6 +43,18 @@ def test_ivf_owner_is_balanced(qadc):
     assert load.sum() == sizes.sum() and load.max() - load.min() <= sizes.max()
 
 
+def test_coarse_ranges_partition_the_cells(qadc):
+    from qadc_b200 import sharding
+    for K in (1, 7, 37, 4096, 65536):
+        for world in (1, 2, 3, 8):
+            nxt = 0
+            for rank in range(world):
+                first, count = sharding.coarse_range(K, rank, world)
+                assert first == nxt and count >= 0
+                nxt = first + count
+            assert nxt == K
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -59,10 +71,14 @@ def _worker(rank, world, port, q):
     keys = np.sort((d << 48) | pos, axis=1)
     ids = (keys & 0xffffffff).astype(np.int32)
     gk, gi = sharding.all_gather_topk(torch.from_numpy(keys), torch.from_numpy(ids))
+    # coarse candidates: each rank's ma best cells of its own cell range, one all-gather
+    first, count = sharding.coarse_range(37, rank, world)
+    ck = np.sort((rng.integers(1, 1 << 30, (nq, 4)).astype(np.int64) << 32) | rng.integers(first, first + count, (nq, 4)), axis=1)
+    gc = sharding.all_gather_keys(torch.from_numpy(ck))
     if rank == 0:
-        q.put((gk.numpy(), gi.numpy()))
+        q.put((gk.numpy(), gi.numpy(), gc.numpy()))
     else:
-        q.put((keys, ids))
+        q.put((keys, ids, ck))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -84,7 +100,9 @@ def test_all_gather_layout_two_ranks_gloo():
         assert p.exitcode == 0
     gathered = [g for g in got if g[0].ndim == 3][0]
     local1 = [g for g in got if g[0].ndim == 2][0]
-    gk, gi = gathered
+    gk, gi, gc = gathered
+    assert gc.shape == (2, 5, 4) and np.array_equal(gc[1], local1[2])          # [G][nq][ma], rank order
+    assert np.all((gc[0] & 0xffffffff) < 19) and np.all((gc[1] & 0xffffffff) >= 19)   # cell ranges 0..18 | 19..36
     assert gk.shape == (2, 5, 7) and gi.shape == (2, 5, 7)
     assert np.array_equal(gk[1], local1[0]) and np.array_equal(gi[1], local1[1])   # rank order, [G][nq][r]
     # merging the gathered lists by key reproduces the global top-r of the union

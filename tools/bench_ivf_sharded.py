@@ -37,6 +37,10 @@ def main():
     ap.add_argument("--ma", type=int, default=MA)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--check", type=int, default=0, help="queries compared with an unsharded single-GPU index on rank 0")
+    ap.add_argument("--replicated-coarse", action="store_true",
+                    help="every rank ranks the queries against all K cells (no coarse exchange), for comparison")
+    ap.add_argument("--as-rank-of", type=int, default=0, metavar="W",
+                    help="single process: hold only rank 0's lists of a W-way sharding (per-GPU work of the W-GPU run, no exchange)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -54,7 +58,8 @@ def main():
     queries = rng.standard_normal((nq, DIM)).astype(np.float32)
     sizes = rng.multinomial(N, np.ones(Kc) / Kc).astype(np.int64)
     offsets = np.zeros(Kc + 1, np.int64); offsets[1:] = np.cumsum(sizes)
-    owner = sharding.ivf_list_owner(sizes, world)
+    shards = args.as_rank_of if (args.as_rank_of and world == 1) else world
+    owner = sharding.ivf_list_owner(sizes, shards)
 
     def build(index, mine):
         """mine: boolean mask of lists this index owns; prefixes are replicated for all lists."""
@@ -72,9 +77,9 @@ def main():
                 labels = torch.arange(int(offsets[p]), int(offsets[p + 1]), dtype=torch.int64, device=dev).to(torch.int32)
                 stream.synchronize()
                 index.upload_codes_device(p, 0, n_p, codes.data_ptr(), labels.data_ptr())
-                if world > 1:
+                if shards > 1:
                     index.set_prefix_device(p, codes.data_ptr(), npre)
-            elif world > 1:
+            elif shards > 1:
                 pre = bench.codes_torch(int(offsets[p]), int(offsets[p]) + npre, dev)
                 stream.synchronize()
                 index.set_prefix_device(p, pre.data_ptr(), npre)
@@ -88,8 +93,31 @@ def main():
     d_cnt = torch.empty(nq, dtype=torch.int32, device=dev); d_keys = torch.empty((nq, R), dtype=torch.int64, device=dev)
     o_ids, o_d, o_cnt = torch.empty_like(d_ids), torch.empty_like(d_d), torch.empty_like(d_cnt)
 
+    # coarse assignment: cells split over the ranks, one all-gather of the partial rankings, merge
+    split_coarse = shards > 1 and not args.replicated_coarse
+    d_assign = torch.empty((nq, ma), dtype=torch.int32, device=dev)
+    d_part = torch.empty((nq, ma), dtype=torch.int64, device=dev)
+    d_gath = None
+    if split_coarse and world == 1:
+        # --as-rank-of: the other ranks' partial rankings are computed once, outside the timed steps
+        d_gath = torch.empty((shards, nq, ma), dtype=torch.int64, device=dev)
+        for g in range(shards):
+            first, count = sharding.coarse_range(Kc, g, shards)
+            ix.coarse_partial_device(d_q.data_ptr(), nq, ma, first, count, d_gath[g].data_ptr())
+        ix.synchronize()
+
     def step():
-        ix.search_device(d_q.data_ptr(), nq, ma, R, d_ids.data_ptr(), d_d.data_ptr(), d_cnt.data_ptr(), d_keys.data_ptr())
+        if split_coarse:
+            if world > 1:
+                sharding.sharded_coarse_assign(ix, d_q, nq, ma, Kc, rank, world, d_part, d_assign)
+            else:
+                first, count = sharding.coarse_range(Kc, 0, shards)
+                ix.coarse_partial_device(d_q.data_ptr(), nq, ma, first, count, d_gath[0].data_ptr())
+                ix.coarse_merge_device(d_gath.data_ptr(), shards, nq, ma, d_assign.data_ptr())
+            ix.search_assigned_device(d_q.data_ptr(), d_assign.data_ptr(), nq, ma, R, d_ids.data_ptr(), d_d.data_ptr(),
+                                      d_cnt.data_ptr(), d_keys.data_ptr())
+        else:
+            ix.search_device(d_q.data_ptr(), nq, ma, R, d_ids.data_ptr(), d_d.data_ptr(), d_cnt.data_ptr(), d_keys.data_ptr())
         if world > 1:
             gk, gi = sharding.all_gather_topk(d_keys, d_ids)
             ix.merge_shards_device(gk.data_ptr(), gi.data_ptr(), world, nq, R, o_ids.data_ptr(), o_d.data_ptr(), o_cnt.data_ptr())
@@ -102,15 +130,24 @@ def main():
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = os.environ.get("QADC_PROFILE_RANGE") == "1"   # ncu --profile-from-start off: only the timed steps
+    if prof:
+        torch.cuda.profiler.start()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize(dev)
+    if prof:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1) / args.steps
     if world > 1:
         t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     ix.synchronize()
+    stages = None
+    if rank == 0:   # per-stage CUDA-event times of one more batch through the host-buffer entry point
+        _, _, _, met = ix.search(queries, ma, R, want_metrics=True)
+        stages = {n: float(getattr(met, n)) for n, _ in met._fields_}
 
     ok = None
     if args.check and rank == 0 and N * (M // 2) < 60e9:
@@ -125,8 +162,8 @@ def main():
     if rank == 0:
         scanned = float(ma) * N / Kc
         print(json.dumps({"config": "5: Deep1B-shaped IVF-%d PQ 16x4, nprobe %d, sharded lists" % (Kc, ma), "n_vectors": N,
-                          "n_gpus": world, "queries": nq, "ms_per_batch": ms, "queries_per_s": nq / (ms * 1e-3),
-                          "vectors_scanned_per_s": scanned * nq / (ms * 1e-3), "build_seconds": t_build,
+                          "n_gpus": world, "shards": shards, "coarse": "split" if split_coarse else "replicated", "queries": nq, "ms_per_batch": ms, "queries_per_s": nq / (ms * 1e-3),
+                          "vectors_scanned_per_s": scanned * nq / (ms * 1e-3), "build_seconds": t_build, "stage_metrics": stages,
                           "matches_unsharded": ok}))
     if world > 1:
         dist.barrier()
