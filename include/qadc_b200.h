@@ -183,7 +183,8 @@ int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* ou
 
 /* ---- tuning knobs (bench / tests) ------------------------------------------------------ */
 /* key: "flat_qb" (queries per pass of the flat scan: 1,2,4,8), "flat_chunks" (CTAs along
- * the database, 0 = auto), "time_scan" (1: record CUDA events around the scan kernel for
+ * the database, 0 = auto), "ivf_sb_per_item" (256-vector blocks per work item of the inverted-list
+ * scan, default 8), "time_scan" (1: record CUDA events around the scan kernel for
  * qadc_last_scan_ms).  Unknown key -> QADC_EINVAL. */
 int qadc_set_option(qadc_ctx* ctx, const char* key, long value);
 

@@ -67,6 +67,7 @@ struct qadc_ctx {
     int* h_err = nullptr;   // pinned
     // options / accounting
     long opt_flat_qb = 0, opt_flat_chunks = 0;
+    int ivf_sb_per_item = 8;   // superblocks per work item of the IVF scan (option "ivf_sb_per_item")
     int launches = 0;
     cudaEvent_t ev[8] = {};
     static constexpr int kScanRing = 64;
@@ -280,17 +281,18 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         if (rc) return rc == QADC_ENOMEM ? fail(ctx, rc, "scan kernel shared memory exceeds 227 KB") : rc;
     } else {
         const int cap = next_pow2(r + kSbVec);
-        const size_t smem = static_cast<size_t>(kNW) * cap * 8 + kNW * 8 + (128 + 2) * 4 + 16;
-        if (smem > kMaxSmem) return fail(ctx, QADC_EINVAL, "r too large for the IVF scan kernel");
         int chunks = std::max(1, std::min((ma + kNW - 1) / kNW, (2 * ctx->sm_count + nq - 1) / nq));
         const int ppc = (ma + chunks - 1) / chunks;
         chunks = (ma + ppc - 1) / ppc;
+        const size_t smem = ivf_smem_bytes(kNW, cap, ppc);
+        if (smem > kMaxSmem) return fail(ctx, QADC_EINVAL, "r or ma too large for the IVF scan kernel");
         n_lists = chunks * kNW;
         ENSURE(ctx->b_lists, static_cast<size_t>(nq) * n_lists * r * 8);
         IvfScanArgs a;
         a.codes = ctx->d_codes; a.part_sb_off = ctx->d_sb_off; a.part_size = ctx->d_size;
         a.part_pos_base = ctx->d_pos_base; a.assign = d_assign; a.qtabs = d_qtables; a.nq = nq; a.ma = ma;
-        a.r = r; a.cap = cap; a.probes_per_chunk = ppc; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
+        a.r = r; a.cap = cap; a.probes_per_chunk = ppc; a.sb_per_item = ctx->ivf_sb_per_item;
+        a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
         a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk;
         dim3 grid(chunks, nq);
         if (M == 16) {
@@ -967,6 +969,10 @@ int qadc_set_option(qadc_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return QADC_EINVAL;
     if (!strcmp(key, "flat_qb")) ctx->opt_flat_qb = value;
     else if (!strcmp(key, "flat_chunks")) ctx->opt_flat_chunks = value;
+    else if (!strcmp(key, "ivf_sb_per_item")) {
+        if (value < 1 || value > (1 << 20)) return fail(ctx, QADC_EINVAL, "ivf_sb_per_item out of range");
+        ctx->ivf_sb_per_item = static_cast<int>(value);
+    }
     else if (!strcmp(key, "time_scan")) ctx->scan_timed = value != 0;
     else return fail(ctx, QADC_EINVAL, std::string("unknown option ") + key);
     return QADC_OK;

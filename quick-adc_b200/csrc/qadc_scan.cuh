@@ -412,9 +412,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 }
 
 // ------------------------------------------------------------------------------------------
-// IVF scan: grid = (probe chunks, queries); each warp takes whole probes of its query in
-// rank order (rank a0+warp, a0+warp+NW, ...), loads that probe's int8 table and streams the
-// inverted list with coalesced 128-bit loads (lists are short and mostly L2-resident).
+// IVF scan: grid = (probe chunks, queries).  The CTA cuts the inverted lists of its probes into
+// work items of `sb_per_item` superblocks, numbered in canonical order (probe rank, position),
+// and its warps claim them from a shared counter: a warp therefore still visits its vectors in
+// increasing canonical order (what the strict pass rule of WarpList needs) while long and short
+// lists, and probes that are empty on this shard, no longer unbalance the warps.  Per item a
+// warp loads that probe's int8 table into registers (kept while consecutive items belong to
+// the same probe) and streams the superblocks with coalesced 128-bit loads.  (A per-warp TMA
+// ring with one-item lookahead was measured slower: the kernel is bound by candidate handling,
+// not by load latency.)
 // ------------------------------------------------------------------------------------------
 struct IvfScanArgs {
     const uint8_t* codes;            // native layout, all partitions
@@ -423,12 +429,20 @@ struct IvfScanArgs {
     const uint32_t* part_pos_base;   // [K]
     const int32_t* assign;           // [nq][ma]
     const int8_t* qtabs;             // [nq][ma][M*16]
-    int nq, ma, r, cap, probes_per_chunk;
+    int nq, ma, r, cap, probes_per_chunk, sb_per_item;
     uint64_t* lists;                 // [nq][n_lists][r]
     int n_lists;                     // gridDim.x * NW
     int* shared_bound;               // [nq]
     PipeK k;
 };
+
+// dynamic shared memory of scan_ivf_kernel: lists | counts, bounds | histogram | probe metadata
+__host__ __device__ inline size_t ivf_smem_bytes(int nw, int cap, int probes_per_chunk) {
+    size_t b = static_cast<size_t>(nw) * cap * 8 + static_cast<size_t>(nw) * 8;
+    b = (b + 15) / 16 * 16 + (128 + 4) * 4;                      // hist, hist_total, hist_next, next_item, pad
+    b += static_cast<size_t>(probes_per_chunk) * (8 + 4 + 4) + (static_cast<size_t>(probes_per_chunk) + 1) * 4;
+    return b;
+}
 
 template <int M, int NW>
 __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) {
@@ -440,32 +454,79 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.y;
     const int a0 = blockIdx.x * a.probes_per_chunk, a1 = min(a0 + a.probes_per_chunk, a.ma);
+    const int n_probe = a1 - a0;
     const PipeK pk = a.k;
 
     int* hist = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(bnd + NW) + 15) & ~uintptr_t(15));   // [128]
     int* hist_total = hist + 128;
     int* hist_next = hist_total + 1;
+    int* next_item = hist_next + 1;
+    uint64_t* m_off = reinterpret_cast<uint64_t*>(hist + 128 + 4);               // [ppc] first superblock of the probe's list
+    uint32_t* m_size = reinterpret_cast<uint32_t*>(m_off + a.probes_per_chunk);  // [ppc]
+    uint32_t* m_pos = m_size + a.probes_per_chunk;                               // [ppc]
+    int* item_off = reinterpret_cast<int*>(m_pos + a.probes_per_chunk);          // [ppc + 1] first item of probe i
+
     for (int i = threadIdx.x; i < 128; i += blockDim.x) hist[i] = 0;
-    if (threadIdx.x == 0) { *hist_total = 0; *hist_next = a.r; }
+    if (threadIdx.x == 0) { *hist_total = 0; *hist_next = a.r; *next_item = 0; }
     WarpList wl{lists + static_cast<size_t>(warp) * a.cap, cnt + warp, bnd + warp};
     for (int i = lane; i < a.cap; i += 32) wl.keys[i] = kEmptyKey;
     if (lane == 0) { *wl.count = 0; *wl.bound = 127; }
+    // probe metadata and the item numbering (warp 0: chunked warp scan over the probes)
+    if (warp == 0) {
+        int running = 0;
+        for (int base = 0; base < n_probe; base += 32) {
+            const int i = base + lane;
+            int items = 0;
+            if (i < n_probe) {
+                const int p = a.assign[static_cast<size_t>(q) * a.ma + a0 + i];
+                const uint32_t size = a.part_size[p];   // 0: nothing to scan (db_query_4.cpp:291-293)
+                m_size[i] = size;
+                m_pos[i] = a.part_pos_base[p];
+                m_off[i] = a.part_sb_off[p];
+                const uint32_t n_sb = (size + kSbVec - 1) / kSbVec;
+                items = static_cast<int>((n_sb + a.sb_per_item - 1) / a.sb_per_item);
+            }
+            int incl = items;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (i < n_probe) item_off[i + 1] = running + incl;
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) item_off[0] = 0;
+    }
     __syncthreads();
+    const int total_items = item_off[n_probe];
     const int compact_at = min(a.cap - kSbVec, 2 * a.r);
     int* sbound = a.shared_bound + q;
 
-    for (int ar = a0 + warp; ar < a1; ar += NW) {
-        const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
-        const uint32_t size = a.part_size[p];
-        if (size == 0) continue;   // db_query_4.cpp:291-293
-        const uint32_t pos_base = a.part_pos_base[p];
-        const uint4* tsrc = reinterpret_cast<const uint4*>(a.qtabs) + (static_cast<size_t>(q) * a.ma + ar) * M;
-        uint4 treg[M];
+    uint4 treg[M];
+    int cur = -1;   // probe (index in the chunk) whose table is in treg
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(next_item, 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= total_items) break;
+        int lo = 0, hi = n_probe;   // item_off[lo] <= it < item_off[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (item_off[mid] <= it) lo = mid; else hi = mid;
+        }
+        const int ar = a0 + lo;
+        const uint32_t size = m_size[lo], pos_base = m_pos[lo];
+        if (lo != cur) {
+            const uint4* tsrc = reinterpret_cast<const uint4*>(a.qtabs) + (static_cast<size_t>(q) * a.ma + ar) * M;
 #pragma unroll
-        for (int j = 0; j < M; ++j) treg[j] = __ldg(tsrc + j);
-        const uint8_t* base = a.codes + a.part_sb_off[p] * kSbBytes;
+            for (int j = 0; j < M; ++j) treg[j] = __ldg(tsrc + j);
+            cur = lo;
+        }
+        const uint8_t* base = a.codes + m_off[lo] * kSbBytes;
         const uint32_t n_sb = (size + kSbVec - 1) / kSbVec;
-        for (uint32_t sb = 0; sb < n_sb; ++sb) {
+        const uint32_t sb0 = static_cast<uint32_t>(it - item_off[lo]) * a.sb_per_item;
+        const uint32_t sb1 = min(sb0 + a.sb_per_item, n_sb);
+        for (uint32_t sb = sb0; sb < sb1; ++sb) {
             const uint32_t bound = static_cast<uint32_t>(min(*wl.bound, load_shared_bound(sbound) + 1));
             GroupAcc g;
             acc_init(g, bound);

@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 N=${1:-1000000000}; W=${2:-8}; Q=${3:-10000}
 python tools/bench_ivf_sharded.py --n-vectors $N --as-rank-of $W --queries $Q --steps 3 > gpurun_out/ivf5.log 2>&1
 tail -1 gpurun_out/ivf5.log | cut -c1-900
+[ -n "$NO_NCU" ] && exit 0
 QADC_PROFILE_RANGE=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 200 --csv \
     --log-file gpurun_out/launches_ivf5.csv python tools/bench_ivf_sharded.py --n-vectors $N --as-rank-of $W --queries $Q --steps 1 \
     > gpurun_out/ivf5_ncu.log 2>&1
