@@ -284,7 +284,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         int chunks = std::max(1, std::min((ma + kNW - 1) / kNW, (2 * ctx->sm_count + nq - 1) / nq));
         const int ppc = (ma + chunks - 1) / chunks;
         chunks = (ma + ppc - 1) / ppc;
-        const size_t smem = ivf_smem_bytes(kNW, cap, ppc);
+        const size_t smem = ivf_smem_bytes(M, kNW, cap, ppc);
         if (smem > kMaxSmem) return fail(ctx, QADC_EINVAL, "r or ma too large for the IVF scan kernel");
         n_lists = chunks * kNW;
         ENSURE(ctx->b_lists, static_cast<size_t>(nq) * n_lists * r * 8);

@@ -417,10 +417,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 // and its warps claim them from a shared counter: a warp therefore still visits its vectors in
 // increasing canonical order (what the strict pass rule of WarpList needs) while long and short
 // lists, and probes that are empty on this shard, no longer unbalance the warps.  Per item a
-// warp loads that probe's int8 table into registers (kept while consecutive items belong to
-// the same probe) and streams the superblocks with coalesced 128-bit loads.  (A per-warp TMA
-// ring with one-item lookahead was measured slower: the kernel is bound by candidate handling,
-// not by load latency.)
+// warp copies that probe's int8 table into its shared-memory slot (kept while consecutive items
+// belong to the same probe) and streams the superblocks with coalesced 128-bit loads; with the
+// tables out of the register file 3-4 CTAs fit an SM and the load latency is covered by
+// occupancy.  (A per-warp TMA ring with one-item lookahead was measured slower.)
 // ------------------------------------------------------------------------------------------
 struct IvfScanArgs {
     const uint8_t* codes;            // native layout, all partitions
@@ -436,19 +436,20 @@ struct IvfScanArgs {
     PipeK k;
 };
 
-// dynamic shared memory of scan_ivf_kernel: lists | counts, bounds | histogram | probe metadata
-__host__ __device__ inline size_t ivf_smem_bytes(int nw, int cap, int probes_per_chunk) {
-    size_t b = static_cast<size_t>(nw) * cap * 8 + static_cast<size_t>(nw) * 8;
+// dynamic shared memory of scan_ivf_kernel: tables | lists | counts, bounds | histogram | probe metadata
+__host__ __device__ inline size_t ivf_smem_bytes(int m, int nw, int cap, int probes_per_chunk) {
+    size_t b = static_cast<size_t>(nw) * m * 16 + static_cast<size_t>(nw) * cap * 8 + static_cast<size_t>(nw) * 8;
     b = (b + 15) / 16 * 16 + (128 + 4) * 4;                      // hist, hist_total, hist_next, next_item, pad
     b += static_cast<size_t>(probes_per_chunk) * (8 + 4 + 4) + (static_cast<size_t>(probes_per_chunk) + 1) * 4;
     return b;
 }
 
 template <int M, int NW>
-__global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) {
+__global__ void __launch_bounds__(NW * 32, M == 16 ? 4 : 3) scan_ivf_kernel(const IvfScanArgs a) {
     constexpr int kQuads = M / 4, kSbBytes = M * 128;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* lists = reinterpret_cast<uint64_t*>(smem);                         // [NW][cap]
+    uint4* wtab = reinterpret_cast<uint4*>(smem) + (threadIdx.x >> 5) * M;       // this warp's int8 table [M]
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem + NW * M * 16);           // [NW][cap]
     int* cnt = reinterpret_cast<int*>(lists + static_cast<size_t>(NW) * a.cap);  // [NW]
     int* bnd = cnt + NW;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -502,8 +503,7 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
     const int compact_at = min(a.cap - kSbVec, 2 * a.r);
     int* sbound = a.shared_bound + q;
 
-    uint4 treg[M];
-    int cur = -1;   // probe (index in the chunk) whose table is in treg
+    int cur = -1;   // probe (index in the chunk) whose table is in wtab
     for (;;) {
         int it = 0;
         if (lane == 0) it = atomicAdd(next_item, 1);
@@ -518,8 +518,9 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
         const uint32_t size = m_size[lo], pos_base = m_pos[lo];
         if (lo != cur) {
             const uint4* tsrc = reinterpret_cast<const uint4*>(a.qtabs) + (static_cast<size_t>(q) * a.ma + ar) * M;
-#pragma unroll
-            for (int j = 0; j < M; ++j) treg[j] = __ldg(tsrc + j);
+            __syncwarp();   // every lane is done with the previous table
+            if (lane < M) wtab[lane] = __ldg(tsrc + lane);
+            __syncwarp();
             cur = lo;
         }
         const uint8_t* base = a.codes + m_off[lo] * kSbBytes;
@@ -529,15 +530,14 @@ __global__ void __launch_bounds__(NW * 32) scan_ivf_kernel(const IvfScanArgs a) 
         for (uint32_t sb = sb0; sb < sb1; ++sb) {
             const uint32_t bound = static_cast<uint32_t>(min(*wl.bound, load_shared_bound(sbound) + 1));
             GroupAcc g;
-            acc_init(g, bound);
             const uint4* src = reinterpret_cast<const uint4*>(base + static_cast<size_t>(sb) * kSbBytes) + lane;
             uint4 w[kQuads];
 #pragma unroll
             for (int qd = 0; qd < kQuads; ++qd) w[qd] = __ldg(src + qd * 32);
 #pragma unroll
-            for (int qd = 0; qd < kQuads; ++qd) {
-                const uint4 tq[4] = {treg[4 * qd], treg[4 * qd + 1], treg[4 * qd + 2], treg[4 * qd + 3]};
-                lut_quad(w[qd], tq, g, pk);
+            for (int p = 0; p < M / 2; ++p) {   // pairs of sub-quantisers, tables read from shared memory (broadcast)
+                const uint4& wq = w[p >> 1];
+                scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, wtab[2 * p], wtab[2 * p + 1], g, pk, bound);
             }
             const bool mine = any_below(g);
             if (__any_sync(0xffffffffu, mine)) {
