@@ -358,9 +358,21 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
     // 2+3. residual, rotation, float tables
     {
         dim3 tgrid((ma + 7) / 8, nq);
-        tables_kernel<<<tgrid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(
-            d_queries, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
-            ctx->b_tables.as<float>(), ctx->b_tmin.as<float>());
+        auto launch_tables = [&](auto kernel) {
+            kernel<<<tgrid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(
+                d_queries, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
+                ctx->b_tables.as<float>(), ctx->b_tmin.as<float>());
+        };
+        switch (dim / M) {   // same arithmetic in every instantiation; the common sub-vector sizes unroll
+            case 2: launch_tables(tables_kernel<2>); break;
+            case 3: launch_tables(tables_kernel<3>); break;
+            case 4: launch_tables(tables_kernel<4>); break;
+            case 6: launch_tables(tables_kernel<6>); break;
+            case 8: launch_tables(tables_kernel<8>); break;
+            case 12: launch_tables(tables_kernel<12>); break;
+            case 16: launch_tables(tables_kernel<16>); break;
+            default: launch_tables(tables_kernel<0>); break;
+        }
         ctx->launches++;
         QCK(cudaGetLastError());
     }

@@ -124,16 +124,39 @@ __global__ void __launch_bounds__(kSelThreads) coarse_select_kernel(const float*
     const float* d = dist + static_cast<size_t>(q) * K;
     BlockTopK top{keys, &count, &bound_key};
     top.init(tid);
-    // first round: nothing to filter against yet, so the keys are stored directly (no shared atomics)
-    const int first = min(kSelCap / 2, K);
-    for (int c = tid; c < first; c += kSelThreads)
-        keys[c] = (static_cast<uint64_t>(__float_as_uint(d[c])) << 32) | static_cast<uint32_t>(c);
-    if (tid == 0) count = first;
-    top.maybe_compact(ma, tid, first >= K);
-    for (int base = first; base < K; base += kSelCap / 2) {
-        for (int c = base + tid; c < min(base + kSelCap / 2, K); c += kSelThreads)
-            top.push((static_cast<uint64_t>(__float_as_uint(d[c])) << 32) | static_cast<uint32_t>(c));
-        top.maybe_compact(ma, tid, base + kSelCap / 2 >= K);
+    auto key_of = [&](int c) { return (static_cast<uint64_t>(__float_as_uint(d[c])) << 32) | static_cast<uint32_t>(c); };
+    if (ma <= kSelThreads / 2 && K >= 8 * kSelThreads) {
+        // Pre-bound: the cells are dealt to the 256 threads round-robin; the ma-th smallest of the
+        // 256 per-thread minima has at least ma keys at or below it, so it is a valid filter, and
+        // for unordered data it lets through only a little more than ma keys.  One cheap rank
+        // computation replaces the sort of the first 1024 keys; the streaming rounds below
+        // (with their compaction as the safety net for adversarial orders) then see few keys.
+        __shared__ __align__(16) uint64_t mins[kSelThreads];
+        uint64_t mn = kEmptyKey;
+        for (int c = tid; c < K; c += kSelThreads) mn = min(mn, key_of(c));
+        mins[tid] = mn;
+        __syncthreads();
+        int rank = 0;
+        for (int i = 0; i < kSelThreads; i += 2) {
+            const ulonglong2 two = *reinterpret_cast<const ulonglong2*>(mins + i);   // broadcast
+            rank += (two.x < mn) + (two.y < mn);
+        }
+        if (rank == ma - 1) bound_key = mn + 1;   // keys are distinct, so exactly one thread has this rank
+        __syncthreads();
+        for (int base = 0; base < K; base += kSelCap / 2) {
+            for (int c = base + tid; c < min(base + kSelCap / 2, K); c += kSelThreads) top.push(key_of(c));
+            top.maybe_compact(ma, tid, base + kSelCap / 2 >= K);
+        }
+    } else {
+        // first round: nothing to filter against yet, so the keys are stored directly (no shared atomics)
+        const int first = min(kSelCap / 2, K);
+        for (int c = tid; c < first; c += kSelThreads) keys[c] = key_of(c);
+        if (tid == 0) count = first;
+        top.maybe_compact(ma, tid, first >= K);
+        for (int base = first; base < K; base += kSelCap / 2) {
+            for (int c = base + tid; c < min(base + kSelCap / 2, K); c += kSelThreads) top.push(key_of(c));
+            top.maybe_compact(ma, tid, base + kSelCap / 2 >= K);
+        }
     }
     for (int a = tid; a < ma; a += kSelThreads) {
         if (out_assign) out_assign[static_cast<size_t>(q) * ma + a] = (a < count) ? static_cast<int32_t>(static_cast<uint32_t>(keys[a])) : 0;
@@ -162,6 +185,8 @@ __global__ void __launch_bounds__(256) coarse_merge_kernel(const uint64_t* __res
 // ---- residual -> rotation -> float tables: one WARP per (query, probe) ----------------------
 // grid = (ceil(ma/8), nq), 8 warps per CTA.  tables[(q*ma + a)*M*16 + j*16 + c];
 // tmin[q*ma + a] = min entry of that table.
+// DSQ = sub-vector dimension when it is one of the common ones (loops unroll completely), 0 = any.
+template <int DSQ>
 __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ queries, int dim, int M,
                                                      const float* __restrict__ codebooks,
                                                      const float* __restrict__ rotation,    // or null
@@ -190,13 +215,14 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ q
         __syncwarp();
         x = rot;
     }
-    const int dsq = dim / M, blocks = dsq / 8, rem = dsq % 8;
+    const int dsq = DSQ ? DSQ : dim / M, blocks = dsq / 8, rem = dsq % 8;
     float local_min = 3.402823466e+38f;
     for (int e = lane; e < M * 16; e += 32) {
         const int j = e >> 4;
         const float* a = x + j * dsq;
         const float* b = codebooks + static_cast<size_t>(e) * dsq;   // (j*16 + c) * dsq
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
         for (int bl = 0; bl < blocks; ++bl) {
             float av[8], bv[8];
             if ((dsq & 3) == 0) {   // 16-byte aligned rows: two 128-bit loads each (same values, same order)
@@ -220,6 +246,7 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ q
 #pragma unroll
         for (int i = 0; i < 2; ++i) acc[i] = __fadd_rn(acc[i], acc[i + 2]);
         float norm = __fadd_rn(acc[0], acc[1]);
+#pragma unroll
         for (int i = 0; i < rem; ++i) {
             const float diff = __fsub_rn(__ldg(b + blocks * 8 + i), a[blocks * 8 + i]);
             norm = __fmaf_rn(diff, diff, norm);

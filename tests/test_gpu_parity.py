@@ -257,17 +257,31 @@ def test_opq_rotation(qadc, oracle):
     ix.close()
 
 
-def test_coarse_assignment_large_k(qadc, oracle):
-    """More than 256 cells: the fixed assignment (the reference's own is wrong there)."""
+@pytest.mark.parametrize("K,ma,order", [(1500, 16, "random"), (5000, 100, "random"), (4096, 64, "ascending"),
+                                        (4096, 64, "descending"), (8192, 64, "clustered"), (2048, 128, "random"),
+                                        (3000, 200, "random")])
+def test_coarse_assignment_large_k(qadc, oracle, K, ma, order):
+    """More than 256 cells: the fixed assignment (the reference's own is wrong there).
+    K >= 2048 with ma <= 128 takes the pre-bounded selection; the orders are its corner cases:
+    distances increasing / decreasing with the cell index, and all near cells dealt to 32 of the
+    256 selection threads (cell index mod 256 < 32), which floods the streaming rounds."""
     rng = np.random.default_rng(12)
-    dim, K, m, n, nq, ma, r = 32, 1500, 16, 30000, 20, 16, 50
+    dim, m, n, nq, r = 32, 16, 30000, 20, 50
     cb = synth.make_pq(rng, dim, m)
     cents = rng.standard_normal((K, dim)).astype(np.float32)
-    codes, labels, offsets = synth.make_ivf(rng, n, K, m)
     q = synth.make_queries(rng, nq, dim)
-    ix = ivf_index(qadc, dim, m, cb, cents, codes, labels, offsets, 0.3)
+    if order in ("ascending", "descending"):
+        direction = rng.standard_normal(dim).astype(np.float32)
+        scale = np.arange(K, dtype=np.float32) if order == "ascending" else np.arange(K, 0, -1).astype(np.float32)
+        cents = (10.0 + scale[:, None]) * direction[None, :] / np.linalg.norm(direction)
+        q = (0.01 * q).astype(np.float32)
+    elif order == "clustered":
+        near = (np.arange(K) % 256) < 32
+        cents[~near] += 50.0
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m)
+    ix = ivf_index(qadc, dim, m, cb, cents.astype(np.float32), codes, labels, offsets, 0.3)
     out = ix.build_tables(q, ma, r)
-    exp_assign, _ = oracle.coarse_assign(q, cents, ma)
+    exp_assign, _ = oracle.coarse_assign(q, cents.astype(np.float32), ma)
     assert np.array_equal(out["assign"], exp_assign)
     ix.close()
 
