@@ -303,6 +303,27 @@ struct WarpList {
         const int i = atomicAdd(count, 1);
         keys[i] = key;
     }
+    // Drop every entry farther than vmax (the query's shared bound: at least r scanned vectors are
+    // at or below it, so nothing farther can reach the top r).  Order-preserving, no sort: one pass
+    // with a ballot prefix.  All 32 lanes call it; the list is left unsorted.
+    __device__ __forceinline__ void filter(int vmax, int lane) {
+        __syncwarp();
+        const int cnt = *count;
+        int w = 0;
+        for (int base = 0; base < cnt; base += 32) {
+            const int i = base + lane;
+            const uint64_t key = (i < cnt) ? keys[i] : kEmptyKey;
+            const bool keep = i < cnt && static_cast<int>(key >> 48) <= vmax;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();   // the whole chunk is in registers before anything is written over it
+            if (keep) keys[w + __popc(m & ((1u << lane) - 1u))] = key;
+            w += __popc(m);
+        }
+        __syncwarp();
+        for (int i = w + lane; i < cnt; i += 32) keys[i] = kEmptyKey;
+        if (lane == 0) *count = w;
+        __syncwarp();
+    }
     // Keep the r smallest (sorted). All 32 lanes call it. Only the occupied power-of-two prefix is
     // sorted.  When the list is full its r-th distance is also published to the query's shared
     // bound (any vector farther than it can no longer be in the top r of the whole scan).

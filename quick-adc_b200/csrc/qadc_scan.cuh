@@ -547,10 +547,15 @@ __global__ void __launch_bounds__(NW * 32, M == 16 ? 4 : 3) scan_ivf_kernel(cons
                 __syncwarp();
                 const int now = *wl.count;
                 hist_update(hist, hist_total, hist_next, now - before, a.r, lane, sbound);
-                if (now >= compact_at) wl.compact(a.cap, a.r, lane, sbound);
+                if (now >= compact_at) {
+                    // cheap first: drop what the shared bound has overtaken; sort only if that frees little
+                    wl.filter(load_shared_bound(sbound), lane);
+                    if (*wl.count >= compact_at / 2) wl.compact(a.cap, a.r, lane, sbound);
+                }
             }
         }
     }
+    wl.filter(load_shared_bound(sbound), lane);
     wl.compact(a.cap, a.r, lane, sbound);
     store_list(wl, a.lists + (static_cast<size_t>(q) * a.n_lists + blockIdx.x * NW + warp) * a.r, a.r, lane);
 }
