@@ -155,13 +155,15 @@ __device__ __forceinline__ int hist_update(int* hist, int* hist_total, int* hist
     int total = 0;
     if (lane == 0) {
         total = atomicAdd(hist_total, added) + added;
-        if (total < *hist_next) total = -1;   // lane 0 alone decides (warp-uniform)
+        // lane 0 alone decides (warp-uniform); the threshold is shared by the CTA's warps, so it is
+        // read and raised with atomics (a stale value would only move the moment of the next update)
+        if (total < atomicAdd(hist_next, 0)) total = -1;
     }
     total = __shfl_sync(0xffffffffu, total, 0);
     if (total < 0) return 127;
     const int hb = hist_bound(hist, r, lane);
     if (lane == 0) {
-        *hist_next = total + max(r / 4, 8);
+        atomicMax(hist_next, total + max(r / 4, 8));
         if (hb < 127) atomicMin(shared_bound, hb);
     }
     return hb;
