@@ -181,6 +181,23 @@ int qadc_download_codes(qadc_ctx* ctx, int part_i, uint8_t* out_codes);
 int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* out_assign,
                 uint8_t* out_codes);
 
+/* ---- plain ADC: the reference's db_query tool ("next" row: scanner_simple, db_query.cpp:17-46;
+ * scan_standard<uint8_t,NSQ> / scan_4<NSQ>, query_common.hpp:59-147) ---------------------------- */
+/* Row-major codes of the whole database, partitions concatenated: partition p holds the vectors
+ * [offsets[p], offsets[p+1]) (partition_count + 1 offsets; 1 partition for a flat database, K for
+ * inverted lists, which also need `labels`).  Code size m*bits/8 bytes; 4-bit codes two per byte,
+ * low nibble first (quantizers.hpp:49-68).  Works for every quantiser qadc_set_pq accepts:
+ * (16,4) (32,4) (4,8) (8,8) (16,8); the 16-bit configurations of db_query are not supported.
+ * Independent of the Quick ADC database (qadc_begin_database .. qadc_finalize). */
+int qadc_adc_load(qadc_ctx* ctx, int partition_count, const uint64_t* offsets, const uint8_t* codes,
+                  const uint32_t* labels);
+/* Float ADC search, host buffers: out_ids / out_dists nq*r, ascending by (distance, probe rank,
+ * position) — the entries the reference's heap ends with (strict `candidate < max` test in scan
+ * order); out_counts[q] real entries, the rest are (0, FLT_MAX) like the reference's pre-filled
+ * heap slots (db_query.cpp:27-30).  Distances are summed in sub-quantiser order in float32. */
+int qadc_adc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, uint32_t* out_ids,
+                    float* out_dists, int32_t* out_counts);
+
 /* ---- tuning knobs (bench / tests) ------------------------------------------------------ */
 /* key: "flat_qb" (queries per pass of the flat scan: 1,2,4,8), "flat_chunks" (CTAs along
  * the database, 0 = auto), "ivf_sb_per_item" (256-vector blocks per work item of the inverted-list

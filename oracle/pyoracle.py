@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libqadc_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libqadc_ref.so")
+REF_ADC_SO = os.path.join(HERE, "_ref", "libqadc_ref_adc.so")   # db_query.cpp (plain ADC), own library
 
 u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
@@ -212,6 +213,25 @@ class Oracle:
         out["rc"] = rc
         return out
 
+    def adc_search(self, db, queries, ma, r):
+        """Plain ADC (db_query): db as for search() plus "bits" (4 or 8); float distances."""
+        queries = np.ascontiguousarray(queries, np.float32)
+        nq = queries.shape[0]
+        K = len(db["offsets"]) - 1 if db.get("centroids") is not None else 0
+        ids = np.empty((nq, r), np.uint32)
+        d = np.empty((nq, r), np.float32)
+        cnt = np.empty(nq, np.int32)
+        f = self.lib.qo_adc_search
+        f.restype = C.c_int
+        rc = f(C.c_int(db["dim"]), C.c_int(db["m"]), C.c_int(db.get("bits", 4)),
+               _opt(np.ascontiguousarray(db["codebooks"], np.float32).reshape(-1)), _opt(db.get("rotation")), C.c_int(K),
+               _opt(db.get("centroids")), _opt(np.ascontiguousarray(db["codes"])), _opt(db.get("labels")),
+               _opt(np.ascontiguousarray(db["offsets"], np.int64)), _opt(queries), C.c_int(nq), C.c_int(ma), C.c_int(r),
+               _opt(ids), _opt(d), _opt(cnt))
+        if rc:
+            raise ValueError("qo_adc_search: unsupported configuration")
+        return dict(ids=ids, d=d, count=cnt)
+
 
 class Ref:
     """The unmodified reference behind oracle/ref_harness.cpp."""
@@ -390,3 +410,36 @@ class Ref:
                                     np.ascontiguousarray(labels, np.uint32),
                                     np.ascontiguousarray(offsets, np.int64))
         return Ref.Handle(self, p, m, dim)
+
+
+class RefAdc:
+    """The unmodified db_query.cpp path (scanner_simple) behind oracle/ref_harness_adc.cpp."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_ADC_SO)
+
+    def __init__(self):
+        L = self.lib = C.CDLL(REF_ADC_SO)
+        L.refadc_create.restype = C.c_void_p
+        L.refadc_destroy.argtypes = [C.c_void_p]
+        L.refadc_search.restype = C.c_int
+
+    def search(self, db, queries, ma, r):
+        """db: dict(dim, m, bits, codebooks, [rotation], [centroids, labels], codes, offsets) -> ids, dists
+        (heap sorted by distance; always r entries, unfilled ones are (0, FLT_MAX - t))."""
+        queries = np.ascontiguousarray(queries, np.float32)
+        nq = queries.shape[0]
+        ivf = db.get("centroids") is not None
+        K = len(db["offsets"]) - 1 if ivf else 0
+        keep = [np.ascontiguousarray(db["codebooks"], np.float32).reshape(-1), np.ascontiguousarray(db["codes"]),
+                np.ascontiguousarray(db["offsets"], np.int64)]
+        lab = np.ascontiguousarray(db["labels"], np.uint32) if ivf else None
+        h = self.lib.refadc_create(C.c_int(db["dim"]), C.c_int(db["m"]), C.c_int(db.get("bits", 4)), _opt(keep[0]),
+                                   _opt(db.get("rotation")), C.c_int(K), _opt(db.get("centroids")), _opt(keep[1]),
+                                   _opt(lab), _opt(keep[2]))
+        ids = np.zeros((nq, r), np.uint32)
+        d = np.zeros((nq, r), np.float32)
+        self.lib.refadc_search(C.c_void_p(h), _opt(queries), C.c_int(nq), C.c_int(ma), C.c_int(r), _opt(ids), _opt(d))
+        self.lib.refadc_destroy(C.c_void_p(h))
+        return ids, d

@@ -72,6 +72,8 @@ def load_library(build_if_missing=True):
     L.qadc_search_assigned_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.qadc_coarse_partial_device.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     L.qadc_coarse_merge_device.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.qadc_adc_load.argtypes = [vp, i32, vp, vp, vp]
+    L.qadc_adc_search.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     L.qadc_synchronize.argtypes = [vp]
     L.qadc_last_launch_count.argtypes = [vp]
     L.qadc_last_scan_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -89,7 +91,7 @@ def load_library(build_if_missing=True):
                  "qadc_synchronize", "qadc_last_launch_count", "qadc_last_scan_ms", "qadc_merge_shards_device",
                  "qadc_build_tables", "qadc_scan_with_tables", "qadc_dump_distances", "qadc_download_codes",
                  "qadc_set_option", "qadc_encode", "qadc_search_assigned_device", "qadc_coarse_partial_device",
-                 "qadc_coarse_merge_device"):
+                 "qadc_coarse_merge_device", "qadc_adc_load", "qadc_adc_search"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -233,6 +235,23 @@ class Index:
     def coarse_merge_device(self, d_keys, G, nq, ma, d_assign):
         """ma smallest of the gathered [G][nq][ma] keys per query -> assignment [nq][ma] int32."""
         self._ck(self.lib.qadc_coarse_merge_device(self.h, _ptr(int(d_keys)), G, nq, ma, _ptr(int(d_assign))))
+
+    # ---- plain ADC (db_query) -------------------------------------------------------------
+    def adc_load(self, codes, labels=None, offsets=None):
+        """Row-major codes [n, m*bits/8]; inverted lists: labels [n] and offsets [K+1]."""
+        codes = np.ascontiguousarray(codes, np.uint8)
+        off = np.ascontiguousarray([0, codes.shape[0]] if offsets is None else offsets, np.uint64)
+        lab = None if labels is None else np.ascontiguousarray(labels, np.uint32)
+        self._ck(self.lib.qadc_adc_load(self.h, len(off) - 1, _ptr(off), _ptr(codes), _ptr(lab)))
+
+    def adc_search(self, queries, ma, r):
+        q = np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        ids = np.empty((nq, r), np.uint32)
+        d = np.empty((nq, r), np.float32)
+        cnt = np.empty(nq, np.int32)
+        self._ck(self.lib.qadc_adc_search(self.h, _ptr(q), nq, ma, r, _ptr(ids), _ptr(d), _ptr(cnt)))
+        return ids, d, cnt
 
     def synchronize(self):
         self._ck(self.lib.qadc_synchronize(self.h))

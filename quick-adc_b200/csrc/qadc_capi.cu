@@ -10,6 +10,7 @@
 #include "../../include/qadc_b200.h"
 #include "qadc_scan.cuh"
 #include "qadc_tables.cuh"
+#include "qadc_adc.cuh"
 
 using namespace qadc;
 
@@ -42,7 +43,7 @@ struct qadc_ctx {
     bool own_stream = false;
     std::string err;
     // quantisers
-    int dim = 0, m = 0;
+    int dim = 0, m = 0, bits = 4;
     float* d_codebooks = nullptr;
     float* d_rotation = nullptr;
     int K = 0;
@@ -60,6 +61,12 @@ struct qadc_ctx {
     uint32_t *d_size = nullptr, *d_pos_base = nullptr, *d_start_size = nullptr;
     uint8_t* d_starts = nullptr;
     uint32_t max_start = 0;
+    // plain-ADC database (db_query path): row-major codes, independent of the Quick ADC layout above
+    int adc_parts = 0;
+    uint8_t* d_rows = nullptr;
+    uint64_t* d_row_off = nullptr;    // [adc_parts + 1]
+    uint32_t* d_adc_labels = nullptr;
+    DevBuf b_adc_dists;
     // scratch
     DevBuf staging, b_queries, b_assign, b_tables, b_tmin, b_qmax, b_qmin, b_qtables, b_lists, b_plists, b_ids,
         b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound, b_cdist;
@@ -361,7 +368,7 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         auto launch_tables = [&](auto kernel) {
             kernel<<<tgrid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(
                 d_queries, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
-                ctx->b_tables.as<float>(), ctx->b_tmin.as<float>());
+                ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), 4);
         };
         switch (dim / M) {   // same arithmetic in every instantiation; the common sub-vector sizes unroll
             case 2: launch_tables(tables_kernel<2>); break;
@@ -481,8 +488,9 @@ void qadc_destroy(qadc_ctx* c) {
     cudaFree(c->d_codebooks); cudaFree(c->d_rotation); cudaFree(c->d_centroids);
     for (DevBuf* b : {&c->staging, &c->b_queries, &c->b_assign, &c->b_tables, &c->b_tmin, &c->b_qmax, &c->b_qmin,
                       &c->b_qtables, &c->b_lists, &c->b_plists, &c->b_ids, &c->b_dists, &c->b_counts, &c->b_keys,
-                      &c->b_dump, &c->b_hist, &c->b_sbound, &c->b_cdist})
+                      &c->b_dump, &c->b_hist, &c->b_sbound, &c->b_cdist, &c->b_adc_dists})
         cudaFree(b->p);
+    cudaFree(c->d_rows); cudaFree(c->d_row_off); cudaFree(c->d_adc_labels);
     cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -497,14 +505,17 @@ const char* qadc_last_error(const qadc_ctx* c) { return c ? c->err.c_str() : g_c
 int qadc_set_pq(qadc_ctx* ctx, int dim, int m, int bits, const float* codebooks, const float* rotation) {
     if (!ctx || !codebooks) return fail(ctx, QADC_EINVAL, "null argument");
     // get_simd_scan_func_epi8 (db_query_4.cpp:23-35), load_database_check (:393-402)
-    if (bits != 4) return fail(ctx, QADC_EINVAL, "Quantizer must have sq_bits=4");
-    if (m != 16 && m != 32)
-        return fail(ctx, QADC_EINVAL, "Unsupported (nsq,nsq_bits) configuration. Supported: (16,4) (32,4).");
+    // plus the 8-bit configurations of the plain ADC tool (get_scan_func, query_common.hpp:122-147); those
+    // contexts only serve qadc_adc_load / qadc_adc_search
+    const bool quick = bits == 4 && (m == 16 || m == 32);
+    const bool adc8 = bits == 8 && (m == 4 || m == 8 || m == 16);
+    if (!quick && !adc8)
+        return fail(ctx, QADC_EINVAL, "Unsupported (nsq,nsq_bits) configuration. Supported: (16,4) (32,4); plain ADC also (4,8) (8,8) (16,8).");
     if (dim <= 0 || dim % m != 0) return fail(ctx, QADC_EINVAL, "dim must be a positive multiple of m");
     QCK(cudaSetDevice(ctx->device));
     cudaFree(ctx->d_codebooks); cudaFree(ctx->d_rotation);
     ctx->d_codebooks = nullptr; ctx->d_rotation = nullptr;
-    const size_t cb = static_cast<size_t>(dim) * 16 * sizeof(float);
+    const size_t cb = (static_cast<size_t>(dim) << bits) * sizeof(float);
     QCK(cudaMalloc(&ctx->d_codebooks, cb));
     QCK(cudaMemcpy(ctx->d_codebooks, codebooks, cb, cudaMemcpyHostToDevice));
     if (rotation) {
@@ -512,7 +523,7 @@ int qadc_set_pq(qadc_ctx* ctx, int dim, int m, int bits, const float* codebooks,
         QCK(cudaMalloc(&ctx->d_rotation, rb));
         QCK(cudaMemcpy(ctx->d_rotation, rotation, rb, cudaMemcpyHostToDevice));
     }
-    ctx->dim = dim; ctx->m = m;
+    ctx->dim = dim; ctx->m = m; ctx->bits = bits;
     return QADC_OK;
 }
 
@@ -533,6 +544,7 @@ int qadc_set_coarse(qadc_ctx* ctx, int K, const float* centroids) {
 int qadc_begin_database(qadc_ctx* ctx, int partition_count, const uint32_t* sizes, int has_labels) {
     if (!ctx || !sizes || partition_count <= 0) return fail(ctx, QADC_EINVAL, "bad database description");
     if (ctx->m == 0) return fail(ctx, QADC_ESTATE, "qadc_set_pq must be called first");
+    if (ctx->bits != 4) return fail(ctx, QADC_EINVAL, "Quantizer must have sq_bits=4");   // load_database_check, db_query_4.cpp:393-402
     if (ctx->K == 0 && partition_count != 1) return fail(ctx, QADC_EINVAL, "a flat database has exactly one partition");
     if (ctx->K > 0 && partition_count != ctx->K) return fail(ctx, QADC_EINVAL, "partition_count != coarse centroid count");
     QCK(cudaSetDevice(ctx->device));
@@ -926,6 +938,7 @@ int qadc_download_codes(qadc_ctx* ctx, int part_i, uint8_t* out_codes) {
 int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* out_assign, uint8_t* out_codes) {
     if (!ctx || !vectors || !out_codes) return fail(ctx, QADC_EINVAL, "null buffer");
     if (ctx->m == 0) return fail(ctx, QADC_ESTATE, "qadc_set_pq must be called first");
+    if (ctx->bits != 4) return fail(ctx, QADC_EINVAL, "Quantizer must have sq_bits=4");
     if (count == 0) return QADC_OK;
     QCK(cudaSetDevice(ctx->device));
     const int dim = ctx->dim, M = ctx->m, CS = M / 2;
@@ -973,6 +986,139 @@ int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* ou
         QCK(cudaMemcpyAsync(out_codes + static_cast<size_t>(off) * CS, ctx->b_dump.p, static_cast<size_t>(n) * CS,
                             cudaMemcpyDeviceToHost, ctx->stream));
         QCK(cudaStreamSynchronize(ctx->stream));
+    }
+    return QADC_OK;
+}
+
+// ---- plain ADC (db_query): row-major database + float scan ---------------------------------
+int qadc_adc_load(qadc_ctx* ctx, int partition_count, const uint64_t* offsets, const uint8_t* codes,
+                  const uint32_t* labels) {
+    if (!ctx || !offsets || partition_count <= 0) return fail(ctx, QADC_EINVAL, "bad database description");
+    if (ctx->m == 0) return fail(ctx, QADC_ESTATE, "qadc_set_pq must be called first");
+    if (ctx->K == 0 && partition_count != 1) return fail(ctx, QADC_EINVAL, "a flat database has exactly one partition");
+    if (ctx->K > 0 && partition_count != ctx->K) return fail(ctx, QADC_EINVAL, "partition_count != coarse centroid count");
+    if (ctx->K > 0 && !labels) return fail(ctx, QADC_EINVAL, "inverted lists need labels");
+    for (int p = 0; p < partition_count; ++p)
+        if (offsets[p + 1] < offsets[p]) return fail(ctx, QADC_EINVAL, "offsets must be non-decreasing");
+    const uint64_t n = offsets[partition_count] - offsets[0];
+    if (n > 0 && !codes) return fail(ctx, QADC_EINVAL, "codes is null");
+    if (n >= (uint64_t(1) << 32)) return fail(ctx, QADC_EINVAL, "more than 2^32 - 1 vectors");
+    QCK(cudaSetDevice(ctx->device));
+    cudaFree(ctx->d_rows); cudaFree(ctx->d_row_off); cudaFree(ctx->d_adc_labels);
+    ctx->d_rows = nullptr; ctx->d_row_off = nullptr; ctx->d_adc_labels = nullptr; ctx->adc_parts = 0;
+    const size_t cs = static_cast<size_t>(ctx->m) * ctx->bits / 8;
+    std::vector<uint64_t> rel(partition_count + 1);
+    for (int p = 0; p <= partition_count; ++p) rel[p] = offsets[p] - offsets[0];
+    QCK(cudaMalloc(&ctx->d_rows, std::max<size_t>(16, n * cs)));
+    QCK(cudaMalloc(&ctx->d_row_off, rel.size() * 8));
+    QCK(cudaMemcpy(ctx->d_row_off, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice));
+    if (n) QCK(cudaMemcpy(ctx->d_rows, codes + offsets[0] * cs, n * cs, cudaMemcpyHostToDevice));
+    if (labels) {
+        QCK(cudaMalloc(&ctx->d_adc_labels, std::max<size_t>(4, n * 4)));
+        if (n) QCK(cudaMemcpy(ctx->d_adc_labels, labels + offsets[0], n * 4, cudaMemcpyHostToDevice));
+    }
+    ctx->adc_parts = partition_count;
+    return QADC_OK;
+}
+
+int qadc_adc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, uint32_t* out_ids, float* out_dists,
+                    int32_t* out_counts) {
+    if (!ctx) return QADC_EINVAL;
+    if (ctx->adc_parts == 0) return fail(ctx, QADC_ESTATE, "qadc_adc_load must be called first");
+    if (!queries || !out_ids || !out_dists) return fail(ctx, QADC_EINVAL, "null buffer");
+    if (nq <= 0 || ma <= 0 || r <= 0) return fail(ctx, QADC_EINVAL, "nq, ma and r must be positive");
+    if (r > kSelCap / 2) return fail(ctx, QADC_EINVAL, "r > 1024 is not supported");
+    if (ctx->K == 0 && ma != 1) return fail(ctx, QADC_EINVAL, "a flat database must be queried with ma = 1 (SURVEY App. B)");
+    if (ctx->K > 0 && (ma > ctx->K || ma > kSelCap / 2)) return fail(ctx, QADC_EINVAL, "ma exceeds the partition count (or 1024)");
+    QCK(cudaSetDevice(ctx->device));
+    const int M = ctx->m, dim = ctx->dim, bits = ctx->bits;
+    const size_t td = static_cast<size_t>(M) << bits;   // floats per table
+    const bool flat = ctx->K == 0;
+    // query sub-batches: float tables <= 1 GiB, grids below 65 536
+    const int bq = static_cast<int>(std::max<size_t>(1, std::min<size_t>(std::min(nq, kMaxBatch), (size_t(1) << 28) / (td * ma))));
+    const int nsplit = std::max(1, std::min(64, (2 * ctx->sm_count + bq - 1) / bq));
+    ctx->launches = 0;
+    for (int q0 = 0; q0 < nq; q0 += bq) {
+        const int n = std::min(bq, nq - q0);
+        const size_t nqa = static_cast<size_t>(n) * ma;
+        ENSURE(ctx->b_queries, static_cast<size_t>(n) * dim * 4);
+        ENSURE(ctx->b_assign, nqa * 4);
+        ENSURE(ctx->b_tables, nqa * td * 4);
+        ENSURE(ctx->b_tmin, nqa * 4);
+        ENSURE(ctx->b_plists, static_cast<size_t>(n) * nsplit * r * 8);
+        ENSURE(ctx->b_keys, static_cast<size_t>(n) * r * 8);
+        ENSURE(ctx->b_ids, static_cast<size_t>(n) * r * 4);
+        ENSURE(ctx->b_adc_dists, static_cast<size_t>(n) * r * 4);
+        ENSURE(ctx->b_counts, static_cast<size_t>(n) * 4);
+        float* d_q = ctx->b_queries.as<float>();
+        int32_t* d_assign = ctx->b_assign.as<int32_t>();
+        QCK(cudaMemcpyAsync(d_q, queries + static_cast<size_t>(q0) * dim, static_cast<size_t>(n) * dim * 4,
+                            cudaMemcpyHostToDevice, ctx->stream));
+        if (flat) {
+            QCK(cudaMemsetAsync(d_assign, 0, nqa * 4, ctx->stream));
+        } else {
+            const int chunk_q = std::max(1, static_cast<int>(std::min<size_t>(n, (size_t(1) << 28) / ctx->K)));
+            ENSURE(ctx->b_cdist, static_cast<size_t>(chunk_q) * ctx->K * 4);
+            for (int c0 = 0; c0 < n; c0 += chunk_q) {
+                const int cn = std::min(chunk_q, n - c0);
+                dim3 grid((cn + kCoarseTQ - 1) / kCoarseTQ, (ctx->K + kCoarseTC - 1) / kCoarseTC);
+                coarse_dist_kernel<<<grid, 256, 0, ctx->stream>>>(d_q + static_cast<size_t>(c0) * dim, cn, dim, ctx->d_centroids,
+                                                                  ctx->K, ctx->b_cdist.as<float>());
+                QCK(cudaGetLastError());
+                coarse_select_kernel<<<cn, kSelThreads, 0, ctx->stream>>>(ctx->b_cdist.as<float>(), ctx->K, ma,
+                                                                         d_assign + static_cast<size_t>(c0) * ma, nullptr, 0u);
+                QCK(cudaGetLastError());
+                ctx->launches += 2;
+            }
+        }
+        {
+            dim3 tgrid((ma + 7) / 8, n);
+            auto launch_tables = [&](auto kernel) {
+                kernel<<<tgrid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(
+                    d_q, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
+                    ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), bits);
+            };
+            switch (dim / M) {
+                case 2: launch_tables(tables_kernel<2>); break;
+                case 3: launch_tables(tables_kernel<3>); break;
+                case 4: launch_tables(tables_kernel<4>); break;
+                case 6: launch_tables(tables_kernel<6>); break;
+                case 8: launch_tables(tables_kernel<8>); break;
+                case 12: launch_tables(tables_kernel<12>); break;
+                case 16: launch_tables(tables_kernel<16>); break;
+                default: launch_tables(tables_kernel<0>); break;
+            }
+            ctx->launches++;
+            QCK(cudaGetLastError());
+        }
+        AdcScanArgs a;
+        a.rows = ctx->d_rows; a.row_off = ctx->d_row_off; a.assign = d_assign; a.tables = ctx->b_tables.as<float>();
+        a.ma = ma; a.r = r; a.nsplit = nsplit; a.lists = ctx->b_plists.as<uint64_t>();
+        dim3 sgrid(nsplit, n);
+        if (bits == 4 && M == 16) adc_scan_kernel<4, 16><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
+        else if (bits == 4 && M == 32) adc_scan_kernel<4, 32><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
+        else if (bits == 8 && M == 4) adc_scan_kernel<8, 4><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
+        else if (bits == 8 && M == 8) adc_scan_kernel<8, 8><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
+        else adc_scan_kernel<8, 16><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        QCK(cudaGetLastError());
+        MergeArgs mg{};
+        mg.in_keys = ctx->b_plists.as<uint64_t>(); mg.L = nsplit; mg.r = r; mg.nq = n;
+        mg.out_keys = ctx->b_keys.as<uint64_t>(); mg.out_counts = ctx->b_counts.as<int32_t>();
+        int rc = run_merge(ctx, mg);
+        if (rc) return rc;
+        adc_finalize_kernel<<<n, 256, 0, ctx->stream>>>(ctx->b_keys.as<uint64_t>(), r, ma, d_assign, ctx->d_row_off,
+                                                        ctx->d_adc_labels, ctx->b_ids.as<uint32_t>(),
+                                                        ctx->b_adc_dists.as<float>());
+        ctx->launches++;
+        QCK(cudaGetLastError());
+        QCK(cudaMemcpyAsync(out_ids + static_cast<size_t>(q0) * r, ctx->b_ids.p, static_cast<size_t>(n) * r * 4,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+        QCK(cudaMemcpyAsync(out_dists + static_cast<size_t>(q0) * r, ctx->b_adc_dists.p, static_cast<size_t>(n) * r * 4,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_counts)
+            QCK(cudaMemcpyAsync(out_counts + q0, ctx->b_counts.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        QCK(cudaStreamSynchronize(ctx->stream));   // scratch is reused by the next sub-batch
     }
     return QADC_OK;
 }

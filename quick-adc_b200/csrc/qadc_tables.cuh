@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ q
                                                      const float* __restrict__ rotation,    // or null
                                                      const float* __restrict__ centroids,   // or null (flat)
                                                      const int32_t* __restrict__ assign, int ma,
-                                                     float* __restrict__ tables, float* __restrict__ tmin) {
+                                                     float* __restrict__ tables, float* __restrict__ tmin, int ncl) {
+    // ncl = log2(entries per sub-quantiser): 4 for Quick ADC, 8 for the plain 8-bit ADC tables
     extern __shared__ __align__(16) float sm[];   // 8 warps x 2 x dim
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.y, a_i = blockIdx.x * 8 + warp;
@@ -217,10 +218,11 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ q
     }
     const int dsq = DSQ ? DSQ : dim / M, blocks = dsq / 8, rem = dsq % 8;
     float local_min = 3.402823466e+38f;
-    for (int e = lane; e < M * 16; e += 32) {
-        const int j = e >> 4;
+    const int entries = M << ncl;
+    for (int e = lane; e < entries; e += 32) {
+        const int j = e >> ncl;
         const float* a = x + j * dsq;
-        const float* b = codebooks + static_cast<size_t>(e) * dsq;   // (j*16 + c) * dsq
+        const float* b = codebooks + static_cast<size_t>(e) * dsq;   // (j * 2^ncl + c) * dsq
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int bl = 0; bl < blocks; ++bl) {
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ q
             const float diff = __fsub_rn(__ldg(b + blocks * 8 + i), a[blocks * 8 + i]);
             norm = __fmaf_rn(diff, diff, norm);
         }
-        tables[qa * M * 16 + e] = norm;
+        tables[qa * entries + e] = norm;
         local_min = fminf(local_min, norm);
     }
     for (int o = 16; o > 0; o >>= 1) local_min = fminf(local_min, __shfl_xor_sync(0xffffffffu, local_min, o));

@@ -7,8 +7,10 @@
 #define QADC_HOST_QUERY_COMMON_HPP_
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <iostream>
+#include <limits>
 #include <memory>
 #include <vector>
 
@@ -135,6 +137,86 @@ struct nns_engine_gpu {
     }
 };
 
+inline std::uint64_t ustime() {   // common.hpp:15-20
+    return static_cast<std::uint64_t>(std::chrono::duration_cast<std::chrono::microseconds>(
+        std::chrono::steady_clock::now().time_since_epoch()).count());
+}
+
+// ---- plain ADC (db_query.cpp): scanner_simple + engine on the GPU float scan ------------------
+// Scanner concept of db_query.cpp:17-46: the database goes to the device row-major as it is.
+struct scanner_gpu_simple {
+    typedef kv_binheap<unsigned, float> BhType;
+    qadc_ctx* ctx = nullptr;
+    explicit scanner_gpu_simple(int device = 0) {
+        if (qadc_create(device, nullptr, &ctx) != QADC_OK) qadc_die(nullptr, "qadc_create");
+    }
+    ~scanner_gpu_simple() { qadc_destroy(ctx); }
+    scanner_gpu_simple(const scanner_gpu_simple&) = delete;
+
+    void prepare_database(base_db& db) {
+        const base_pq& pq = *db.pq;
+        // get_scan_func (query_common.hpp:122-147) rejects other (nsq, bits) pairs with the same words
+        if (qadc_set_pq(ctx, pq.dim, pq.sq_count, pq.sq_bits, pq.centroids_flat.data(), pq.rotation_ptr())) qadc_die(ctx, "qadc_set_pq");
+        const int parts = db.partition_count();
+        if (db.coarse_centroids() && qadc_set_coarse(ctx, parts, db.coarse_centroids())) qadc_die(ctx, "qadc_set_coarse");
+        const size_t cs = pq.code_size();
+        std::vector<std::uint64_t> offsets(parts + 1, 0);
+        std::vector<std::uint8_t> codes_all;
+        std::vector<std::uint32_t> labels_all;
+        const std::uint8_t* codes;
+        unsigned* labels;
+        unsigned size;
+        for (int p = 0; p < parts; ++p) {
+            db.get_partition(p, codes, labels, size);
+            offsets[p + 1] = offsets[p] + size;
+            codes_all.insert(codes_all.end(), codes, codes + static_cast<size_t>(size) * cs);
+            if (labels) labels_all.insert(labels_all.end(), labels, labels + size);
+            db.free_partition(p);
+        }
+        if (qadc_adc_load(ctx, parts, offsets.data(), codes_all.data(), db.coarse_centroids() ? labels_all.data() : nullptr))
+            qadc_die(ctx, "qadc_adc_load");
+    }
+};
+
+struct nns_engine_gpu_adc {
+    base_db& db_;
+    std::unique_ptr<scanner_gpu_simple> scanner_;
+    int ma_, r_, batch_count_;
+    std::vector<std::uint32_t> ids_;
+    std::vector<float> dists_;
+    std::vector<std::int32_t> counts_;
+    int batch_first_ = -1, batch_size_ = 0;
+
+    nns_engine_gpu_adc(std::unique_ptr<scanner_gpu_simple>&& scanner, base_db& db, int ma, int r, int batch_count)
+        : db_(db), scanner_(std::move(scanner)), ma_(ma), r_(r), batch_count_(batch_count <= 0 ? 1 << 14 : batch_count) {
+        std::cerr << "NNS Engine Batch size: " << batch_count_ << " queries" << std::endl;
+    }
+    void prepare_database() { scanner_->prepare_database(db_); }
+
+    template <typename DistType, typename MetricsType>
+    void process_query(const int query_i, const float* queries, const int count, kv_binheap<unsigned, DistType>& bh,
+                       MetricsType& metrics) {
+        metrics = MetricsType();
+        if (query_i % batch_count_ == 0 || query_i < batch_first_ || query_i >= batch_first_ + batch_size_) {
+            batch_first_ = (query_i / batch_count_) * batch_count_;
+            batch_size_ = std::min(batch_count_, count - batch_first_);
+            ids_.resize(static_cast<size_t>(batch_size_) * r_);
+            dists_.resize(ids_.size());
+            counts_.resize(batch_size_);
+            const std::uint64_t t0 = ustime();
+            if (qadc_adc_search(scanner_->ctx, queries + static_cast<long>(batch_first_) * db_.pq->dim, batch_size_, ma_, r_,
+                                ids_.data(), dists_.data(), counts_.data()))
+                qadc_die(scanner_->ctx, "qadc_adc_search");
+            metrics.scan_us = ustime() - t0;   // whole batch (assignment, tables, scan, copies), booked on its first query
+        }
+        const int b = query_i - batch_first_;
+        // scanner_simple::query_scan (db_query.cpp:27-30) pre-fills the heap, then the scan replaces entries
+        for (int t = 0; t < bh.capacity(); ++t) bh.push(0, std::numeric_limits<DistType>::max() - t);
+        for (int i = 0; i < counts_[b]; ++i)
+            bh.push(ids_[static_cast<size_t>(b) * r_ + i], static_cast<DistType>(dists_[static_cast<size_t>(b) * r_ + i]));
+    }
+};
+
 // recall.hpp:45-54 with t = 1 (query_common.hpp:342): 1 iff the first ground-truth id is returned.
 struct recall_file {
     vectors_owner<int> groundtruth;
@@ -149,9 +231,9 @@ struct recall_file {
 };
 
 // query_common.hpp:330-368
-template <typename EngineType, typename BhType, typename MetricsType>
+template <typename EngineType, typename BhType, typename MetricsType, typename DumpT = std::int8_t>
 void process_queries(query_args& args, base_db& db, EngineType& engine, MetricsType& total_metrics, double& total_recall,
-                     std::vector<unsigned>* dump_keys = nullptr, std::vector<std::int8_t>* dump_vals = nullptr,
+                     std::vector<unsigned>* dump_keys = nullptr, std::vector<DumpT>* dump_vals = nullptr,
                      int max_queries = -1) {
     vectors_owner<float> queries = load_vectors_by_extension(args.query_file);
     if (max_queries > 0) queries.count = max_queries;
@@ -172,7 +254,7 @@ void process_queries(query_args& args, base_db& db, EngineType& engine, MetricsT
         total_metrics += metrics;
         if (dump_keys) {
             std::vector<unsigned> k(args.r, 0);
-            std::vector<std::int8_t> v(args.r, 127);
+            std::vector<DumpT> v(args.r, std::numeric_limits<DumpT>::max());
             bh.sort(k.data(), v.data());
             dump_keys->insert(dump_keys->end(), k.begin(), k.end());
             dump_vals->insert(dump_vals->end(), v.begin(), v.end());

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
-from oracle.pyoracle import Ref  # noqa: E402
+from oracle.pyoracle import Ref, RefAdc  # noqa: E402
 import synth  # noqa: E402
 
 
@@ -123,6 +123,29 @@ def archive_case(ref, name, seed, dim, m, n, K):
     print(name, {k: v.size for k, v in out.items() if k.startswith("ref_")})
 
 
+def adc_case(name, seed, dim, m, bits, n, nq, r, K=0, ma=1, opq=False):
+    """db_query (plain ADC, "next" row N4): scanner_simple over 8-bit or 4-bit codes, flat or IVF."""
+    rng = np.random.default_rng(seed)
+    cs = m * bits // 8
+    out = dict(dim=dim, m=m, bits=bits, r=r, ma=ma, codebooks=rng.standard_normal((m, 1 << bits, dim // m)).astype(np.float32),
+               queries=synth.make_queries(rng, nq, dim))
+    if opq:
+        out["rotation"] = np.ascontiguousarray(np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32))
+    if K:
+        sizes = rng.multinomial(n, np.ones(K) / K)
+        sizes[K // 3] = 0
+        out["offsets"] = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        n = int(out["offsets"][-1])
+        out["centroids"] = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+        out["labels"] = rng.permutation(n).astype(np.uint32)
+    else:
+        out["offsets"] = np.array([0, n], np.int64)
+    out["codes"] = rng.integers(0, 256, (n, cs), dtype=np.uint8)
+    out["ref_ids"], out["ref_dists"] = RefAdc().search(out, out["queries"], ma, r)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "first distances", out["ref_dists"][0, :3])
+
+
 def main():
     """python tests/golden/make_golden.py [name ...]  (no names: every fixture)"""
     ref = Ref()
@@ -144,6 +167,12 @@ def main():
         ivf_case(ref, "ivf_m16", seed=103, dim=128, m=16, n=6000, K=24, ma=5, nq=8, r=20, keep=0.08, empty=(3,))
     if want("ivf_m32"):
         ivf_case(ref, "ivf_m32", seed=104, dim=96, m=32, n=4000, K=12, ma=3, nq=6, r=10, keep=0.1)
+    if want("adc_flat_8x8"):
+        adc_case("adc_flat_8x8", seed=109, dim=64, m=8, bits=8, n=4000, nq=8, r=20)
+    if want("adc_ivf_16x8"):
+        adc_case("adc_ivf_16x8", seed=110, dim=128, m=16, bits=8, n=6000, nq=8, r=20, K=16, ma=5)
+    if want("adc_ivf_opq_32x4"):
+        adc_case("adc_ivf_opq_32x4", seed=111, dim=96, m=32, bits=4, n=5000, nq=6, r=16, K=12, ma=4, opq=True)
     if want("archives"):
         archive_case(ref, "archives", seed=108, dim=32, m=16, n=300, K=6)
     # OPQ: the rotation sits between the residuals and the tables

@@ -11,7 +11,8 @@ import numpy as np
 import pytest
 
 import synth
-from test_oracle import FLAT, IVF, OPQ, FLOAT_RTOL, load, rel_err, blas_scale, tie_class_check, golden_db, rotated
+from test_oracle import (FLAT, IVF, OPQ, ADC, FLOAT_RTOL, load, rel_err, blas_scale, tie_class_check, golden_db, rotated,
+                         adc_db, check_adc_against_reference)
 
 pytestmark = pytest.mark.gpu
 
@@ -337,8 +338,12 @@ def test_argument_errors(qadc):
     ix = qadc.Index(0)
     with pytest.raises(qadc.QadcError):
         ix.set_pq(128, 8, synth.make_pq(rng, 128, 8))          # (8,4) unsupported, db_query_4.cpp:32-34
-    with pytest.raises(qadc.QadcError):
-        ix.set_pq(128, 16, synth.make_pq(rng, 128, 16), bits=8)   # sq_bits must be 4, :396-400
+    # an 8-bit quantiser is accepted for the plain ADC path only: the Quick ADC database refuses it
+    # ("Quantizer must have sq_bits=4", load_database_check, db_query_4.cpp:393-402)
+    ix.set_pq(128, 16, rng.standard_normal((16, 256, 8)).astype(np.float32), bits=8)
+    with pytest.raises(qadc.QadcError) as e:
+        ix.load_flat(rng.integers(0, 256, (1000, 16), dtype=np.uint8), 0.5)
+    assert "sq_bits=4" in str(e.value)
     ix.set_pq(128, 16, synth.make_pq(rng, 128, 16))
     with pytest.raises(qadc.QadcError):
         ix.search(synth.make_queries(rng, 1, 128), 1, 10)      # no database yet
@@ -687,3 +692,81 @@ def test_recall_at_100_matches_reference(qadc, oracle, ref):
     rec_ref = np.mean([gt[i] in res["keys"][i][:res["sizes"][i]] for i in range(nq)])
     assert rec_gpu >= 0.5 and abs(rec_gpu - rec_ref) <= 0.02, (rec_gpu, rec_ref)
     ix.close()
+
+
+# ---- "next" row N4: the plain ADC scan of db_query on the GPU ----------------------------------
+def adc_index(qadc, db):
+    ix = qadc.Index(0)
+    ix.set_pq(db["dim"], db["m"], db["codebooks"], rotation=db.get("rotation"), bits=db["bits"])
+    if db.get("centroids") is not None:
+        ix.set_coarse(db["centroids"])
+        ix.adc_load(db["codes"], db["labels"], db["offsets"])
+    else:
+        ix.adc_load(db["codes"])
+    return ix
+
+
+@pytest.mark.parametrize("name", ADC)
+def test_adc_search_golden(qadc, oracle, name):
+    """GPU float ADC == oracle bit for bit (ids, float distances, counts) and within the stated
+    1e-5 of the reference's db_query path on the golden inputs."""
+    g = load(name)
+    db = adc_db(g)
+    ix = adc_index(qadc, db)
+    ids, d, cnt = ix.adc_search(g["queries"], int(g["ma"]), int(g["r"]))
+    exp = oracle.adc_search(db, g["queries"], int(g["ma"]), int(g["r"]))
+    assert np.array_equal(cnt, exp["count"]) and np.array_equal(ids, exp["ids"])
+    assert np.array_equal(d.view(np.uint32), exp["d"].view(np.uint32))
+    check_adc_against_reference(ids, d, g)
+    ix.close()
+
+
+@pytest.mark.parametrize("m,bits,ivf", [(8, 8, False), (16, 8, False), (4, 8, True), (16, 4, False), (32, 4, True)])
+def test_adc_search_larger(qadc, oracle, m, bits, ivf):
+    """Splits, compaction rounds, duplicate codes (distance ties broken by scan order), r = 100."""
+    rng = np.random.default_rng(200 + m + bits)
+    dim, n, nq, r = 8 * m, 150000, 9, 100
+    db = dict(dim=dim, m=m, bits=bits, codebooks=rng.standard_normal((m, 1 << bits, dim // m)).astype(np.float32))
+    ma = 1
+    if ivf:
+        K, ma = 20, 6
+        sizes = rng.multinomial(n, np.ones(K) / K)
+        sizes[4] = 0
+        db.update(offsets=np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64),
+                  centroids=(2 * rng.standard_normal((K, dim))).astype(np.float32),
+                  labels=rng.permutation(n).astype(np.uint32))
+    else:
+        db["offsets"] = np.array([0, n], np.int64)
+    codes = rng.integers(0, 256, (n, m * bits // 8), dtype=np.uint8)
+    codes[n // 2:n // 2 + 3000] = codes[:3000]          # exact duplicates -> equal distances
+    db["codes"] = codes
+    q = synth.make_queries(rng, nq, dim)
+    ix = adc_index(qadc, db)
+    ids, d, cnt = ix.adc_search(q, ma, r)
+    exp = oracle.adc_search(db, q, ma, r)
+    assert np.array_equal(cnt, exp["count"]) and np.array_equal(ids, exp["ids"])
+    assert np.array_equal(d.view(np.uint32), exp["d"].view(np.uint32))
+    ix.close()
+
+
+def test_adc_short_database_and_errors(qadc, oracle):
+    rng = np.random.default_rng(3)
+    db = dict(dim=32, m=4, bits=8, codebooks=rng.standard_normal((4, 256, 8)).astype(np.float32),
+              codes=rng.integers(0, 256, (5, 4), dtype=np.uint8), offsets=np.array([0, 5], np.int64))
+    q = synth.make_queries(rng, 2, 32)
+    ix = qadc.Index(0)
+    ix.set_pq(32, 4, db["codebooks"], bits=8)
+    with pytest.raises(qadc.QadcError) as e:
+        ix.adc_search(q, 1, 8)                           # nothing loaded yet
+    assert e.value.code == qadc.QADC_ESTATE
+    with pytest.raises(qadc.QadcError):
+        ix.begin_database(np.array([5], np.uint32), False)   # Quick ADC needs 4-bit codes (db_query_4.cpp:393-402)
+    ix.adc_load(db["codes"])
+    ids, d, cnt = ix.adc_search(q, 1, 8)
+    exp = oracle.adc_search(db, q, 1, 8)
+    assert np.array_equal(cnt, exp["count"]) and np.array_equal(ids, exp["ids"]) and np.array_equal(d, exp["d"])
+    with pytest.raises(qadc.QadcError):
+        ix.adc_search(q, 2, 8)                           # flat database: ma must be 1
+    ix.close()
+    with pytest.raises(qadc.QadcError):
+        qadc.Index(0).set_pq(32, 2, rng.standard_normal((2, 65536, 16)).astype(np.float32), bits=16)   # 16-bit: unsupported

@@ -258,3 +258,54 @@ def test_db_build_then_query(cli, oracle, tmp_path, ivf):
     for qi in range(nq):
         for v in np.unique(d[qi]):
             assert set(ids[qi][d[qi] == v].tolist()) == set(exp["ids"][qi][exp["d"][qi] == v].tolist())
+
+
+# ---- db_query: the plain ADC tool ("next" row N4) -------------------------------------------------
+def test_db_query_builds_and_prints_usage(cli):
+    p = subprocess.run([os.path.join(HOST, "db_query")], capture_output=True, text=True)
+    assert p.returncode == 1 and "Usage: db_query: [-r R] [-m MA] [-b BATCH_SIZE]" in p.stderr   # db_query.cpp:48-52
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,bits,ivf", [(8, 8, False), (16, 8, True), (16, 4, True)])
+def test_db_query_matches_oracle(cli, oracle, tmp_path, m, bits, ivf):
+    """db_query on a database file in the reference's archive layout: same distances as the oracle's
+    plain ADC (bitwise), same ids per distance, recall column, CSV header of db_query.cpp:116-119."""
+    from qadc_b200 import dbfile
+    rng = np.random.default_rng(60 + m + bits)
+    dim, n, nq, r, K, ma = 8 * m, 20000, 9, 30, 12, 4
+    cb = rng.standard_normal((m, 1 << bits, dim // m)).astype(np.float32)
+    codes = rng.integers(0, 256, (n, m * bits // 8), dtype=np.uint8)
+    q = synth.make_queries(rng, nq, dim)
+    db = dict(dim=dim, m=m, bits=bits, codebooks=cb, codes=codes, offsets=np.array([0, n], np.int64))
+    kw = dict(dim=dim, m=m, codebooks=cb, codes=codes, bits=bits)
+    if ivf:
+        sizes = rng.multinomial(n, np.ones(K) / K)
+        sizes[5] = 0
+        db.update(offsets=np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64),
+                  centroids=(2 * rng.standard_normal((K, dim))).astype(np.float32), labels=rng.permutation(n).astype(np.uint32))
+        kw.update(centroids=db["centroids"], labels=db["labels"], offsets=db["offsets"])
+    else:
+        ma = 1
+    exp = oracle.adc_search(db, q, ma, r)
+    gt = exp["ids"][:, :1].astype(np.int32).copy()
+    gt[1::2] = n + 7                                          # every other query cannot be recalled
+    dbfile.write_archive_db(tmp_path / "db.bin", **kw)
+    dbfile.write_vecs(tmp_path / "q.fvecs", q)
+    dbfile.write_vecs(tmp_path / "gt.ivecs", gt)
+    out = tmp_path / "res.bin"
+    p = subprocess.run([os.path.join(HOST, "db_query"), "-r", str(r), "-m", str(ma), "-b", "4", "-o", str(out),
+                        str(tmp_path / "db.bin"), str(tmp_path / "q.fvecs"), str(tmp_path / "gt.ivecs")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    lines = p.stdout.strip().splitlines()
+    assert lines[0] == "r,recall,ma,adc_type,index_us,rotate_us,table_us,scan_us"
+    f = lines[1].split(",")
+    assert f[0] == str(r) and f[2] == str(ma) and f[3] == "adc" and abs(float(f[1]) - 5 / 9) < 1e-6
+    raw = np.fromfile(out, np.uint8).reshape(nq, r * 8)
+    ids = raw[:, :4 * r].copy().view(np.uint32)
+    d = raw[:, 4 * r:].copy().view(np.float32)
+    assert np.array_equal(d.view(np.uint32), exp["d"].view(np.uint32))
+    for qi in range(nq):
+        for v in np.unique(d[qi]):
+            assert set(ids[qi][d[qi] == v].tolist()) == set(exp["ids"][qi][exp["d"][qi] == v].tolist())

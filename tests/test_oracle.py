@@ -221,6 +221,48 @@ def test_full_pipeline_self_consistent(oracle, name):
         assert np.array_equal(ids, res["ids"][q]) and np.array_equal(d, res["d"][q]) and cnt == res["count"][q]
 
 
+ADC = ["adc_flat_8x8", "adc_ivf_16x8", "adc_ivf_opq_32x4"]   # db_query (plain ADC): 8-bit flat / IVF, 4-bit IVF + OPQ
+
+
+def adc_db(g):
+    db = dict(dim=int(g["dim"]), m=int(g["m"]), bits=int(g["bits"]), codebooks=g["codebooks"], codes=g["codes"],
+              offsets=g["offsets"])
+    if "centroids" in g:
+        db.update(centroids=g["centroids"], labels=g["labels"])
+    if "rotation" in g:
+        db["rotation"] = g["rotation"]
+    return db
+
+
+def check_adc_against_reference(ids, d, g):
+    """Float ADC results vs the reference's sorted heap (scanner_simple): distances within 1e-5
+    relative (the -ffast-math build may reassociate the per-vector sum), same ids wherever the
+    r-th and (r+1)-th candidates are not closer than that."""
+    assert np.max(np.abs(d - g["ref_dists"]) / np.maximum(np.abs(g["ref_dists"]), 1e-30)) <= FLOAT_RTOL
+    for q in range(d.shape[0]):
+        assert set(ids[q].tolist()) == set(g["ref_ids"][q].tolist())
+
+
+@pytest.mark.parametrize("name", ADC)
+def test_adc_oracle_vs_reference_golden(oracle, name):
+    g = load(name)
+    res = oracle.adc_search(adc_db(g), g["queries"], int(g["ma"]), int(g["r"]))
+    assert np.all(res["count"] == int(g["r"]))
+    assert np.all(np.diff(res["d"], axis=1) >= 0)
+    check_adc_against_reference(res["ids"], res["d"], g)
+
+
+def test_adc_oracle_short_database_pads_like_the_reference(oracle):
+    """Fewer vectors than r: the tail is (0, FLT_MAX), the reference's pre-filled heap slots."""
+    rng = np.random.default_rng(3)
+    db = dict(dim=32, m=4, bits=8, codebooks=rng.standard_normal((4, 256, 8)).astype(np.float32),
+              codes=rng.integers(0, 256, (5, 4), dtype=np.uint8), offsets=np.array([0, 5], np.int64))
+    res = oracle.adc_search(db, synth.make_queries(rng, 2, 32), 1, 8)
+    assert np.all(res["count"] == 5) and np.all(res["ids"][:, 5:] == 0)
+    assert np.all(res["d"][:, 5:] == np.finfo(np.float32).max)
+    assert all(sorted(res["ids"][q, :5].tolist()) == [0, 1, 2, 3, 4] for q in range(2))
+
+
 def test_prefix_too_small_is_reported(oracle):
     """Fewer than r prefix vectors -> qmax = FLT_MAX -> the reference exits (db_query_4.cpp:271-274)."""
     rng = np.random.default_rng(5)
