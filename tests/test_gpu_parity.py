@@ -694,6 +694,28 @@ def test_recall_at_100_matches_reference(qadc, oracle, ref):
     ix.close()
 
 
+def test_ivf_schedule_does_not_change_results(qadc, oracle):
+    """The inverted-list scan hands superblock items to warps dynamically; any schedule must give
+    the canonical result.  Long lists with many exact duplicates (distance ties at every rank),
+    item sizes from one superblock to whole lists, repeated runs: always bit-equal to the oracle."""
+    rng = np.random.default_rng(91)
+    dim, m, n, K, ma, nq, r, keep = 64, 16, 300000, 16, 6, 25, 100, 0.01
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(3,))
+    codes[n // 2:n // 2 + 40000] = codes[:40000]        # duplicates: ties between lists and inside lists
+    q = synth.make_queries(rng, nq, dim)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=keep,
+                             offsets=offsets), q, ma, r, want_tables=False)
+    ix = ivf_index(qadc, dim, m, cb, cents, codes, labels, offsets, keep)
+    for spi in (8, 1, 3, 64, 4096, 8):
+        ix.set_option("ivf_sb_per_item", spi)
+        for _ in range(2):
+            ids, d, cnt = ix.search(q, ma, r)
+            assert np.array_equal(cnt, exp["count"]) and np.array_equal(d, exp["d"]) and np.array_equal(ids, exp["ids"]), spi
+    ix.close()
+
+
 # ---- "next" row N4: the plain ADC scan of db_query on the GPU ----------------------------------
 def adc_index(qadc, db):
     ix = qadc.Index(0)
