@@ -114,11 +114,7 @@ int ensure(qadc_ctx* ctx, DevBuf& b, size_t bytes) {
     } while (0)
 
 PipeK make_pipek() {
-#ifdef QADC_CORE_PACKED
-    return PipeK{1u, 0xffffffffu};
-#else
     return PipeK{1u, 0xffffffffu, 1u, 1u << 8, 1u << 16, 1u << 24};
-#endif
 }
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }

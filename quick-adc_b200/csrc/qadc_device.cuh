@@ -108,97 +108,21 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
     return d;
 }
 
-#ifdef QADC_CORE_PACKED   // earlier variant, kept for A/B runs (-DQADC_CORE_PACKED)
-// Accumulators of one group of 8 vectors.  Vector k of the group lives in a 16-bit lane:
-//   k=0: ea[15:0]   k=2: ea[31:16]   k=1: oa[23:8]   k=3: oa[39:24]
-//   k=4: eb[15:0]   k=6: eb[31:16]   k=5: ob[23:8]   k=7: ob[39:24]
-// Every lane starts at 0x8000 - bound, so its top bit is set iff sum >= bound.
-// The odd bytes of a pair sum stay where they are (o = p - e, bytes 1 and 3) and are
-// accumulated in 64 bits, which needs no shift at all.
-struct GroupAcc {
-    uint32_t ea, eb;
-    uint64_t oa, ob;
-};
-
-// `one` / `neg1` are the constants 1 and -1 passed as kernel arguments: the compiler cannot
-// fold them, so a*one+b is emitted as IMAD / IMAD.WIDE on the FMA pipe instead of competing
-// with PRMT/LOP3/SHF for the ALU pipe, which is what bounds this kernel.
-struct PipeK {
-    uint32_t one, neg1;
-};
-
-__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const PipeK& k) { return a * k.one + b; }
-
-__device__ __forceinline__ void acc_init(GroupAcc& g, uint32_t bound) {
-    const uint32_t lane = 0x8000u - bound;
-    g.ea = g.eb = lane * 0x00010001u;
-    g.oa = g.ob = (static_cast<uint64_t>(lane) << 8) | (static_cast<uint64_t>(lane) << 24);
-}
-
-// Two sub-quantisers (words w0,w1 with tables t0,t1) for the 8 vectors of a group.
-__device__ __forceinline__ void lut_pair(uint32_t w0, uint32_t w1, const uint4& t0, const uint4& t1, GroupAcc& g,
-                                         const PipeK& k) {
-    const uint32_t x0 = w0 ^ 0x88888888u, x1 = w1 ^ 0x88888888u;
-    const uint32_t pa = fadd(fadd(prmt(t0.x, t0.y, w0), prmt(t0.z, t0.w, x0), k),
-                             fadd(prmt(t1.x, t1.y, w1), prmt(t1.z, t1.w, x1), k), k);
-    const uint32_t pb = fadd(fadd(prmt(t0.x, t0.y, w0 >> 16), prmt(t0.z, t0.w, x0 >> 16), k),
-                             fadd(prmt(t1.x, t1.y, w1 >> 16), prmt(t1.z, t1.w, x1 >> 16), k), k);
-    const uint32_t ea = pa & 0x00ff00ffu, eb = pb & 0x00ff00ffu;
-    g.ea = fadd(ea, g.ea, k);
-    g.eb = fadd(eb, g.eb, k);
-    g.oa = static_cast<uint64_t>(ea * k.neg1 + pa) * k.one + g.oa;   // IMAD, then IMAD.WIDE
-    g.ob = static_cast<uint64_t>(eb * k.neg1 + pb) * k.one + g.ob;
-}
-
-// One quad = 4 sub-quantisers.
-__device__ __forceinline__ void lut_quad(const uint4& w, const uint4 (&t)[4], GroupAcc& g, const PipeK& k) {
-    lut_pair(w.x, w.y, t[0], t[1], g, k);
-    lut_pair(w.z, w.w, t[2], t[3], g, k);
-}
-
-// true iff at least one of the 8 sums is < bound
-__device__ __forceinline__ bool any_below(const GroupAcc& g) {
-    const uint32_t e = g.ea & g.eb & 0x80008000u;                                                   // bits 15, 31
-    const uint32_t o1 = static_cast<uint32_t>(g.oa) & static_cast<uint32_t>(g.ob) & 0x00800000u;     // bit 23
-    const uint32_t o3 = static_cast<uint32_t>(g.oa >> 32) & static_cast<uint32_t>(g.ob >> 32) & 0x80u;   // bit 39
-    return (e | o1 | o3) != 0x80808080u;
-}
-// raw 16-bit lane of vector k (0..7)
-__device__ __forceinline__ uint32_t lane_raw(const GroupAcc& g, int k) {
-    const uint32_t e = (k & 4) ? g.eb : g.ea;
-    const uint64_t o = (k & 4) ? g.ob : g.oa;
-    switch (k & 3) {
-        case 0: return e & 0xffffu;
-        case 2: return e >> 16;
-        case 1: return static_cast<uint32_t>(o >> 8) & 0xffffu;
-        default: return static_cast<uint32_t>(o >> 24) & 0xffffu;
-    }
-}
-// sum of vector k given the bound the accumulators were started with (sum <= 127*32)
-__device__ __forceinline__ uint32_t lane_sum(const GroupAcc& g, int k, uint32_t bound) {
-    return lane_raw(g, k) + bound - 0x8000u;
-}
-
-#else
-// Variant: one 32-bit accumulator per vector, fed with IDP.4A (dot product with a one-hot byte
-// selector) so that neither the even/odd split nor the final test needs ALU-pipe masks.
+// Accumulators of one group of 8 vectors: one 32-bit accumulator per vector, fed with IDP.4A (dot
+// product with a one-hot byte selector), so neither the byte extraction nor the final test needs
+// ALU-pipe masks.  `one`, `neg1` and the selectors are kernel arguments: the compiler cannot fold
+// them, so a*one+b is emitted as IMAD on the FMA pipe instead of competing with PRMT/LOP3/SHF for
+// the ALU pipe, which is what bounds the scan.  (An earlier variant with packed 16-bit lanes and
+// mask/shift extraction was 10 % slower.)
 struct GroupAcc {
     uint32_t v[8];   // sum - bound (negative <=> candidate)
 };
 struct PipeK {
     uint32_t one, neg1, s0, s1, s2, s3;   // 1, -1, and the byte selectors 1, 1<<8, 1<<16, 1<<24
 };
-// selector of vectors 4..7 = upper half of the word.  With QADC_SHIFT_FMA the shift is a
-// multiply-high by 2^16 (s2) on the FMA pipe instead of SHF on the ALU pipe.
-__device__ __forceinline__ uint32_t hi16(uint32_t w, const PipeK& k) {
-#if defined(QADC_SHIFT_FMA)
-    return __umulhi(w, k.s2);
-#elif defined(QADC_SHIFT_WIDE)
-    return static_cast<uint32_t>((static_cast<uint64_t>(w) * k.s2) >> 32);   // IMAD.WIDE.U32, upper word
-#else
-    return w >> 16;
-#endif
-}
+// selector of vectors 4..7 = upper half of the word (SHF on the ALU pipe; multiply-high and
+// IMAD.WIDE forms on the FMA pipe were measured 10 % / 9 % slower)
+__device__ __forceinline__ uint32_t hi16(uint32_t w, const PipeK&) { return w >> 16; }
 __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, const PipeK& k) { return a * k.one + b; }
 __device__ __forceinline__ void acc_init(GroupAcc& g, uint32_t bound) {
 #pragma unroll
@@ -234,7 +158,6 @@ __device__ __forceinline__ bool any_below(const GroupAcc& g) {
 // 16-bit "raw lane" compatible with the packed variant: bit 15 set <=> sum >= bound
 __device__ __forceinline__ uint32_t lane_raw(const GroupAcc& g, int k) { return (g.v[k] + 0x8000u) & 0xffffu; }
 __device__ __forceinline__ uint32_t lane_sum(const GroupAcc& g, int k, uint32_t bound) { return g.v[k] + bound; }
-#endif
 
 // ---- bounded candidate lists: bitonic sort of u64 keys in shared memory ------------------
 // Sorts n (power of two) keys ascending with the threads [0, nthreads) of a group that

@@ -105,36 +105,11 @@ __device__ __forceinline__ int hist_bound(const int* hist, int r, int lane) {
     return __shfl_sync(0xffffffffu, b, src);
 }
 
-// One quad of the scan; the first quad of a vector starts the accumulators at -bound.
-__device__ __forceinline__ void scan_quad(bool first, const uint4& w, const uint4 (&t)[4], GroupAcc& g, const PipeK& k,
-                                          uint32_t bound) {
-#ifdef QADC_CORE_PACKED
-    if (first) acc_init(g, bound);
-    lut_quad(w, t, g, k);
-#else
-    if (first) lut_quad_t<true>(w, t, g, k, 0u - bound);
-    else lut_quad_t<false>(w, t, g, k, 0u);
-#endif
-}
-
-// Early abandon (skip the last sub-quantisers once every vector of a superblock has reached the
-// bound) is exact but measured SLOWER on B200 for the 1e9 x 16x4 bench (643 vs 680 G vectors/s):
-// the extra vote/branch splits the unrolled lookup chain.  Off unless -DQADC_EARLY_ABANDON.
-#ifdef QADC_EARLY_ABANDON
-constexpr bool kEarlyAbandon = true;
-#else
-constexpr bool kEarlyAbandon = false;
-#endif
 // One pair of sub-quantisers; the first pair of a vector starts the accumulators at -bound.
 __device__ __forceinline__ void scan_pair(bool first, uint32_t w0, uint32_t w1, const uint4& t0, const uint4& t1,
                                           GroupAcc& g, const PipeK& k, uint32_t bound) {
-#ifdef QADC_CORE_PACKED
-    if (first) acc_init(g, bound);
-    lut_pair(w0, w1, t0, t1, g, k);
-#else
     if (first) lut_pair<true>(w0, w1, t0, t1, g, k, 0u - bound);
     else lut_pair<false>(w0, w1, t0, t1, g, k, 0u);
-#endif
 }
 
 // Writes a warp's final sorted list (r keys, kEmptyKey padded) to global memory.
@@ -304,37 +279,26 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 #pragma unroll
                 for (int qi = 0; qi < QB; ++qi) gb_next[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
             }
-#ifndef QADC_LATE_RELEASE
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty_a + stage * 8);   // the words are in registers: release the stage early
-#endif
 #pragma unroll
             for (int qi = 0; qi < QB; ++qi) {
                 if (qi < nqb) {
-#ifdef QADC_NO_SHARED_BOUND
-                    const uint32_t bound = static_cast<uint32_t>(lbound[qi]);
-#else
                     const uint32_t bound = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
-#endif
                     GroupAcc g;
-                    // Early abandon: table entries are >= 0, so partial sums only grow.  Once every vector
-                    // of the superblock has reached the bound after kCheck sub-quantisers, the rest of the
-                    // lookups cannot produce a candidate and are skipped (exact; data dependent).
-                    bool alive = true;
+                    // (Early abandon — skipping the last sub-quantisers once every vector of the superblock
+                    // has reached the bound — is exact but was measured 5 % slower: the vote/branch splits
+                    // the unrolled lookup chain.)
 #pragma unroll
                     for (int p = 0; p < M / 2; ++p) {   // pairs of sub-quantisers
-                        if (alive) {
-                            uint4 t0, t1;
-                            if constexpr (Cfg::kRegTab) { t0 = treg[2 * p]; t1 = treg[2 * p + 1]; }
-                            else { t0 = qtab[qi * M + 2 * p]; t1 = qtab[qi * M + 2 * p + 1]; }
-                            const uint4& wq = w[p >> 1];
-                            scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, t0, t1, g, pk, bound);
-                            if (kEarlyAbandon && ((M == 16 && p == 5) || (M == 32 && (p == 9 || p == 12))))
-                                alive = __any_sync(0xffffffffu, any_below(g));
-                        }
+                        uint4 t0, t1;
+                        if constexpr (Cfg::kRegTab) { t0 = treg[2 * p]; t1 = treg[2 * p + 1]; }
+                        else { t0 = qtab[qi * M + 2 * p]; t1 = qtab[qi * M + 2 * p + 1]; }
+                        const uint4& wq = w[p >> 1];
+                        scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, t0, t1, g, pk, bound);
                     }
-                    const bool mine = alive && any_below(g);
-                    if (alive && __any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
+                    const bool mine = any_below(g);
+                    if (__any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
                         // small lists (cap < r + 256) take the superblock in two position-ordered halves
                         for (int half = 0; half < halves; ++half) {
                             const int before = *wl[qi].count;
@@ -369,10 +333,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 #pragma unroll
                 for (int qi = 0; qi < QB; ++qi) gb[qi] = gb_next[qi];
             }
-#ifdef QADC_LATE_RELEASE
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(empty_a + stage * 8);
-#endif
         } else {
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty_a + stage * 8);
