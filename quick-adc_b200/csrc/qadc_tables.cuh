@@ -165,19 +165,37 @@ __global__ void __launch_bounds__(kSelThreads) coarse_select_kernel(const float*
 }
 
 // Sharded coarse assignment, second half: the ma smallest of the G*ma keys of one query
-// (keys laid out [G][nq][ma]); one CTA per query, bitonic sort in shared memory.
+// (keys laid out [G][nq][ma], every list ascending); one CTA per query.  The largest of the lists'
+// ceil(ma/G)-th keys has at least ma keys at or below it, so only keys up to it are kept (about
+// ma of them instead of G*ma) and sorted in shared memory.
 __global__ void __launch_bounds__(256) coarse_merge_kernel(const uint64_t* __restrict__ keys, int G, int nq, int ma,
                                                            int n_sort, int32_t* __restrict__ out_assign) {
-    extern __shared__ __align__(16) uint64_t mk[];
+    extern __shared__ __align__(16) uint64_t mk[];   // n_sort = pow2 >= G * ma
+    __shared__ int count;
+    __shared__ unsigned long long bound;
     const int q = blockIdx.x, tid = threadIdx.x;
-    for (int i = tid; i < n_sort; i += 256) {
+    const int per = (ma + G - 1) / G;
+    if (tid == 0) { count = 0; bound = 0ull; }
+    __syncthreads();
+    if (tid < G) atomicMax(&bound, static_cast<unsigned long long>(keys[(static_cast<size_t>(tid) * nq + q) * ma + per - 1]));
+    for (int g = tid + 256; g < G; g += 256)
+        atomicMax(&bound, static_cast<unsigned long long>(keys[(static_cast<size_t>(g) * nq + q) * ma + per - 1]));
+    __syncthreads();
+    const uint64_t b = bound;
+    for (int i = tid; i < G * ma; i += 256) {
         const int g = i / ma, a = i - g * ma;
-        mk[i] = (g < G) ? keys[(static_cast<size_t>(g) * nq + q) * ma + a] : ~0ull;
+        const uint64_t k = keys[(static_cast<size_t>(g) * nq + q) * ma + a];
+        if (k <= b && k != ~0ull) mk[atomicAdd(&count, 1)] = k;
     }
     __syncthreads();
-    bitonic_sort_u64(mk, n_sort, tid, 256, BlockSync());
+    const int c = count;
+    int n2 = 2;
+    while (n2 < c) n2 <<= 1;   // <= n_sort
+    for (int i = c + tid; i < n2; i += 256) mk[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(mk, n2, tid, 256, BlockSync());
     for (int a = tid; a < ma; a += 256) {
-        const uint64_t k = mk[a];
+        const uint64_t k = a < c ? mk[a] : ~0ull;
         out_assign[static_cast<size_t>(q) * ma + a] = (k == ~0ull) ? 0 : static_cast<int32_t>(static_cast<uint32_t>(k));
     }
 }
