@@ -309,3 +309,40 @@ def test_db_query_matches_oracle(cli, oracle, tmp_path, m, bits, ivf):
     for qi in range(nq):
         for v in np.unique(d[qi]):
             assert set(ids[qi][d[qi] == v].tolist()) == set(exp["ids"][qi][exp["d"][qi] == v].tolist())
+
+
+def test_file_formats_random_shapes(cli, qadc, tmp_path):
+    """Python writer/reader against the C++ loader/saver over random small databases: flat and
+    inverted lists, PQ and OPQ, 4- and 8-bit codes, empty partitions, both formats, both directions."""
+    from qadc_b200 import dbfile
+    rng = np.random.default_rng(2024)
+    conv = os.path.join(HOST, "db_convert")
+    for case in range(24):
+        bits = int(rng.choice([4, 8]))
+        m = int(rng.choice([16, 32] if bits == 4 else [4, 8, 16]))
+        dim = m * int(rng.integers(1, 5))
+        n = int(rng.integers(0, 400))
+        ivf, opq = bool(case & 1), bool(case & 2)
+        kw = dict(dim=dim, m=m, bits=bits, codebooks=rng.standard_normal((m, 1 << bits, dim // m)).astype(np.float32),
+                  codes=rng.integers(0, 256, (n, m * bits // 8), dtype=np.uint8),
+                  rotation=rng.standard_normal((dim, dim)).astype(np.float32) if opq else None)
+        if ivf:
+            K = int(rng.integers(1, 9))
+            sizes = rng.multinomial(n, np.ones(K) / K)
+            kw.update(centroids=rng.standard_normal((K, dim)).astype(np.float32), labels=rng.permutation(n).astype(np.uint32),
+                      offsets=np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64))
+        first, second = ("a.db", "b.qdb") if case & 4 else ("a.qdb", "b.db")
+        (dbfile.write_qdb if first.endswith(".qdb") else dbfile.write_archive_db)(tmp_path / first, **kw)
+        p = subprocess.run([conv, str(tmp_path / first), str(tmp_path / second)], capture_output=True, text=True)
+        assert p.returncode == 0, (case, p.stderr)
+        assert "Vectors: %d" % n in p.stderr
+        (dbfile.write_qdb if second.endswith(".qdb") else dbfile.write_archive_db)(tmp_path / "expect", **kw)
+        assert (tmp_path / second).read_bytes() == (tmp_path / "expect").read_bytes(), case
+        back = dbfile.read_db(tmp_path / second)
+        for k, v in kw.items():
+            if v is None:
+                assert k not in back
+            elif k in ("dim", "m", "bits"):
+                assert back[k] == v
+            else:
+                assert np.array_equal(back[k], v), (case, k)
