@@ -143,10 +143,13 @@ class Oracle:
                                   assign.reshape(-1), _opt(dists))
         return assign, dists
 
-    def encode(self, vectors, m, codebooks):
+    def encode(self, vectors, m, codebooks, bits=4):
         v = np.ascontiguousarray(vectors, np.float32)
-        codes = np.zeros((v.shape[0], m // 2), np.uint8)
-        self.lib.qo_encode(v, v.shape[0], v.shape[1], m, np.ascontiguousarray(codebooks.reshape(-1)), codes.reshape(-1))
+        codes = np.zeros((v.shape[0], m * bits // 8), np.uint8)
+        f = self.lib.qo_encode_n
+        f.restype = None
+        f(_opt(v), C.c_long(v.shape[0]), C.c_int(v.shape[1]), C.c_int(m), C.c_int(bits),
+          _opt(np.ascontiguousarray(codebooks, np.float32).reshape(-1)), _opt(codes))
         return codes
 
     def start_size(self, size, keep):
@@ -324,11 +327,13 @@ class Ref:
                                       np.ascontiguousarray(neighbors), out.reshape(-1))
         return out
 
-    def encode(self, vectors, m, codebooks):
+    def encode(self, vectors, m, codebooks, bits=4):
         v = np.array(vectors, np.float32, order="C", copy=True)
-        codes = np.zeros((v.shape[0], m // 2), np.uint8)
-        self.lib.ref_encode(v.shape[1], m, np.ascontiguousarray(codebooks.reshape(-1)), v, v.shape[0],
-                            codes.reshape(-1))
+        codes = np.zeros((v.shape[0], m * bits // 8), np.uint8)
+        f = self.lib.ref_encode_bits
+        f.restype = None
+        f(C.c_int(v.shape[1]), C.c_int(m), C.c_int(bits), _opt(np.ascontiguousarray(codebooks, np.float32).reshape(-1)),
+          _opt(v), C.c_int(v.shape[0]), _opt(codes))
         return codes
 
     class Handle:

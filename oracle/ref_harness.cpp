@@ -367,4 +367,11 @@ __attribute__((visibility("default"))) void ref_encode(
     pq.encode_multiple_vectors(vectors, codes, count);
 }
 
+// Same for any sq_bits the reference packs (4 or 8 here): base_pq(m, bits, ...).
+__attribute__((visibility("default"))) void ref_encode_bits(
+        int dim, int m, int bits, const float* codebooks, float* vectors, int count, std::uint8_t* codes) {
+    base_pq pq(m, bits, dim, const_cast<float*>(codebooks));
+    pq.encode_multiple_vectors(vectors, codes, count);
+}
+
 }  // extern "C"

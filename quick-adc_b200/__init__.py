@@ -140,7 +140,7 @@ class Index:
         cb = np.ascontiguousarray(codebooks, np.float32).reshape(-1)
         rot = None if rotation is None else np.ascontiguousarray(rotation, np.float32).reshape(-1)
         self._ck(self.lib.qadc_set_pq(self.h, dim, m, bits, _ptr(cb), _ptr(rot)))
-        self.dim, self.m = dim, m
+        self.dim, self.m, self.bits = dim, m, bits
 
     def set_coarse(self, centroids):
         c = np.ascontiguousarray(centroids, np.float32)
@@ -195,7 +195,7 @@ class Index:
     def encode(self, vectors):
         """PQ-encode float vectors (and, for an IVF context, assign them to coarse cells)."""
         v = np.ascontiguousarray(vectors, np.float32)
-        codes = np.empty((v.shape[0], self.m // 2), np.uint8)
+        codes = np.empty((v.shape[0], self.m * getattr(self, "bits", 4) // 8), np.uint8)
         assign = np.empty(v.shape[0], np.int32) if self.K else None
         self._ck(self.lib.qadc_encode(self.h, _ptr(v), v.shape[0], _ptr(assign), _ptr(codes)))
         return (codes, assign) if self.K else codes

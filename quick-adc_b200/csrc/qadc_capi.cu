@@ -934,10 +934,9 @@ int qadc_download_codes(qadc_ctx* ctx, int part_i, uint8_t* out_codes) {
 int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* out_assign, uint8_t* out_codes) {
     if (!ctx || !vectors || !out_codes) return fail(ctx, QADC_EINVAL, "null buffer");
     if (ctx->m == 0) return fail(ctx, QADC_ESTATE, "qadc_set_pq must be called first");
-    if (ctx->bits != 4) return fail(ctx, QADC_EINVAL, "Quantizer must have sq_bits=4");
     if (count == 0) return QADC_OK;
     QCK(cudaSetDevice(ctx->device));
-    const int dim = ctx->dim, M = ctx->m, CS = M / 2;
+    const int dim = ctx->dim, M = ctx->m, CS = M * ctx->bits / 8;
     const bool ivf = ctx->K > 0;
     const uint32_t kChunk = 1u << 20;
     ENSURE(ctx->b_queries, static_cast<size_t>(std::min(count, kChunk)) * dim * 4);
@@ -977,7 +976,7 @@ int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* ou
         }
         const size_t threads = static_cast<size_t>(n) * CS;
         encode_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(
-            d_in, n, dim, M, ctx->d_codebooks, ivf ? ctx->d_centroids : nullptr, d_assign, ctx->b_dump.as<uint8_t>());
+            d_in, n, dim, M, ctx->bits, ctx->d_codebooks, ivf ? ctx->d_centroids : nullptr, d_assign, ctx->b_dump.as<uint8_t>());
         QCK(cudaGetLastError());
         QCK(cudaMemcpyAsync(out_codes + static_cast<size_t>(off) * CS, ctx->b_dump.p, static_cast<size_t>(n) * CS,
                             cudaMemcpyDeviceToHost, ctx->stream));

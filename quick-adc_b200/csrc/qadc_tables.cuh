@@ -387,15 +387,16 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_probes_kernel(const P
 }
 
 // ---- PQ encoder ("next" row N1) ---------------------------------------------------------------
-// base_pq::encode_multiple_vectors + multiple_set_bits_4 (quantizers.hpp:49-68, :222-245): one
-// thread per (vector, code byte) finds the nearest of 16 centroids for sub-quantisers 2b and 2b+1
-// (direct squared distance, first minimum wins like the k=1 heap) and writes idx[2b] | idx[2b+1]<<4.
+// base_pq::encode_multiple_vectors + multiple_set_bits_4 / _native<uint8_t> (quantizers.hpp:36-68,
+// :222-245): one thread per (vector, code byte) finds the nearest of the 2^bits centroids (direct
+// squared distance, first minimum wins like the k=1 heap) for the sub-quantisers of that byte:
+// 4-bit codes hold idx[2b] | idx[2b+1]<<4, 8-bit codes idx[b].
 // `centroids`/`assign` given: encode the residual x - centroid[assign[v]] (index_db::add_vectors).
 __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ vectors, uint32_t count, int dim, int M,
-                                                     const float* __restrict__ codebooks,
+                                                     int bits, const float* __restrict__ codebooks,
                                                      const float* __restrict__ centroids,
                                                      const int32_t* __restrict__ assign, uint8_t* __restrict__ codes) {
-    const int CS = M / 2, dsq = dim / M;
+    const int CS = M * bits / 8, dsq = dim / M, per = 8 / bits, ncent = 1 << bits;
     const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= static_cast<size_t>(count) * CS) return;
     const uint32_t v = static_cast<uint32_t>(t / CS);
@@ -403,12 +404,12 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ v
     const float* x = vectors + static_cast<size_t>(v) * dim;
     const float* cent = centroids ? centroids + static_cast<size_t>(assign[v]) * dim : nullptr;
     uint32_t code = 0;
-    for (int h = 0; h < 2; ++h) {
-        const int j = 2 * b + h;
+    for (int h = 0; h < per; ++h) {
+        const int j = per * b + h;
         int best = 0;
         float bd = 0.f;
-        for (int c = 0; c < 16; ++c) {
-            const float* cb = codebooks + (static_cast<size_t>(j) * 16 + c) * dsq;
+        for (int c = 0; c < ncent; ++c) {
+            const float* cb = codebooks + (static_cast<size_t>(j) * ncent + c) * dsq;
             float s = 0.f;
             for (int i = 0; i < dsq; ++i) {
                 const float xi = cent ? __fsub_rn(x[j * dsq + i], __ldg(cent + j * dsq + i)) : x[j * dsq + i];
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ v
             }
             if (c == 0 || s < bd) { bd = s; best = c; }
         }
-        code |= static_cast<uint32_t>(best) << (4 * h);
+        code |= static_cast<uint32_t>(best) << (bits * h);
     }
     codes[t] = static_cast<uint8_t>(code);
 }

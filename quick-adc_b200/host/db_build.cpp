@@ -22,7 +22,6 @@ int main(int argc, char* argv[]) {
     }
     if (argc - optind < 3) { std::cerr << "Usage: db_build [-c centroids.fvecs] [-g GPU] pq_file base_file out_db" << std::endl; return 1; }
     std::unique_ptr<base_pq> pq = pq_from_data_file(argv[optind]);
-    if (pq->sq_bits != 4) { std::cerr << "Quantizer must have  sq_bits=4" << std::endl; return 1; }
     vectors_owner<float> base = load_vectors_by_extension(argv[optind + 1]);
     if (base.dimension != pq->dim) { std::cerr << "Base dimension " << base.dimension << " != quantizer dimension " << pq->dim << std::endl; return 1; }
     qadc_ctx* enc = nullptr;

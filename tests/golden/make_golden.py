@@ -86,13 +86,13 @@ def ivf_case(ref, name, seed, dim, m, n, K, ma, nq, r, keep, empty=(), opq=False
     print(name, "heap sizes", res["sizes"])
 
 
-def encode_case(ref, name, seed, dim, m, n):
+def encode_case(ref, name, seed, dim, m, n, bits=4):
     """base_pq::encode_multiple_vectors (quantizers.hpp:222-245) on seeded vectors."""
     rng = np.random.default_rng(seed)
-    cb = synth.make_pq(rng, dim, m)
+    cb = synth.make_pq(rng, dim, m) if bits == 4 else rng.standard_normal((m, 1 << bits, dim // m)).astype(np.float32)
     x = rng.standard_normal((n, dim)).astype(np.float32)
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), dim=dim, m=m, codebooks=cb, vectors=x,
-                        ref_codes=ref.encode(x, m, cb))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), dim=dim, m=m, bits=bits, codebooks=cb, vectors=x,
+                        ref_codes=ref.encode(x, m, cb, bits))
     print(name, "encoded", n)
 
 
@@ -154,7 +154,8 @@ def main():
     def want(name):
         return not only or name in only
 
-    for name, kw in (("encode_m16", dict(seed=105, dim=128, m=16, n=400)), ("encode_m32", dict(seed=106, dim=256, m=32, n=200))):
+    for name, kw in (("encode_m16", dict(seed=105, dim=128, m=16, n=400)), ("encode_m32", dict(seed=106, dim=256, m=32, n=200)),
+                     ("encode_8x8", dict(seed=112, dim=64, m=8, n=300, bits=8))):
         if want(name):
             encode_case(ref, name, **kw)
     # n = 3003: not a multiple of 16 -> exercises the pad-lane duplicate quirk

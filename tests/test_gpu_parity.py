@@ -565,14 +565,42 @@ def test_sharded_coarse_assignment_equals_unsharded(qadc, oracle, G, K, ma):
 
 
 # ---- "next" row N1: PQ encoder on the GPU ----------------------------------------------------
-@pytest.mark.parametrize("name", ["encode_m16", "encode_m32"])
+@pytest.mark.parametrize("name", ["encode_m16", "encode_m32", "encode_8x8"])
 def test_gpu_encoder_matches_reference_and_oracle(qadc, oracle, name):
     g = load(name)
+    bits = int(g["bits"]) if "bits" in g else 4
     ix = qadc.Index(0)
-    ix.set_pq(int(g["dim"]), int(g["m"]), g["codebooks"])
+    ix.set_pq(int(g["dim"]), int(g["m"]), g["codebooks"], bits=bits)
     codes = ix.encode(g["vectors"])
     assert np.array_equal(codes, g["ref_codes"])                                   # reference encoder output
-    assert np.array_equal(codes, oracle.encode(g["vectors"], int(g["m"]), g["codebooks"]))
+    assert np.array_equal(codes, oracle.encode(g["vectors"], int(g["m"]), g["codebooks"], bits))
+    ix.close()
+
+
+def test_gpu_encode_8bit_ivf_then_adc_search(qadc, oracle):
+    """8-bit quantiser end to end: coarse assignment + residual codes on the GPU (== oracle), loaded as
+    a plain-ADC database, searched (== oracle)."""
+    rng = np.random.default_rng(17)
+    dim, m, bits, n, K, ma, nq, r = 64, 8, 8, 20000, 10, 3, 8, 25
+    cb = (0.5 * rng.standard_normal((m, 256, dim // m))).astype(np.float32)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    base = (cents[rng.integers(0, K, n)] + rng.standard_normal((n, dim))).astype(np.float32)
+    ix = qadc.Index(0)
+    ix.set_pq(dim, m, cb, bits=bits)
+    ix.set_coarse(cents)
+    codes, assign = ix.encode(base)
+    exp_assign, _ = oracle.coarse_assign(base, cents, 1)
+    assert np.array_equal(assign, exp_assign[:, 0])
+    assert np.array_equal(codes, oracle.encode((base - cents[assign]).astype(np.float32), m, cb, bits))
+    order = np.argsort(assign, kind="stable")
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(assign, minlength=K))]).astype(np.int64)
+    db = dict(dim=dim, m=m, bits=bits, codebooks=cb, centroids=cents, codes=codes[order], labels=order.astype(np.uint32),
+              offsets=offsets)
+    ix.adc_load(db["codes"], db["labels"], offsets)
+    q = synth.make_queries(rng, nq, dim)
+    ids, d, cnt = ix.adc_search(q, ma, r)
+    exp = oracle.adc_search(db, q, ma, r)
+    assert np.array_equal(ids, exp["ids"]) and np.array_equal(d.view(np.uint32), exp["d"].view(np.uint32))
     ix.close()
 
 

@@ -324,15 +324,16 @@ def test_live_reference_coarse_bug_documented(oracle, ref):
     assert np.array_equal(ref.find_k_neighbors(q, small, 4), brute_s)
 
 
-@pytest.mark.parametrize("name", ["encode_m16", "encode_m32"])
+@pytest.mark.parametrize("name", ["encode_m16", "encode_m32", "encode_8x8"])
 def test_encoder_matches_reference(oracle, name):
-    """PQ encoder (quantizers.hpp:222-245, :49-68): same codes as the reference's encoder."""
+    """PQ encoder (quantizers.hpp:222-245, :36-68): same codes as the reference's encoder."""
     g = load(name)
-    mine = oracle.encode(g["vectors"], int(g["m"]), g["codebooks"])
+    bits = int(g["bits"]) if "bits" in g else 4
+    mine = oracle.encode(g["vectors"], int(g["m"]), g["codebooks"], bits)
     assert np.array_equal(mine, g["ref_codes"])
-    # code format: byte b = idx[2b] | idx[2b+1] << 4
+    # code format: 4-bit: byte b = idx[2b] | idx[2b+1] << 4; 8-bit: byte b = idx[b]
     x, cb, m = g["vectors"], g["codebooks"], int(g["m"])
     dsq = x.shape[1] // m
     idx = np.stack([np.argmin(((x[:, None, j * dsq:(j + 1) * dsq] - cb[j][None]) ** 2).sum(-1), axis=1) for j in range(m)], 1)
-    packed = (idx[:, 0::2] | (idx[:, 1::2] << 4)).astype(np.uint8)
+    packed = (idx[:, 0::2] | (idx[:, 1::2] << 4)).astype(np.uint8) if bits == 4 else idx.astype(np.uint8)
     assert (packed != mine).mean() < 1e-3   # float64 argmin vs float32 direct form: only near-ties may differ
