@@ -246,6 +246,8 @@ def run_ours(args):
     if args.qb:
         ix.set_option("flat_qb", args.qb)
     ix.set_option("time_scan", 1)
+    if args.flat_filter is not None:
+        ix.set_option("flat_filter", args.flat_filter)
 
     # device-resident buffers (the `value` leg)
     d_q = torch.from_numpy(queries).to(dev)
@@ -410,6 +412,7 @@ def main():
     ap.add_argument("--n-vectors", type=int, default=int(os.environ.get("QADC_BENCH_N", 10 ** 9)))
     ap.add_argument("--queries", type=int, default=16)
     ap.add_argument("--qb", type=int, default=1, help="queries per pass of the flat scan (0 = library default)")
+    ap.add_argument("--flat-filter", type=int, default=None, help="0: exact lookup core only (A/B against the pre-filter)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verify", type=int, default=2, help="queries cross-checked at full size after timing (N=1 only)")
     args = ap.parse_args()

@@ -93,6 +93,13 @@ int qadc_begin_database(qadc_ctx* ctx, int partition_count, const uint32_t* size
  * ownership (the reference's scanner then calls db.free_partition, db_query_4.cpp:190). */
 int qadc_upload_codes(qadc_ctx* ctx, int part_i, uint32_t first, uint32_t count,
                       const uint8_t* codes, const uint32_t* labels, int on_device);
+/* The whole database in one call: `codes` / `labels` hold the partitions back to back in partition
+ * order (sum of sizes vectors), e.g. an inverted index kept as one sorted array.  One copy and one
+ * re-layout launch per run of partitions instead of one per partition (65 536 lists: seconds -> ms). */
+int qadc_upload_database(qadc_ctx* ctx, const uint8_t* codes, const uint32_t* labels, int on_device);
+/* Same from one host pointer per partition, as base_db::get_partition hands them out
+ * (databases.hpp:120-134, :233-250): part_codes[p] / part_labels[p] may be NULL where sizes[p] == 0. */
+int qadc_upload_partitions(qadc_ctx* ctx, const uint8_t* const* part_codes, const uint32_t* const* part_labels);
 /* Sharded databases only: position of this context's first vector inside the full
  * partition (flat database split across GPUs), default 0. */
 int qadc_set_position_base(qadc_ctx* ctx, int part_i, uint32_t pos_base);
@@ -201,7 +208,8 @@ int qadc_adc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, 
 
 /* ---- tuning knobs (bench / tests) ------------------------------------------------------ */
 /* key: "flat_qb" (queries per pass of the flat scan: 1,2,4,8), "flat_chunks" (CTAs along
- * the database, 0 = auto), "ivf_sb_per_item" (256-vector blocks per work item of the inverted-list
+ * the database, 0 = auto), "flat_filter" (1 = default: clamped byte-lane pre-filter in front of the exact
+ * lookup core of the one-query-per-pass flat scan, 0 = exact core only; same results), "ivf_sb_per_item" (256-vector blocks per work item of the inverted-list
  * scan, default 8), "time_scan" (1: record CUDA events around the scan kernel for
  * qadc_last_scan_ms).  Unknown key -> QADC_EINVAL. */
 int qadc_set_option(qadc_ctx* ctx, const char* key, long value);

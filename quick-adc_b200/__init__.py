@@ -64,6 +64,8 @@ def load_library(build_if_missing=True):
     L.qadc_set_coarse.argtypes = [vp, i32, vp]
     L.qadc_begin_database.argtypes = [vp, i32, vp, i32]
     L.qadc_upload_codes.argtypes = [vp, i32, u32, u32, vp, vp, i32]
+    L.qadc_upload_database.argtypes = [vp, vp, vp, i32]
+    L.qadc_upload_partitions.argtypes = [vp, vp, vp]
     L.qadc_set_position_base.argtypes = [vp, i32, u32]
     L.qadc_set_prefix.argtypes = [vp, i32, vp, u32, i32]
     L.qadc_finalize.argtypes = [vp, f32]
@@ -86,7 +88,7 @@ def load_library(build_if_missing=True):
     L.qadc_download_codes.argtypes = [vp, i32, vp]
     L.qadc_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.qadc_encode.argtypes = [vp, vp, u32, vp, vp]
-    for name in ("qadc_create", "qadc_set_pq", "qadc_set_coarse", "qadc_begin_database", "qadc_upload_codes",
+    for name in ("qadc_upload_database", "qadc_upload_partitions", "qadc_create", "qadc_set_pq", "qadc_set_coarse", "qadc_begin_database", "qadc_upload_codes",
                  "qadc_set_position_base", "qadc_set_prefix", "qadc_finalize", "qadc_search", "qadc_search_device",
                  "qadc_synchronize", "qadc_last_launch_count", "qadc_last_scan_ms", "qadc_merge_shards_device",
                  "qadc_build_tables", "qadc_scan_with_tables", "qadc_dump_distances", "qadc_download_codes",
@@ -158,6 +160,15 @@ class Index:
         lab = None if labels is None else np.ascontiguousarray(labels, np.uint32)
         self._ck(self.lib.qadc_upload_codes(self.h, part_i, first, codes.shape[0], _ptr(codes), _ptr(lab), 0))
 
+    def upload_database(self, codes, labels=None):
+        """All partitions at once: rows in partition order (qadc_upload_database)."""
+        codes = np.ascontiguousarray(codes, np.uint8)
+        lab = None if labels is None else np.ascontiguousarray(labels, np.uint32)
+        self._ck(self.lib.qadc_upload_database(self.h, _ptr(codes), _ptr(lab), 0))
+
+    def upload_database_device(self, d_codes, d_labels=None):
+        self._ck(self.lib.qadc_upload_database(self.h, _ptr(int(d_codes)), _ptr(None if d_labels is None else int(d_labels)), 1))
+
     def upload_codes_device(self, part_i, first, count, d_codes, d_labels=None):
         self._ck(self.lib.qadc_upload_codes(self.h, part_i, first, count, _ptr(int(d_codes)),
                                             _ptr(None if d_labels is None else int(d_labels)), 1))
@@ -187,9 +198,8 @@ class Index:
         offsets = np.asarray(offsets, np.int64)
         sizes = np.diff(offsets).astype(np.uint32)
         self.begin_database(sizes, True)
-        for p in range(len(sizes)):
-            if sizes[p]:
-                self.upload_codes(p, 0, codes[offsets[p]:offsets[p + 1]], labels[offsets[p]:offsets[p + 1]])
+        lo, hi = int(offsets[0]), int(offsets[-1])
+        self.upload_database(codes[lo:hi], labels[lo:hi])
         self.finalize(keep)
 
     def encode(self, vectors):

@@ -73,7 +73,7 @@ struct qadc_ctx {
     int* d_err = nullptr;
     int* h_err = nullptr;   // pinned
     // options / accounting
-    long opt_flat_qb = 0, opt_flat_chunks = 0;
+    long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1;
     int ivf_sb_per_item = 8;   // superblocks per work item of the IVF scan (option "ivf_sb_per_item")
     int launches = 0;
     cudaEvent_t ev[8] = {};
@@ -279,7 +279,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         a.codes = ctx->d_codes; a.n_sb = static_cast<uint32_t>(ctx->total_sb); a.size = ctx->h_size[0];
         a.pos_base = ctx->h_pos_base[0]; a.sb_per_chunk = pl.sb_per_chunk; a.qtabs = d_qtables; a.nq = nq;
         a.r = r; a.cap = pl.cap; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
-        a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk;
+        a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk; a.use_filter = static_cast<int>(ctx->opt_flat_filter);
         rc = pl.v->launch(ctx, a, pl.chunks);
         if (rc) return rc == QADC_ENOMEM ? fail(ctx, rc, "scan kernel shared memory exceeds 227 KB") : rc;
     } else {
@@ -362,6 +362,9 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
     {
         dim3 tgrid((ma + 7) / 8, nq);
         auto launch_tables = [&](auto kernel) {
+            // 8 warps x (residual + rotated copy) x dim floats; above 48 KB (dim > 768, e.g. GIST-960) the kernel opts in
+            if (static_cast<size_t>(dim) * 64 > 48 * 1024)
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dim * 64);
             kernel<<<tgrid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(
                 d_queries, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
                 ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), 4);
@@ -508,6 +511,8 @@ int qadc_set_pq(qadc_ctx* ctx, int dim, int m, int bits, const float* codebooks,
     if (!quick && !adc8)
         return fail(ctx, QADC_EINVAL, "Unsupported (nsq,nsq_bits) configuration. Supported: (16,4) (32,4); plain ADC also (4,8) (8,8) (16,8).");
     if (dim <= 0 || dim % m != 0) return fail(ctx, QADC_EINVAL, "dim must be a positive multiple of m");
+    if (static_cast<size_t>(dim) * 64 > static_cast<size_t>(kMaxSmem))
+        return fail(ctx, QADC_EINVAL, "dim > 3632 is not supported (the table kernel keeps 8 x 2 x dim floats in shared memory)");
     QCK(cudaSetDevice(ctx->device));
     cudaFree(ctx->d_codebooks); cudaFree(ctx->d_rotation);
     ctx->d_codebooks = nullptr; ctx->d_rotation = nullptr;
@@ -603,6 +608,100 @@ int qadc_upload_codes(qadc_ctx* ctx, int part_i, uint32_t first, uint32_t count,
         QCK(cudaMemcpyAsync(ctx->d_labels + ctx->h_label_off[part_i] + first, labels, static_cast<size_t>(count) * 4,
                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     QCK(cudaStreamSynchronize(ctx->stream));
+    ctx->finalized = false;
+    return QADC_OK;
+}
+
+// Uploads the partitions [p0, p1) from one contiguous source (device pointer, or host through the staging buffer).
+static int upload_run(qadc_ctx* ctx, int p0, int p1, const uint8_t* codes, const uint32_t* labels, bool src_on_device) {
+    const int M = ctx->m, CS = M / 2;
+    const uint64_t v0 = ctx->h_label_off[p0];
+    const uint64_t v1 = (p1 < ctx->parts) ? ctx->h_label_off[p1] : ctx->total_vec;
+    const uint64_t sb0 = ctx->h_sb_off[p0], sb1 = (p1 < ctx->parts) ? ctx->h_sb_off[p1] : ctx->total_sb;
+    if (v1 == v0) return QADC_OK;
+    const uint8_t* d_src = codes;
+    if (!src_on_device) {
+        ENSURE(ctx->staging, (v1 - v0) * CS);
+        QCK(cudaMemcpyAsync(ctx->staging.p, codes, (v1 - v0) * CS, cudaMemcpyHostToDevice, ctx->stream));
+        d_src = ctx->staging.as<uint8_t>();
+    }
+    const uint64_t threads = (sb1 - sb0) * 32;
+    const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
+    if (M == 16)
+        transpose_partitions_kernel<16><<<blocks, 256, 0, ctx->stream>>>(d_src, p0, p1, ctx->d_sb_off, ctx->d_label_off, ctx->d_size, sb1, ctx->d_codes);
+    else
+        transpose_partitions_kernel<32><<<blocks, 256, 0, ctx->stream>>>(d_src, p0, p1, ctx->d_sb_off, ctx->d_label_off, ctx->d_size, sb1, ctx->d_codes);
+    QCK(cudaGetLastError());
+    if (ctx->has_labels)
+        QCK(cudaMemcpyAsync(ctx->d_labels + v0, labels, (v1 - v0) * 4, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                            ctx->stream));
+    QCK(cudaStreamSynchronize(ctx->stream));   // the staging buffer / the caller's buffers are free again
+    return QADC_OK;
+}
+
+int qadc_upload_database(qadc_ctx* ctx, const uint8_t* codes, const uint32_t* labels, int on_device) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "qadc_begin_database must be called first");
+    if (ctx->total_vec == 0) return QADC_OK;
+    if (!codes) return fail(ctx, QADC_EINVAL, "codes is null");
+    if (ctx->has_labels && !labels) return fail(ctx, QADC_EINVAL, "labels is null but the database has labels");
+    QCK(cudaSetDevice(ctx->device));
+    const int CS = ctx->m / 2;
+    const uint64_t kChunk = 1u << 23;   // vectors per run (64 / 128 MiB of staging)
+    int p0 = 0;
+    while (p0 < ctx->parts) {
+        const uint64_t v0 = ctx->h_label_off[p0];
+        if (ctx->h_size[p0] > kChunk) {   // a partition larger than a run goes through the chunked single-partition path
+            int rc = qadc_upload_codes(ctx, p0, 0, ctx->h_size[p0], codes + v0 * CS, labels ? labels + v0 : nullptr, on_device);
+            if (rc) return rc;
+            ++p0;
+            continue;
+        }
+        int p1 = p0 + 1;
+        while (p1 < ctx->parts && ctx->h_size[p1] <= kChunk && ctx->h_label_off[p1] + ctx->h_size[p1] - v0 <= kChunk) ++p1;
+        int rc = upload_run(ctx, p0, p1, codes + v0 * CS, labels ? labels + v0 : nullptr, on_device != 0);
+        if (rc) return rc;
+        p0 = p1;
+    }
+    ctx->finalized = false;
+    return QADC_OK;
+}
+
+int qadc_upload_partitions(qadc_ctx* ctx, const uint8_t* const* part_codes, const uint32_t* const* part_labels) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "qadc_begin_database must be called first");
+    if (!part_codes) return fail(ctx, QADC_EINVAL, "part_codes is null");
+    if (ctx->has_labels && !part_labels) return fail(ctx, QADC_EINVAL, "part_labels is null but the database has labels");
+    QCK(cudaSetDevice(ctx->device));
+    const size_t CS = ctx->m / 2;
+    const uint64_t kChunk = 1u << 22;
+    std::vector<uint8_t> hc;
+    std::vector<uint32_t> hl;
+    int p0 = 0;
+    while (p0 < ctx->parts) {
+        if (ctx->h_size[p0] > kChunk) {
+            int rc = qadc_upload_codes(ctx, p0, 0, ctx->h_size[p0], part_codes[p0], ctx->has_labels ? part_labels[p0] : nullptr, 0);
+            if (rc) return rc;
+            ++p0;
+            continue;
+        }
+        // gather a run of short partitions into one host buffer, then one copy + one re-layout launch
+        int p1 = p0;
+        uint64_t n = 0;
+        while (p1 < ctx->parts && ctx->h_size[p1] <= kChunk && n + ctx->h_size[p1] <= kChunk) { n += ctx->h_size[p1]; ++p1; }
+        hc.resize(n * CS);
+        if (ctx->has_labels) hl.resize(n);
+        uint64_t at = 0;
+        for (int p = p0; p < p1; ++p) {
+            const uint32_t sz = ctx->h_size[p];
+            if (!sz) continue;
+            if (!part_codes[p] || (ctx->has_labels && !part_labels[p])) return fail(ctx, QADC_EINVAL, "null partition pointer");
+            memcpy(hc.data() + at * CS, part_codes[p], sz * CS);
+            if (ctx->has_labels) memcpy(hl.data() + at, part_labels[p], static_cast<size_t>(sz) * 4);
+            at += sz;
+        }
+        int rc = upload_run(ctx, p0, p1, hc.data(), ctx->has_labels ? hl.data() : nullptr, false);
+        if (rc) return rc;
+        p0 = p1;
+    }
     ctx->finalized = false;
     return QADC_OK;
 }
@@ -1069,6 +1168,8 @@ int qadc_adc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, 
         {
             dim3 tgrid((ma + 7) / 8, n);
             auto launch_tables = [&](auto kernel) {
+                if (static_cast<size_t>(dim) * 64 > 48 * 1024)
+                    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dim * 64);
                 kernel<<<tgrid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(
                     d_q, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
                     ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), bits);
@@ -1122,6 +1223,7 @@ int qadc_set_option(qadc_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return QADC_EINVAL;
     if (!strcmp(key, "flat_qb")) ctx->opt_flat_qb = value;
     else if (!strcmp(key, "flat_chunks")) ctx->opt_flat_chunks = value;
+    else if (!strcmp(key, "flat_filter")) ctx->opt_flat_filter = value != 0;
     else if (!strcmp(key, "ivf_sb_per_item")) {
         if (value < 1 || value > (1 << 20)) return fail(ctx, QADC_EINVAL, "ivf_sb_per_item out of range");
         ctx->ivf_sb_per_item = static_cast<int>(value);

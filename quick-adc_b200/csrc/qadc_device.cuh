@@ -159,6 +159,62 @@ __device__ __forceinline__ bool any_below(const GroupAcc& g) {
 __device__ __forceinline__ uint32_t lane_raw(const GroupAcc& g, int k) { return (g.v[k] + 0x8000u) & 0xffffu; }
 __device__ __forceinline__ uint32_t lane_sum(const GroupAcc& g, int k, uint32_t bound) { return g.v[k] + bound; }
 
+// ---- pre-filter: clamped tables summed in byte lanes ------------------------------------------
+// A vector is a candidate iff S = sum_j T[j][c_j] <= t (t = bound - 1 <= 126).  With F[j][c] =
+// min(T[j][c], cap) the sum F_S = sum_j F[j][c_j] <= S, so F_S > t proves S > t: a conservative
+// test that needs no widening at all when the byte lanes cannot wrap.  A lane starts at 127 - t and
+// receives M entries <= cap, cap = (128 + t) / M, so it ends at 127 - t + F_S <= 255 and its bit 7
+// says F_S > t.  Per sub-quantiser word (8 vectors): 1 XOR + 2 SHF + 4 PRMT on the ALU pipe and
+// 4 IMAD on the FMA pipe — the 8 IDP.4A + 2 IMAD per word pair of the exact core are gone.  Only
+// superblocks in which some vector passes (a few percent once the bound has tightened: the clamp
+// loses little because entries above cap already take a large share of t) run the exact core.
+struct FiltAcc {
+    uint32_t a, b;   // byte lane k of a: vector k (0..3) of the group, of b: vector 4 + k
+};
+__device__ __forceinline__ int filt_cap(int t, int m) { return (128 + t) / m; }
+__device__ __forceinline__ uint32_t filt_start(int t) { return static_cast<uint32_t>(127 - t) * 0x01010101u; }
+// a * one + b as an opaque IMAD: written in C++ the compiler factors the multiplications out of the whole
+// sum of a superblock and adds the PRMT results with IADD3 on the ALU pipe, the pipe that binds
+__device__ __forceinline__ uint32_t madd(uint32_t a, uint32_t b, const PipeK& k) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(k.one), "r"(b));
+    return d;
+}
+#ifndef QADC_FILT_ADD
+#define QADC_FILT_ADD 0
+#endif
+#ifndef QADC_FILT_HI16
+#define QADC_FILT_HI16 0   // 0: SHF (ALU pipe), 1: multiply-high by 65536 (FMA pipe), 2: 32x32->64 multiply, upper word
+#endif
+__device__ __forceinline__ uint32_t filt_hi16(uint32_t w, const PipeK& k) {
+#if QADC_FILT_HI16 == 1
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(w), "r"(k.s2));   // s2 = 1 << 16, opaque
+    return d;
+#elif QADC_FILT_HI16 == 2
+    uint64_t d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(w), "r"(k.s2));
+    return static_cast<uint32_t>(d >> 32);
+#else
+    return hi16(w, k);
+#endif
+}
+__device__ __forceinline__ void filt_word(uint32_t w, const uint4& f, FiltAcc& g, const PipeK& k) {
+    const uint32_t x = w ^ 0x88888888u;
+#if QADC_FILT_ADD == 1      // three-input adds on the ALU pipe (half the add instructions, on the busier pipe)
+    g.a = g.a + prmt(f.x, f.y, w) + prmt(f.z, f.w, x);
+    g.b = g.b + prmt(f.x, f.y, filt_hi16(w, k)) + prmt(f.z, f.w, filt_hi16(x, k));
+#elif QADC_FILT_ADD == 2    // one accumulator on each pipe
+    g.a = g.a + prmt(f.x, f.y, w) + prmt(f.z, f.w, x);
+    g.b = madd(madd(prmt(f.x, f.y, filt_hi16(w, k)), prmt(f.z, f.w, filt_hi16(x, k)), k), g.b, k);
+#else
+    g.a = madd(madd(prmt(f.x, f.y, w), prmt(f.z, f.w, x), k), g.a, k);
+    g.b = madd(madd(prmt(f.x, f.y, filt_hi16(w, k)), prmt(f.z, f.w, filt_hi16(x, k)), k), g.b, k);
+#endif
+}
+// some vector of the group may be a candidate (bit 7 of its lane still clear)
+__device__ __forceinline__ bool filt_any(const FiltAcc& g) { return (~(g.a & g.b) & 0x80808080u) != 0u; }
+
 // ---- bounded candidate lists: bitonic sort of u64 keys in shared memory ------------------
 // Sorts n (power of two) keys ascending with the threads [0, nthreads) of a group that
 // synchronises through `sync()` (a __syncwarp or a named barrier).

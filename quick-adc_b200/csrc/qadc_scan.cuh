@@ -44,6 +44,50 @@ __global__ void __launch_bounds__(256) transpose_codes_kernel(const uint8_t* __r
         dst[q * 32 + lane] = make_uint4(word[4 * q], word[4 * q + 1], word[4 * q + 2], word[4 * q + 3]);
 }
 
+// Same for a run of partitions [p0, p1) whose row-major codes lie back to back in `codes` (partition p0
+// first): one launch for thousands of short inverted lists instead of one per list.  One thread per
+// (superblock, lane) of the run; the partition of a superblock is found by bisection of sb_off.
+template <int M>
+__global__ void __launch_bounds__(256) transpose_partitions_kernel(const uint8_t* __restrict__ codes, int p0, int p1,
+                                                                   const uint64_t* __restrict__ sb_off,      // [P] first superblock
+                                                                   const uint64_t* __restrict__ vec_off,     // [P] first vector
+                                                                   const uint32_t* __restrict__ size,        // [P]
+                                                                   uint64_t sb_end,                          // first superblock after the run
+                                                                   uint8_t* __restrict__ out) {              // native layout, whole database
+    constexpr int CS = M / 2;
+    const uint64_t sb_first = sb_off[p0];
+    const uint64_t gidx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t sb = sb_first + gidx / 32;
+    if (sb >= sb_end) return;
+    const uint32_t lane = static_cast<uint32_t>(gidx % 32);
+    int lo = p0, hi = p1;   // last p in [p0, p1) with sb_off[p] <= sb (empty partitions share their successor's offset)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (sb_off[mid] <= sb) lo = mid; else hi = mid;
+    }
+    const uint32_t n = size[lo];
+    const uint32_t local = static_cast<uint32_t>(sb - sb_off[lo]) * kSbVec + lane * 8;
+    const uint8_t* src = codes + (vec_off[lo] - vec_off[p0]) * CS;
+    uint32_t word[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) word[j] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t v = min(local + k, n - 1);
+        const uint8_t* c = src + static_cast<size_t>(v) * CS;
+#pragma unroll
+        for (int b = 0; b < CS; ++b) {
+            const uint32_t byte = c[b];
+            word[2 * b] |= (byte & 15u) << (4 * k);
+            word[2 * b + 1] |= (byte >> 4) << (4 * k);
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + sb * sb_bytes(M));
+#pragma unroll
+    for (int q = 0; q < M / 4; ++q)
+        dst[q * 32 + lane] = make_uint4(word[4 * q], word[4 * q + 1], word[4 * q + 2], word[4 * q + 3]);
+}
+
 // Inverse (tests: layout round trip).
 template <int M>
 __global__ void __launch_bounds__(256) untranspose_codes_kernel(const uint8_t* __restrict__ native, uint32_t size,
@@ -122,6 +166,22 @@ __device__ __forceinline__ void store_list(const WarpList& list, uint64_t* dst, 
 // the top r if d <= v.  Read with a volatile load so every tile sees recent updates.
 __device__ __forceinline__ int load_shared_bound(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
+// Same, predicated on sel == 0 and written straight into `v` (a predicated load into the variable's own register:
+// the C++ form goes through a temporary whose copy waits for the load at once).
+__device__ __forceinline__ void load_shared_bound_if(int& v, const int* p, uint32_t sel) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.u32 p, %2, 0;\n\t"
+        "@p ld.volatile.global.s32 %0, [%1];\n\t}"
+        : "+r"(v)
+        : "l"(p), "r"(sel)
+        : "memory");
+}
+
+__device__ __forceinline__ void load_shared_bound_now(int& v, const int* p) {
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+}
+
 // After a warp pushed `added` candidates: count them CTA-wide and, when the count passes the next
 // threshold, re-derive the query's shared bound from the CTA histogram.  Whole warp calls it;
 // returns the new bound (or 127 when nothing changed).
@@ -162,6 +222,7 @@ struct FlatScanArgs {
     int n_lists;            // gridDim.x * NW
     int* shared_bound;      // [nq]
     PipeK k;                // {1, -1}
+    int use_filter;         // register-table variant: clamped byte-lane pre-filter before the exact core
 };
 
 template <int M, int QB, int NW, int NS>
@@ -171,9 +232,10 @@ struct FlatCfg {
     static constexpr int kTileBytes = NW * kSbBytes;
     static constexpr bool kRegTab = (QB == 1 && M == 16 && NW <= 16);   // more warps: tables stay in shared memory
     static constexpr int kThreads = (NW + 1) * 32;
-    // tiles | tables | full/empty barriers | histogram + counters | list counts/bounds, rounded to 16 bytes
+    static constexpr int kFiltBytes = kRegTab ? NW * M * 16 : 0;   // per-warp clamped table (pre-filter)
+    // tiles | tables | filter tables | full/empty barriers | histogram + counters | list counts/bounds, rounded to 16 bytes
     static constexpr int kFixedBytes =
-        ((NS * kTileBytes + QB * M * 16 + 2 * NS * 8 + QB * (128 + 2) * 4 + NW * QB * 8) + 15) / 16 * 16;
+        ((NS * kTileBytes + QB * M * 16 + kFiltBytes + 2 * NS * 8 + QB * (128 + 2) * 4 + NW * QB * 8) + 15) / 16 * 16;
     static size_t smem_bytes(int cap) { return static_cast<size_t>(kFixedBytes) + static_cast<size_t>(NW) * QB * cap * 8; }
 };
 
@@ -185,7 +247,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
     // lookup loop); only the candidate lists, whose size depends on `cap`, come last
     uint8_t* tiles = smem;
     uint4* qtab = reinterpret_cast<uint4*>(tiles + static_cast<size_t>(NS) * Cfg::kTileBytes);   // [QB][M]
-    uint64_t* full = reinterpret_cast<uint64_t*>(qtab + QB * M);
+    uint4* ftab = qtab + QB * M;                                                                  // [NW][M] (kRegTab only)
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ftab) + Cfg::kFiltBytes);
     uint64_t* empty = full + NS;
     int* hist = reinterpret_cast<int*>(empty + NS);   // [QB][128] candidate histogram (16-byte aligned)
     int* hist_total = hist + QB * 128;                // [QB] candidates counted
@@ -245,11 +308,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
         wl[qi].count = cnt + warp * QB + qi;
         wl[qi].bound = bnd + warp * QB + qi;
     }
-    uint4 treg[Cfg::kRegTab ? M : 1];
-    if constexpr (Cfg::kRegTab) {
-#pragma unroll
-        for (int j = 0; j < M; ++j) treg[j] = qtab[j];
-    }
     const int halves = (a.cap < a.r + kSbVec) ? 2 : 1;
     const int compact_at = min(a.cap - kSbVec / halves, 2 * a.r);
 
@@ -267,78 +325,196 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
         gb[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
     }
 
-    for (uint32_t t = 0; t < n_tiles; ++t) {
-        mbar_wait_a(full_a + stage * 8, phase);
-        if (t < n_left) {
+    // the rare path of one (superblock, query): append the candidates of the group sums `g`, count them
+    // CTA-wide (histogram -> shared bound) and compact the list when it fills up
+    auto emit_group = [&](const GroupAcc& g, const bool mine, const uint32_t bound, const int qi, const uint32_t sb) {
+        // small lists (cap < r + 256) take the superblock in two position-ordered halves
+        for (int half = 0; half < halves; ++half) {
+            const int before = *wl[qi].count;
+            __syncwarp();
+            const bool my_turn = halves == 1 || (lane >> 4) == half;
+            if (mine && my_turn)
+                emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi], hist + qi * 128);
+            __syncwarp();
+            const int now = *wl[qi].count;
+            {
+                // CTA-wide count of candidates; when it passes the next threshold this warp
+                // re-derives the query's shared bound from the CTA histogram
+                const int hb = hist_update(hist + qi * 128, hist_total + qi, hist_next + qi, now - before,
+                                           a.r, lane, a.shared_bound + qbase + qi);
+                if (hb < gb[qi]) gb[qi] = hb;
+            }
+            if (now >= compact_at) {
+                wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
+                lbound[qi] = *wl[qi].bound;
+            }
+        }
+    };
+
+    if constexpr (Cfg::kRegTab) {
+        // ---- one query per pass, its table in 64 registers ----
+        // treg holds either the exact table or (pre-filter on) the clamped one; the filter starts on
+        // and a warp falls back to the exact core for a while when too many superblocks pass it
+        // (loose bound, saturated tables), so the worst case costs what the exact core costs.
+        uint4 treg[M];
+        uint4* my_ftab = ftab + warp * M;
+        // bound = the strict bound of the moment (min of the local strict bound and the shared bound + 1), the
+        // only bound kept across iterations; f_start = start value of the filter lanes (127 - t_f in every byte,
+        // t_f = the threshold the clamped table in treg was built for); ctl = mode control: filter on -> pass-rate
+        // score (+6 per passing superblock, -1 otherwise, floor 0), filter off -> superblocks left before the
+        // filter is tried again
+        int bound = min(lbound[0], gb[0] + 1);
+        uint32_t f_start = 0;
+        bool filt_on = a.use_filter != 0;
+        int ctl = 0;
+        auto load_table = [&]() {   // all lanes; (re)builds treg for the current mode and bound
+            if (filt_on) {
+                const int t_f = bound - 1;
+                f_start = filt_start(t_f);
+                const uint32_t cap4 = static_cast<uint32_t>(filt_cap(t_f, M)) * 0x01010101u;
+                __syncwarp();
+                if (lane < M) {
+                    const uint4 t = qtab[lane];
+                    my_ftab[lane] = make_uint4(__vminu4(t.x, cap4), __vminu4(t.y, cap4), __vminu4(t.z, cap4), __vminu4(t.w, cap4));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < M; ++j) treg[j] = my_ftab[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < M; ++j) treg[j] = qtab[j];
+            }
+        };
+        load_table();
+        int gb_pending = bound - 1;
+
+        uint32_t t = 0;
+        for (; t < n_left; ++t) {
+            mbar_wait_a(full_a + stage * 8, phase);
             const uint32_t src = slot + stage * Cfg::kTileBytes;
             uint4 w[Cfg::kQuads];
 #pragma unroll
             for (int q = 0; q < Cfg::kQuads; ++q) w[q] = lds128(src + q * 512);
-            int gb_next[QB];
-            if (stage == 0) {
-#pragma unroll
-                for (int qi = 0; qi < QB; ++qi) gb_next[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
-            }
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty_a + stage * 8);   // the words are in registers: release the stage early
-#pragma unroll
-            for (int qi = 0; qi < QB; ++qi) {
-                if (qi < nqb) {
-                    const uint32_t bound = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
-                    GroupAcc g;
-                    // (Early abandon — skipping the last sub-quantisers once every vector of the superblock
-                    // has reached the bound — is exact but was measured 5 % slower: the vote/branch splits
-                    // the unrolled lookup chain.)
-#pragma unroll
-                    for (int p = 0; p < M / 2; ++p) {   // pairs of sub-quantisers
-                        uint4 t0, t1;
-                        if constexpr (Cfg::kRegTab) { t0 = treg[2 * p]; t1 = treg[2 * p + 1]; }
-                        else { t0 = qtab[qi * M + 2 * p]; t1 = qtab[qi * M + 2 * p + 1]; }
-                        const uint4& wq = w[p >> 1];
-                        scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, t0, t1, g, pk, bound);
-                    }
-                    const bool mine = any_below(g);
-                    if (__any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
-                        // small lists (cap < r + 256) take the superblock in two position-ordered halves
-                        for (int half = 0; half < halves; ++half) {
-                            const int before = *wl[qi].count;
-                            __syncwarp();
-                            const bool my_turn = halves == 1 || (lane >> 4) == half;
-                            if (mine && my_turn)
-                                emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl[qi], hist + qi * 128);
-                            __syncwarp();
-                            const int now = *wl[qi].count;
-                            {
-                                // CTA-wide count of candidates; when it passes the next threshold this warp
-                                // re-derives the query's shared bound from the CTA histogram
-                                const int hb = hist_update(hist + qi * 128, hist_total + qi, hist_next + qi, now - before,
-                                                           a.r, lane, a.shared_bound + qbase + qi);
-                                if (hb < gb[qi]) gb[qi] = hb;
-                            }
-                            if (now >= compact_at) {
-                                wl[qi].compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
-                                lbound[qi] = *wl[qi].bound;
-                            }
-                        }
-                        if constexpr (Cfg::kRegTab) {
-                            // the 64 table registers are re-read from shared memory here, so they need not
-                            // stay live (or be spilled) across the rare path above
-#pragma unroll
-                            for (int j = 0; j < M; ++j) treg[j] = qtab[j];
-                        }
-                    }
-                }
-            }
+            bool reload = false;
             if (stage == 0) {
-#pragma unroll
-                for (int qi = 0; qi < QB; ++qi) gb[qi] = gb_next[qi];
+                // the shared bound is read once per ring revolution and used one revolution later: the load
+                // (an L2 hit, ~1 us under load) is never waited for
+                bound = min(bound, gb_pending + 1);
+                load_shared_bound_now(gb_pending, a.shared_bound + qbase);
+                // rebuild the clamped table when the bound has moved enough to allow a tighter one
+                reload = filt_on && bound + 3 <= 127 - static_cast<int>(f_start & 0xffu);
             }
-        } else {
+            GroupAcc g;
+            bool mine = false;
+            if (filt_on) {
+#ifdef QADC_FILT_ACC4
+                // two accumulator pairs (even / odd quads): half the dependent-add chain length
+                FiltAcc f{f_start, f_start}, f2{0u, 0u};
+#pragma unroll
+                for (int q = 0; q < Cfg::kQuads; ++q) {
+                    FiltAcc& fq = (q & 1) ? f2 : f;
+                    filt_word(w[q].x, treg[4 * q], fq, pk);
+                    filt_word(w[q].y, treg[4 * q + 1], fq, pk);
+                    filt_word(w[q].z, treg[4 * q + 2], fq, pk);
+                    filt_word(w[q].w, treg[4 * q + 3], fq, pk);
+                }
+                f.a = madd(f2.a, f.a, pk); f.b = madd(f2.b, f.b, pk);
+#else
+                FiltAcc f{f_start, f_start};
+#pragma unroll
+                for (int q = 0; q < Cfg::kQuads; ++q) {
+                    filt_word(w[q].x, treg[4 * q], f, pk);
+                    filt_word(w[q].y, treg[4 * q + 1], f, pk);
+                    filt_word(w[q].z, treg[4 * q + 2], f, pk);
+                    filt_word(w[q].w, treg[4 * q + 3], f, pk);
+                }
+#endif
+                ctl = max(ctl - 1, 0);
+                if (__any_sync(0xffffffffu, filt_any(f))) {
+                    // some vector may be below the bound: exact sums with the table read from shared memory
+                    // (the words pass through an opaque IMAD so that ptxas does not keep the filter's 48
+                    // selector registers alive, i.e. spilled, for reuse here)
+                    ctl += 6;
+                    if (ctl > 96) { filt_on = false; ctl = 256; reload = true; }   // ~1 superblock in 6 passes the filter
+#pragma unroll
+                    for (int p = 0; p < M / 2; ++p) {
+                        const uint4 t0 = qtab[2 * p], t1 = qtab[2 * p + 1];
+                        const uint4& wq = w[p >> 1];
+                        scan_pair(p == 0, madd((p & 1) ? wq.z : wq.x, 0u, pk), madd((p & 1) ? wq.w : wq.y, 0u, pk), t0, t1, g, pk, bound);
+                    }
+                    mine = any_below(g);
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < M / 2; ++p) {   // pairs of sub-quantisers
+                    const uint4& wq = w[p >> 1];
+                    scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, treg[2 * p], treg[2 * p + 1], g, pk, bound);
+                }
+                mine = any_below(g);
+                if (--ctl <= 0 && a.use_filter) { filt_on = true; ctl = 0; reload = true; }
+            }
+            if (__any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
+                lbound[0] = bound; gb[0] = bound - 1;   // equivalent split of the one strict bound
+                emit_group(g, mine, bound, 0, sb0 + warp + t * NW);
+                bound = min(bound, min(lbound[0], gb[0] + 1));
+                reload = true;   // the 64 table registers need not stay live (or be spilled) across the rare path
+            }
+            if (reload) load_table();
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        for (; t < n_tiles; ++t) {   // the chunk's last tile may hold no superblock for this warp
+            mbar_wait_a(full_a + stage * 8, phase);
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty_a + stage * 8);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        sb += NW;
-        if (++stage == NS) { stage = 0; phase ^= 1; }
+    } else {
+        // ---- QB queries share every pass; their tables are read from shared memory per pair ----
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            mbar_wait_a(full_a + stage * 8, phase);
+            if (t < n_left) {
+                const uint32_t src = slot + stage * Cfg::kTileBytes;
+                uint4 w[Cfg::kQuads];
+#pragma unroll
+                for (int q = 0; q < Cfg::kQuads; ++q) w[q] = lds128(src + q * 512);
+                int gb_next[QB];
+                if (stage == 0) {
+#pragma unroll
+                    for (int qi = 0; qi < QB; ++qi) gb_next[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(empty_a + stage * 8);   // the words are in registers: release the stage early
+#pragma unroll
+                for (int qi = 0; qi < QB; ++qi) {
+                    if (qi < nqb) {
+                        const uint32_t bound = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
+                        GroupAcc g;
+                        // (Early abandon — skipping the last sub-quantisers once every vector of the superblock
+                        // has reached the bound — is exact but was measured 5 % slower: the vote/branch splits
+                        // the unrolled lookup chain.)
+#pragma unroll
+                        for (int p = 0; p < M / 2; ++p) {   // pairs of sub-quantisers
+                            const uint4 t0 = qtab[qi * M + 2 * p], t1 = qtab[qi * M + 2 * p + 1];
+                            const uint4& wq = w[p >> 1];
+                            scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, t0, t1, g, pk, bound);
+                        }
+                        const bool mine = any_below(g);
+                        if (__any_sync(0xffffffffu, mine)) emit_group(g, mine, bound, qi, sb);   // rare
+                    }
+                }
+                if (stage == 0) {
+#pragma unroll
+                    for (int qi = 0; qi < QB; ++qi) gb[qi] = min(gb[qi], gb_next[qi]);
+                }
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(empty_a + stage * 8);
+            }
+            sb += NW;
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
     }
 
     // ---- final: one sorted list per (CTA, query) when the NW warp lists fit a CTA-wide sort in
