@@ -47,8 +47,8 @@ def codes_np(lo, hi):
         return mix64_np(np.arange(lo, hi, dtype=np.uint64)).view(np.uint8).reshape(-1, CODE_BYTES)
 
 
-def codes_torch(lo, hi, device):
-    """Same generator on the device (int64 arithmetic wraps like uint64)."""
+def codes_torch_at(idx):
+    """Same generator on the device for an int64 tensor of vector indices (int64 arithmetic wraps like uint64)."""
     import torch
 
     def c(v):  # uint64 constant as int64
@@ -57,11 +57,16 @@ def codes_torch(lo, hi, device):
     def lsr(x, s):  # logical shift right on int64
         return (x >> s) & ((1 << (64 - s)) - 1)
 
-    z = torch.arange(lo, hi, dtype=torch.int64, device=device) + c((0x9E3779B97F4A7C15 * SEED) & ((1 << 64) - 1))
+    z = idx + c((0x9E3779B97F4A7C15 * SEED) & ((1 << 64) - 1))
     z = (z ^ lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
     z = (z ^ lsr(z, 27)) * c(0x94D049BB133111EB)
     z = z ^ lsr(z, 31)
     return z.view(torch.uint8).view(-1, CODE_BYTES)
+
+
+def codes_torch(lo, hi, device):
+    import torch
+    return codes_torch_at(torch.arange(lo, hi, dtype=torch.int64, device=device))
 
 
 def make_quantizer_and_queries(nq):
@@ -128,21 +133,23 @@ def measured_peak_hbm():
 
 
 def ncu_traffic_per_launch(n_local, nq, qb):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch from the committed `ncu --set full`
-    capture (profiles/r01_scan_flat_16x4_1B_ncu_full.txt), which was taken on exactly the default workload
-    (1e9 local vectors, 16 queries per step, 1 query per pass); None for any other configuration."""
+    """(bytes, source): dram__bytes_read.sum + dram__bytes_write.sum of one scan launch.  NOT measured in this run (ncu
+    cannot run inside a timed bench): read from the committed `ncu --set full` capture of exactly the default workload
+    (1e9 local vectors, 16 queries per step, 1 query per pass); (None, None) for any other configuration."""
     if (n_local, nq, qb) != (10 ** 9, 16, 1):
-        return None
-    p = os.path.join(ROOT, "profiles", "r01_scan_flat_16x4_1B_ncu_full.txt")
-    try:
-        vals = {}
-        for line in open(p):
-            t = line.split()
-            if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                vals[t[0]] = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[t[2]]
-        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
-    except Exception:
-        return None
+        return None, None
+    for name in ("r02_scan_flat_16x4_1B_ncu_full.txt", "r01_scan_flat_16x4_1B_ncu_full.txt"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            vals = {}
+            for line in open(p):
+                t = line.split()
+                if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    vals[t[0]] = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[t[2]]
+            return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"], f"committed ncu capture profiles/{name} (same workload, not this run)"
+        except Exception:
+            continue
+    return None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -181,13 +188,21 @@ def run_reference(args):
     n_cpu = min(args.n_vectors, 1 << 25)
     nq = max(threads, 32) * 2
     res = cpu_reference_run(n_cpu, nq, threads, args.steps, args.warmup)
-    sample = (f"first {n_cpu} vectors of the same synthetic database, {nq} queries per step, OpenMP over queries "
-              f"around the reference's scanner_4::query_scan")
+    sample = (f"first {n_cpu} vectors of the same synthetic database ({n_cpu * CODE_BYTES >> 20} MiB of codes, larger than the "
+              f"host's last-level cache share per thread but far smaller than the 8 GB the GPU arm streams), {nq} queries "
+              f"per step, OpenMP over queries around the reference's scanner_4::query_scan; a step of the full "
+              f"{args.n_vectors}-vector workload would take {args.n_vectors / n_cpu:.0f}x longer at the same rate")
+    cfg = workload_config(args, nq, 1)
+    cfg.update(sampled_n_vectors=n_cpu, queries_per_step=nq, sharding="none (host cores)",
+               reference_build="unmodified sources, the reference's own flags (CMakeLists.txt:7) except -march=haswell "
+                               "instead of -march=native so that the library built in the CPU container runs on this host; "
+                               "the scan is explicit AVX2 intrinsics (simd_scan.hpp:125-187)",
+               l2="n/a (CPU)")
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "vectors/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-        "config": workload_config(args, nq, None),
+        "config": cfg,
         "cpu_baseline": {"value": res["value"], "unit": "vectors/s", "cores": threads, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": res["value"], "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -254,7 +269,8 @@ def run_ours(args):
     d_ids = torch.empty((nq, R), dtype=torch.int32, device=dev)
     d_d = torch.empty((nq, R), dtype=torch.int8, device=dev)
     d_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
-    d_keys = torch.empty((nq, R), dtype=torch.int64, device=dev)
+    d_keys = torch.empty((nq, R), dtype=torch.int64, device=dev)   # the only buffer exchanged: a flat id is the key's low 32 bits
+    g_keys = torch.empty((world, nq, R), dtype=torch.int64, device=dev) if world > 1 else None
     o_ids, o_d, o_cnt = torch.empty_like(d_ids), torch.empty_like(d_d), torch.empty_like(d_cnt)
     flush = None
     if n_local * CODE_BYTES <= 512e6:
@@ -267,8 +283,8 @@ def run_ours(args):
         ix.search_device(d_q.data_ptr(), nq, 1, R, d_ids.data_ptr(), d_d.data_ptr(), d_cnt.data_ptr(), d_keys.data_ptr())
         launches[0] += ix.last_launch_count()
         if world > 1:
-            gk, gi = sharding.all_gather_topk(d_keys, d_ids)
-            ix.merge_shards_device(gk.data_ptr(), gi.data_ptr(), world, nq, R, o_ids.data_ptr(), o_d.data_ptr(), o_cnt.data_ptr())
+            dist.all_gather_into_tensor(g_keys.view(world * nq, R), d_keys)   # ONE NCCL all-gather per step (nq*r*8 B per rank)
+            ix.merge_shards_device(g_keys.data_ptr(), None, world, nq, R, o_ids.data_ptr(), o_d.data_ptr(), o_cnt.data_ptr())
             launches[0] += 1
 
     # host-buffer leg (`e2e`): pinned queries in, pinned results out, copies inside the timed region
@@ -349,23 +365,67 @@ def run_ours(args):
     peak, peak_src = measured_peak_hbm()
 
     verify = None
-    if world == 1 and args.verify:
-        # full-size cross-check outside the timed region: the scan result of `--verify` queries must equal
-        # the canonical rule evaluated (numpy) on the per-vector distances of an independent kernel
-        res_ids = d_ids.cpu().numpy().view(np.uint32); res_d = d_d.cpu().numpy(); res_c = d_cnt.cpu().numpy()
+    if args.verify:
+        # full-size cross-check outside the timed region, on EVERY rank: the (merged) result of `--verify` queries
+        # must equal the canonical rule evaluated with numpy on the per-vector distances of an independent kernel
+        # (qadc_dump_distances over this rank's shard); with several GPUs the per-shard candidates are gathered and
+        # merged on the host, so the device-side all-gather + merge is what is being checked.
+        fin_ids, fin_d, fin_c = (o_ids, o_d, o_cnt) if world > 1 else (d_ids, d_d, d_cnt)
+        res_ids = fin_ids.cpu().numpy().view(np.uint32); res_d = fin_d.cpu().numpy(); res_c = fin_c.cpu().numpy()
         tabs = ix.build_tables(queries[:args.verify], 1, R)
+        cand = np.full((args.verify, R), np.iinfo(np.int64).max, np.int64)   # (distance << 32 | global position), ascending
+        for s_ in range(args.verify):
+            dd = ix.dump_distances(0, tabs["qtables"][s_, 0])
+            thr = res_d[s_][res_c[s_] - 1] if res_c[s_] == R else 126
+            pos = np.nonzero(dd <= thr)[0]
+            order = np.lexsort((pos, dd[pos]))[:R]
+            cand[s_, :len(order)] = (dd[pos[order]].astype(np.int64) << 32) | (pos[order].astype(np.int64) + lo)
+            del dd
+        if world > 1:
+            gc = sharding.all_gather_keys(torch.from_numpy(cand).to(dev)).cpu().numpy()   # [world, verify, R]
+        else:
+            gc = cand[None]
         okv = True
         for s_ in range(args.verify):
-            dist = ix.dump_distances(0, tabs["qtables"][s_, 0])
-            thr = res_d[s_][res_c[s_] - 1] if res_c[s_] == R else 126
-            pos = np.nonzero(dist <= thr)[0]
-            order = np.lexsort((pos, dist[pos]))[:R]
-            okv = okv and np.array_equal(res_ids[s_][:len(order)], pos[order].astype(np.uint32)) \
-                and np.array_equal(res_d[s_][:len(order)], dist[pos[order]])
-            del dist
-        verify = {"queries": args.verify, "method": "canonical top-r recomputed from qadc_dump_distances", "ok": bool(okv)}
+            k = np.sort(gc[:, s_].reshape(-1))[:R]
+            k = k[k != np.iinfo(np.int64).max]
+            n_ = len(k)
+            okv = okv and res_c[s_] == n_ and np.array_equal(res_ids[s_][:n_], (k & 0xffffffff).astype(np.uint32)) \
+                and np.array_equal(res_d[s_][:n_].astype(np.int64), k >> 32)
+        if world > 1:
+            t_ok = torch.tensor([1 if okv else 0], device=dev)
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            okv = bool(t_ok.item())
+        verify = {"queries": args.verify, "ok": bool(okv),
+                  "method": "canonical top-r recomputed from qadc_dump_distances (independent kernel) + numpy on every shard, "
+                            "gathered and merged on the host, compared with the device result on every rank"}
+
+    configs = None
+    if not args.no_configs:
+        from tools import bench_legs
+        sm_mhz = float((clocks or {}).get("sm_max_mhz") or 1965.0)
+        configs = {}
+        try:
+            if world == 1:
+                ix.close(); ix = None
+                torch.cuda.empty_cache()
+                configs["1"] = bench_legs.leg_flat(qadc_b200, torch, dev, stream, "1: SIFT1M-shaped flat PQ 16x4, 10k queries, top-100",
+                                                   10 ** 6, 128, 16, 0.01, 10000, (1, 2, 4), 1235, sm_mhz)
+                configs["2"] = bench_legs.leg_ivf(qadc_b200, torch, dev, stream, "2: SIFT1M-shaped IVF-4096 residual PQ 16x4, nprobe 64, 10k queries, top-100",
+                                                  10 ** 6, 128, 16, 4096, 64, 0.01, 10000, 1236)
+                configs["3"] = bench_legs.leg_flat(qadc_b200, torch, dev, stream, "3: Deep10M-shaped flat PQ 32x4 (96-d), batched 10k queries, top-100",
+                                                   10 ** 7, 96, 32, 0.001, 10000, (1, 2), 1237, sm_mhz, check=2)
+            else:
+                ix.close(); ix = None
+                torch.cuda.empty_cache()
+                n5 = 10 ** 9 if world == 8 else 125 * 10 ** 6 * world   # the full Deep1B shape on 8 GPUs, the same per-GPU share otherwise
+                configs["5"] = bench_legs.leg_config5_sharded(qadc_b200, torch, dist, sharding, codes_torch, codes_torch_at, dev, stream,
+                                                              rank, world, n5, 10000)
+        except Exception as e:   # an informational leg must never take the headline down
+            configs["error"] = repr(e)[:500]
 
     if rank == 0:
+        traffic, traffic_src = ncu_traffic_per_launch(n_local, nq, qb_used)
         value = N * nq / (ms_step * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "vectors/s", "n_gpus": world, "steps": args.steps,
@@ -380,9 +440,10 @@ def run_ours(args):
                 "queries_per_pass": 4, "value": N * nq / (ms_batched * 1e-3), "unit": "vectors/s", "ms_per_step": ms_batched,
                 "note": "informational: same step, 4 queries share each pass over the codes (integer-issue bound)"},
             "verify": verify,
+            "configs": configs,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_per_launch(n_local, nq, qb_used), "peak_source": peak_src, "kernel": "scan_flat_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "scan_flat_kernel",
                          "kernel_ms": t_scan * 1e3, "kernel_share_of_step": t_scan * 1e3 / ms_step,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": passes * n_local * CODE_BYTES},
@@ -400,7 +461,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ix.close()
+    if ix is not None:
+        ix.close()
 
 
 def main():
@@ -414,7 +476,8 @@ def main():
     ap.add_argument("--qb", type=int, default=1, help="queries per pass of the flat scan (0 = library default)")
     ap.add_argument("--flat-filter", type=int, default=None, help="0: exact lookup core only (A/B against the pre-filter)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--verify", type=int, default=2, help="queries cross-checked at full size after timing (N=1 only)")
+    ap.add_argument("--verify", type=int, default=2, help="queries cross-checked at full size after timing (every N)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the informational `configs` legs (BASELINE configs 1-3 / 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

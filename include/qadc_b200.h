@@ -108,6 +108,9 @@ int qadc_set_position_base(qadc_ctx* ctx, int part_i, uint32_t pos_base);
  * shards derive identical quantisation bounds.  Overrides the prefix finalize derives. */
 int qadc_set_prefix(qadc_ctx* ctx, int part_i, const uint8_t* codes, uint32_t count,
                     int on_device);
+/* Same for every partition at once: `codes` holds the prefixes back to back in partition order,
+ * counts[p] vectors each (0 = derive that partition's prefix from the uploaded codes). */
+int qadc_set_prefixes(qadc_ctx* ctx, const uint8_t* codes, const uint32_t* counts, int on_device);
 /* keep: fraction of each partition scanned in float to bound the quantiser,
  * starts_sizes[p] = max(1, (unsigned)(size * keep)) in float32 (db_query_4.cpp:125-126). */
 int qadc_finalize(qadc_ctx* ctx, float keep);

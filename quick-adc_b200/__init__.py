@@ -68,6 +68,7 @@ def load_library(build_if_missing=True):
     L.qadc_upload_partitions.argtypes = [vp, vp, vp]
     L.qadc_set_position_base.argtypes = [vp, i32, u32]
     L.qadc_set_prefix.argtypes = [vp, i32, vp, u32, i32]
+    L.qadc_set_prefixes.argtypes = [vp, vp, vp, i32]
     L.qadc_finalize.argtypes = [vp, f32]
     L.qadc_search.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.qadc_search_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
@@ -88,7 +89,7 @@ def load_library(build_if_missing=True):
     L.qadc_download_codes.argtypes = [vp, i32, vp]
     L.qadc_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.qadc_encode.argtypes = [vp, vp, u32, vp, vp]
-    for name in ("qadc_upload_database", "qadc_upload_partitions", "qadc_create", "qadc_set_pq", "qadc_set_coarse", "qadc_begin_database", "qadc_upload_codes",
+    for name in ("qadc_set_prefixes", "qadc_upload_database", "qadc_upload_partitions", "qadc_create", "qadc_set_pq", "qadc_set_coarse", "qadc_begin_database", "qadc_upload_codes",
                  "qadc_set_position_base", "qadc_set_prefix", "qadc_finalize", "qadc_search", "qadc_search_device",
                  "qadc_synchronize", "qadc_last_launch_count", "qadc_last_scan_ms", "qadc_merge_shards_device",
                  "qadc_build_tables", "qadc_scan_with_tables", "qadc_dump_distances", "qadc_download_codes",
@@ -182,6 +183,16 @@ class Index:
 
     def set_prefix_device(self, part_i, d_codes, count):
         self._ck(self.lib.qadc_set_prefix(self.h, part_i, _ptr(int(d_codes)), count, 1))
+
+    def set_prefixes_device(self, d_codes, counts):
+        """Explicit keep-prefixes of all partitions at once (device pointer, counts[p] vectors each)."""
+        c = np.ascontiguousarray(counts, np.uint32)
+        self._ck(self.lib.qadc_set_prefixes(self.h, _ptr(int(d_codes)), _ptr(c), 1))
+
+    def set_prefixes(self, codes, counts):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        c = np.ascontiguousarray(counts, np.uint32)
+        self._ck(self.lib.qadc_set_prefixes(self.h, _ptr(codes), _ptr(c), 0))
 
     def finalize(self, keep):
         self._ck(self.lib.qadc_finalize(self.h, np.float32(keep)))

@@ -53,7 +53,8 @@ struct qadc_ctx {
     bool has_labels = false, begun = false, finalized = false;
     std::vector<uint32_t> h_size, h_pos_base, h_start_size, h_explicit_count;
     std::vector<uint64_t> h_sb_off, h_label_off, h_start_off;
-    std::vector<uint8_t*> h_explicit_prefix;   // device pointers (owned) or null
+    std::vector<uint8_t*> h_explicit_prefix;   // device pointers (owned, or into d_prefix_block) or null
+    uint8_t* d_prefix_block = nullptr;         // qadc_set_prefixes: all explicit prefixes in one allocation
     uint64_t total_sb = 0, total_vec = 0;
     uint8_t* d_codes = nullptr;
     uint32_t* d_labels = nullptr;
@@ -123,7 +124,9 @@ void free_db(qadc_ctx* c) {
     cudaFree(c->d_codes); cudaFree(c->d_labels); cudaFree(c->d_sb_off); cudaFree(c->d_label_off);
     cudaFree(c->d_start_off); cudaFree(c->d_size); cudaFree(c->d_pos_base); cudaFree(c->d_start_size);
     cudaFree(c->d_starts);
-    for (auto p : c->h_explicit_prefix) cudaFree(p);
+    for (auto p : c->h_explicit_prefix)
+        if (p && !c->d_prefix_block) cudaFree(p);
+    cudaFree(c->d_prefix_block); c->d_prefix_block = nullptr;
     c->d_codes = nullptr; c->d_labels = nullptr; c->d_sb_off = c->d_label_off = c->d_start_off = nullptr;
     c->d_size = c->d_pos_base = c->d_start_size = nullptr; c->d_starts = nullptr;
     c->h_explicit_prefix.clear(); c->h_explicit_count.clear();
@@ -315,6 +318,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
     mg.in_keys = ctx->b_lists.as<uint64_t>(); mg.in_ids = nullptr; mg.L = n_lists; mg.r = r; mg.nq = nq;
     mg.shard_major = 0; mg.out_keys = d_keys; mg.out_ids = d_ids; mg.out_dists = d_dists; mg.out_counts = d_counts;
     mg.out_rth_value = nullptr;
+    mg.init_bound = ctx->b_sbound.as<int>();   // final shared bound: at least r scanned vectors are at or below it
     if (ctx->has_labels) {
         mg.labels = ctx->d_labels; mg.label_off = ctx->d_label_off; mg.part_pos_base = ctx->d_pos_base;
         mg.assign = d_assign; mg.ma = ma;
@@ -397,19 +401,18 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         QCK(cudaGetLastError());
     } else {
         int nsplit = 1;
-        if (flat) nsplit = static_cast<int>(std::min<uint32_t>(64, std::max<uint32_t>(1, ctx->max_start / 16384)));
+        if (flat) nsplit = static_cast<int>(std::min<uint32_t>(64, std::max<uint32_t>(1, ctx->max_start / 8192)));
         ENSURE(ctx->b_plists, static_cast<size_t>(nq) * nsplit * r * 8);
-        pa.nsplit = nsplit; pa.lists = ctx->b_plists.as<uint64_t>();
+        pa.nsplit = nsplit; pa.lists = ctx->b_plists.as<uint32_t>();
         dim3 pgrid(nsplit, nq);
         if (M == 16) prefix_scan_kernel<16><<<pgrid, kSelThreads, 0, ctx->stream>>>(pa);
         else prefix_scan_kernel<32><<<pgrid, kSelThreads, 0, ctx->stream>>>(pa);
         ctx->launches++;
         QCK(cudaGetLastError());
         if (nsplit > 1) {
-            MergeArgs mg{};
-            mg.in_keys = pa.lists; mg.L = nsplit; mg.r = r; mg.nq = nq; mg.out_rth_value = ctx->b_qmax.as<float>();
-            int rc = run_merge(ctx, mg);
-            if (rc) return rc;
+            prefix_select_kernel<<<nq, kSelThreads, 0, ctx->stream>>>(pa.lists, nsplit * r, r, ctx->b_qmax.as<float>());
+            ctx->launches++;
+            QCK(cudaGetLastError());
         }
     }
     // 5. bounds + int8 tables
@@ -719,12 +722,38 @@ int qadc_set_prefix(qadc_ctx* ctx, int part_i, const uint8_t* codes, uint32_t co
     if (part_i < 0 || part_i >= ctx->parts) return fail(ctx, QADC_EINVAL, "bad partition index");
     if (!codes || count == 0) return fail(ctx, QADC_EINVAL, "empty prefix");
     QCK(cudaSetDevice(ctx->device));
+    if (ctx->d_prefix_block) return fail(ctx, QADC_ESTATE, "prefixes were set in bulk (qadc_set_prefixes)");
     cudaFree(ctx->h_explicit_prefix[part_i]);
     ctx->h_explicit_prefix[part_i] = nullptr;
     const size_t bytes = static_cast<size_t>(count) * (ctx->m / 2);
     QCK(cudaMalloc(&ctx->h_explicit_prefix[part_i], bytes));
     QCK(cudaMemcpy(ctx->h_explicit_prefix[part_i], codes, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     ctx->h_explicit_count[part_i] = count;
+    ctx->finalized = false;
+    return QADC_OK;
+}
+
+int qadc_set_prefixes(qadc_ctx* ctx, const uint8_t* codes, const uint32_t* counts, int on_device) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "qadc_begin_database must be called first");
+    if (!codes || !counts) return fail(ctx, QADC_EINVAL, "null argument");
+    QCK(cudaSetDevice(ctx->device));
+    for (auto& p : ctx->h_explicit_prefix) {
+        if (p && !ctx->d_prefix_block) cudaFree(p);
+        p = nullptr;
+    }
+    cudaFree(ctx->d_prefix_block); ctx->d_prefix_block = nullptr;
+    const size_t CS = ctx->m / 2;
+    uint64_t total = 0;
+    for (int p = 0; p < ctx->parts; ++p) total += counts[p];
+    if (total == 0) return fail(ctx, QADC_EINVAL, "empty prefixes");
+    QCK(cudaMalloc(&ctx->d_prefix_block, total * CS));
+    QCK(cudaMemcpy(ctx->d_prefix_block, codes, total * CS, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    uint64_t at = 0;
+    for (int p = 0; p < ctx->parts; ++p) {
+        ctx->h_explicit_prefix[p] = counts[p] ? ctx->d_prefix_block + at * CS : nullptr;
+        ctx->h_explicit_count[p] = counts[p];
+        at += counts[p];
+    }
     ctx->finalized = false;
     return QADC_OK;
 }
@@ -770,10 +799,17 @@ int qadc_finalize(qadc_ctx* ctx, float keep) {
         extract_prefix_kernel<32><<<grid, 256, 0, ctx->stream>>>(ctx->d_codes, ctx->d_sb_off, ctx->d_start_size,
                                                                  ctx->d_start_off, d_flags, ctx->d_starts);
     QCK(cudaGetLastError());
-    for (int p = 0; p < P; ++p)
-        if (ctx->h_explicit_prefix[p])
-            QCK(cudaMemcpyAsync(ctx->d_starts + ctx->h_start_off[p] * CS, ctx->h_explicit_prefix[p],
-                                static_cast<size_t>(ctx->h_explicit_count[p]) * CS, cudaMemcpyDeviceToDevice, ctx->stream));
+    bool all_explicit = ctx->d_prefix_block != nullptr;
+    for (int p = 0; p < P && all_explicit; ++p) all_explicit = ctx->h_explicit_prefix[p] || ctx->h_start_size[p] == 0;
+    if (all_explicit) {
+        // set in bulk for every partition: the block has the layout of d_starts, one copy
+        QCK(cudaMemcpyAsync(ctx->d_starts, ctx->d_prefix_block, off * CS, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        for (int p = 0; p < P; ++p)
+            if (ctx->h_explicit_prefix[p])
+                QCK(cudaMemcpyAsync(ctx->d_starts + ctx->h_start_off[p] * CS, ctx->h_explicit_prefix[p],
+                                    static_cast<size_t>(ctx->h_explicit_count[p]) * CS, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     QCK(cudaStreamSynchronize(ctx->stream));
     ctx->finalized = true;
     return QADC_OK;

@@ -181,7 +181,7 @@ __device__ __forceinline__ uint32_t madd(uint32_t a, uint32_t b, const PipeK& k)
     return d;
 }
 #ifndef QADC_FILT_ADD
-#define QADC_FILT_ADD 0
+#define QADC_FILT_ADD 2   // measured on the 1e9 scan: 2 (one accumulator per pipe) 23.6 ms, 1 (IADD3 only) 23.8, 0 (IMAD only) 24.3
 #endif
 #ifndef QADC_FILT_HI16
 #define QADC_FILT_HI16 0   // 0: SHF (ALU pipe), 1: multiply-high by 65536 (FMA pipe), 2: 32x32->64 multiply, upper word

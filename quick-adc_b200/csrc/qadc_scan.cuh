@@ -738,13 +738,17 @@ __global__ void __launch_bounds__(256) prefix_hist_kernel(const PrefixBoundArgs 
         __syncwarp();
         const uint8_t* codes = a.starts + a.start_off[p] * CS;
         for (uint32_t v = v0 + vfirst; v < v1; v += vstep) {
-            const uint8_t* c = codes + static_cast<size_t>(v) * CS;
+            uint32_t w[CS / 4];   // one 8- / 16-byte load per vector instead of CS byte loads
+            if constexpr (CS == 8) {
+                const uint2 c = *reinterpret_cast<const uint2*>(codes + static_cast<size_t>(v) * CS);
+                w[0] = c.x; w[1] = c.y;
+            } else {
+                const uint4 c = *reinterpret_cast<const uint4*>(codes + static_cast<size_t>(v) * CS);
+                w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w;
+            }
             int sum = 0;
 #pragma unroll
-            for (int b = 0; b < CS; ++b) {
-                const uint32_t byte = c[b];
-                sum += tab[warp][(2 * b) * 16 + (byte & 15u)] + tab[warp][(2 * b + 1) * 16 + (byte >> 4)];
-            }
+            for (int j = 0; j < M; ++j) sum += tab[warp][j * 16 + ((w[j >> 3] >> (4 * (j & 7))) & 15u)];
             atomicAdd(&hist[min(sum, 127)], 1u);
         }
     }
@@ -814,7 +818,8 @@ struct MergeArgs {
     uint32_t* out_ids;
     int8_t* out_dists;
     int32_t* out_counts;
-    float* out_rth_value;      // [nq]: float bits of the r-th key >> 32 (prefix qmax), FLT_MAX if < r keys
+    float* out_rth_value;      // [nq]: float bits of the r-th key >> 32, FLT_MAX if < r keys
+    const int* init_bound;     // [nq] or null: only keys with distance <= init_bound[q] can be in the result (the scan's shared bound)
     // label resolution
     const uint32_t* labels;
     const uint64_t* label_off;       // [K]
@@ -833,7 +838,10 @@ __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(const MergeA
     __shared__ unsigned long long bound_key;
     const int q = blockIdx.x, tid = threadIdx.x;
     for (int i = tid; i < kMergeCap; i += kMergeThreads) { keys[i] = kEmptyKey; vals[i] = 0; }
-    if (tid == 0) { count = 0; bound_key = kEmptyKey; }
+    if (tid == 0) {
+        count = 0;
+        bound_key = a.init_bound ? (static_cast<unsigned long long>(a.init_bound[q] + 1) << 48) : kEmptyKey;
+    }
     __syncthreads();
     const int total = a.L * a.r;
     const int step = kMergeCap / 2;   // inputs per round; buffer holds <= r <= cap/2 before a round

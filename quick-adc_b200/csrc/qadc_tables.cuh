@@ -47,6 +47,95 @@ struct BlockTopK {
     }
 };
 
+// Block-wide exact selection without sorting: the k-th smallest (1-based, k <= n) of n uint32 keys (shared or
+// global memory), found with four 8-bit histogram passes from the most significant byte (kSelThreads = 256
+// threads = 256 bins).  Returns the key; n_less = how many keys are strictly smaller.  Used where only
+// the VALUE of the r-th smallest matters (the keep-prefix bound qmax): a bitonic sort of the 2048-key buffer cost
+// 6 600 instructions per thread, this costs a few hundred.
+__device__ __forceinline__ uint32_t block_radix_select(const uint32_t* vals, int n, int k, int* hist, int* state, int tid,
+                                                       int& n_less) {
+    uint32_t prefix = 0;
+    int kk = k;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += kSelThreads) {
+            const uint32_t v = vals[i];
+            if (shift == 24 || (v >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(v >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {   // warp 0: lane l owns bins 8l .. 8l+7
+            int c[8], mine = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = hist[tid * 8 + i]; mine += c[i]; }
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += up;
+            }
+            const unsigned reached = __ballot_sync(0xffffffffu, incl >= kk);
+            const int src = __ffs(reached) - 1;   // reached != 0 because kk <= keys matching the prefix
+            if (tid == src) {
+                int cum = incl - mine, b = 0;
+                while (cum + c[b] < kk) { cum += c[b]; ++b; }
+                state[0] = tid * 8 + b;
+                state[1] = kk - cum;
+            }
+        }
+        __syncthreads();
+        prefix |= static_cast<uint32_t>(state[0]) << shift;
+        kk = state[1];
+        __syncthreads();
+    }
+    n_less = k - kk;
+    return prefix;
+}
+
+// Streaming "r smallest float values" over a shared buffer of 2048 value slots (ping-pong halves of kSelCap),
+// compacted with block_radix_select: only the multiset of values matters (ties are interchangeable).
+struct BlockMinValues {
+    uint32_t* buf[2];       // kSelCap/2 ... each kSelCap uint32
+    int* count;             // entries in buf[cur]
+    int* hist;              // 256
+    int* state;             // 2
+    unsigned int* bound;    // pass iff bits < *bound
+    int cur;
+    __device__ __forceinline__ void init(int tid) {
+        if (tid == 0) { *count = 0; *bound = 0xffffffffu; }
+        cur = 0;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void push(uint32_t bits) {
+        if (bits < *bound) buf[cur][atomicAdd(count, 1)] = bits;
+    }
+    // call after every round of <= kSelCap/2 pushes (all threads); force = last round
+    __device__ __forceinline__ void maybe_compact(int r, int tid, bool force) {
+        __syncthreads();
+        const int c = *count;
+        __syncthreads();
+        if ((c > kSelCap / 2 || force) && c >= r) {
+            int n_less;
+            const uint32_t b = block_radix_select(buf[cur], c, r, hist, state, tid, n_less);
+            __syncthreads();
+            if (tid == 0) *count = 0;
+            __syncthreads();
+            uint32_t* dst = buf[cur ^ 1];
+            for (int i = tid; i < c; i += kSelThreads) {
+                const uint32_t v = buf[cur][i];
+                if (v < b) dst[atomicAdd(count, 1)] = v;
+            }
+            __syncthreads();
+            for (int i = n_less + tid; i < r; i += kSelThreads) dst[i] = b;   // the r-th value and its ties
+            __syncthreads();
+            if (tid == 0) { *count = r; *bound = b; }
+            cur ^= 1;
+            __syncthreads();
+        }
+    }
+};
+
 // ---- coarse assignment ------------------------------------------------------------------------
 // d(q,c) = sum_i fma(diff_i, diff_i, .) sequentially over the dimension (the FIXED statement of
 // find_k_neighbors, neighbors.cpp:30-76 with the :64 stride bug removed); the ma smallest under
@@ -289,21 +378,20 @@ struct PrefixArgs {
     const int32_t* assign;          // [nq][ma]
     const float* tables;            // [nq][ma][M*16]
     int ma, r, M, nsplit;
-    uint64_t* lists;                // [nq][nsplit][r]
+    uint32_t* lists;                // [nq][nsplit][r] float bits, FLT_MAX-padded (nsplit > 1)
     float* qmax;                    // [nq], written directly when nsplit == 1
 };
 
 template <int M>
 __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixArgs a) {
     constexpr int CS = M / 2;
-    __shared__ uint64_t keys[kSelCap];
+    __shared__ uint32_t vbuf[2][kSelCap];
     __shared__ float tab[M * 16];
-    __shared__ int count;
-    __shared__ unsigned long long bound_key;
+    __shared__ int count, hist[256], state[2];
+    __shared__ unsigned int bound;
     const int split = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
-    BlockTopK top{keys, &count, &bound_key};
+    BlockMinValues top{{vbuf[0], vbuf[1]}, &count, hist, state, &bound, 0};
     top.init(tid);
-    uint32_t running = 0;
     for (int ar = 0; ar < a.ma; ++ar) {
         const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
         const uint32_t n = a.start_size[p];
@@ -328,18 +416,32 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixAr
                 float s = 0.f;
 #pragma unroll
                 for (int j = 0; j < M; ++j) s = __fadd_rn(s, tab[j * 16 + ((w[j >> 3] >> (4 * (j & 7))) & 15u)]);
-                top.push((static_cast<uint64_t>(__float_as_uint(s)) << 32) | (running + (v - v0)));
+                top.push(__float_as_uint(s));   // sums of non-negative entries: the bit patterns order like the values
             }
             top.maybe_compact(a.r, tid, false);
         }
-        running += v1 - v0;
     }
     top.maybe_compact(a.r, tid, true);
-    uint64_t* dst = a.lists + (static_cast<size_t>(q) * a.nsplit + split) * a.r;
-    for (int i = tid; i < a.r; i += kSelThreads) dst[i] = keys[i];
-    // a single split needs no merge: the r-th key is qmax (FLT_MAX when the prefix is too short)
-    if (a.nsplit == 1 && tid == 0)
-        a.qmax[q] = (count == a.r) ? __uint_as_float(static_cast<uint32_t>(keys[a.r - 1] >> 32)) : 3.402823466e+38f;
+    // r smallest values of this split (FLT_MAX-padded); a single split needs no merge: the r-th value is qmax
+    // (FLT_MAX when the prefix is too short)
+    const int c = count;
+    const uint32_t* res = top.buf[top.cur];
+    if (a.nsplit == 1) {
+        if (tid == 0) a.qmax[q] = (c >= a.r) ? __uint_as_float(bound) : 3.402823466e+38f;
+    } else {
+        uint32_t* dst = a.lists + (static_cast<size_t>(q) * a.nsplit + split) * a.r;
+        for (int i = tid; i < a.r; i += kSelThreads) dst[i] = (i < c) ? res[i] : 0x7f7fffffu;
+    }
+}
+
+// The r-th smallest of the nsplit * r values the splits of one query left (grid = queries) -> qmax.
+__global__ void __launch_bounds__(kSelThreads) prefix_select_kernel(const uint32_t* __restrict__ lists, int n_per_query, int r,
+                                                                   float* __restrict__ qmax) {
+    __shared__ int hist[256], state[2];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    int n_less;
+    const uint32_t b = block_radix_select(lists + static_cast<size_t>(q) * n_per_query, n_per_query, r, hist, state, tid, n_less);
+    if (tid == 0) qmax[q] = __uint_as_float(b);   // FLT_MAX (the padding) when fewer than r prefix vectors exist
 }
 
 // Short prefixes (inverted lists): one warp per probe, lanes over the few prefix vectors; the

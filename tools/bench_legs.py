@@ -1,0 +1,313 @@
+"""The bench line's informational `configs` object: BASELINE.json configs 1, 2, 3 on one B200 and config 5
+(inverted lists sharded over the GPUs) on N > 1, each measured OUTSIDE the headline timed region with CUDA
+events on the launching stream, with a spot check of a few queries against the canonical rule evaluated by
+numpy on per-vector distances of an independent kernel (qadc_dump_distances).  Oracle / reference parity of
+the same shapes is the job of tests/test_gpu_baseline_shapes.py; nothing here touches oracle/.
+
+Also usable on its own:  python tools/bench_legs.py [1] [2] [3]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+R = 100
+SM_COUNT, ALU_LANES_PER_CLK = 148, 64          # B200: ALU pipe (PRMT/SHF/LOP3) = 16 lanes x 4 sub-partitions per SM
+
+
+def alu_ceiling_pairs_per_s(m, sm_mhz):
+    """Integer-pipe roofline of the lookup core: per (vector, query) pair m/2 PRMT + m/4 SHF + m/8 XOR on the ALU
+    pipe, 64 lanes per clock per SM."""
+    ops = m / 2 + m / 4 + m / 8
+    return SM_COUNT * ALU_LANES_PER_CLK * sm_mhz * 1e6 / ops
+
+
+def spot_check(ix, offsets, labels, queries, ma, ids, d, cnt):
+    """Canonical rule (d, probe rank, position) over d < 127, evaluated by numpy on dumped distances."""
+    tabs = ix.build_tables(queries, ma, R)
+    ok = True
+    for s in range(queries.shape[0]):
+        dist, rank, pos = [], [], []
+        for a, p in enumerate(tabs["assign"][s]):
+            if offsets[p + 1] == offsets[p]:
+                continue
+            dd = ix.dump_distances(int(p), tabs["qtables"][s, a])
+            keep = np.nonzero(dd < 127)[0]
+            dist.append(dd[keep]); rank.append(np.full(len(keep), a)); pos.append(keep + offsets[p])
+        dist, rank, pos = (np.concatenate(x) if x else np.zeros(0, np.int64) for x in (dist, rank, pos))
+        order = np.lexsort((pos, rank, dist))[:R]
+        e_ids = (labels[pos[order]] if labels is not None else pos[order]).astype(np.uint32)
+        n = len(order)
+        ok = ok and cnt[s] == n and np.array_equal(ids[s][:n], e_ids) and np.array_equal(d[s][:n], dist[order])
+    return bool(ok)
+
+
+def time_search(torch, ix, stream, dev, queries, ma, reps=3, flush=None):
+    """Device-resident batch (CUDA events on the stream) and the same through qadc_search with host buffers."""
+    nq = queries.shape[0]
+    d_q = torch.from_numpy(queries).to(dev)
+    d_ids = torch.empty((nq, R), dtype=torch.int32, device=dev)
+    d_d = torch.empty((nq, R), dtype=torch.int8, device=dev)
+    d_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    ix.set_option("time_scan", 1)
+
+    def once():
+        ix.search_device(d_q.data_ptr(), nq, ma, R, d_ids.data_ptr(), d_d.data_ptr(), d_cnt.data_ptr())
+
+    once(); ix.synchronize()
+    best, scan_ms = None, None
+    for _ in range(reps):
+        if flush is not None:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); once(); e1.record(stream)
+        ix.synchronize()
+        ms = e0.elapsed_time(e1)
+        if best is None or ms < best:
+            best = ms
+            n_sub = -(-nq // 32768)                       # the library splits a call into sub-batches of 32768 queries
+            scan_ms = float(sum(ix.scan_ms_history(n_sub)))
+    launches = ix.last_launch_count()
+    ids, d, cnt, met = ix.search(queries, ma, R, want_metrics=True)
+    t_e2e = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        ids, d, cnt, met = ix.search(queries, ma, R, want_metrics=True)
+        dt = time.perf_counter() - t0
+        t_e2e = dt if t_e2e is None else min(t_e2e, dt)
+    stages = {n: round(float(getattr(met, n)) / 1e3, 4) for n, _ in met._fields_}   # ms
+    return dict(ms=best, scan_kernel_ms=scan_ms, e2e_ms=t_e2e * 1e3, launches=launches, stage_ms=stages), (ids, d, cnt)
+
+
+def leg_flat(qadc, torch, dev, stream, name, n, dim, m, keep, nq, qbs, seed, sm_mhz, check=4):
+    rng = np.random.default_rng(seed)
+    cb = rng.standard_normal((m, 16, dim // m)).astype(np.float32)
+    codes = rng.integers(0, 256, (n, m // 2), dtype=np.uint8)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    ix = qadc.Index(dev.index, stream.cuda_stream)
+    ix.set_pq(dim, m, cb)
+    ix.load_flat(codes, keep)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    offsets = np.array([0, n], np.int64)
+    out = dict(config=name, n_vectors=n, dim=dim, m=m, keep=keep, queries=nq, r=R,
+               l2="database resident in the 126 MB L2 after the first pass" if n * m // 2 < 100e6 else
+                  "database larger than L2: every pass streams it from HBM",
+               bound="integer ALU pipe (PRMT/SHF/LOP3): 10 000 queries share the database, so HBM traffic per pair is ~0",
+               variants=[])
+    best = None
+    for qb in qbs:
+        ix.set_option("flat_qb", qb)
+        t, (ids, d, cnt) = time_search(torch, ix, stream, dev, q, 1, flush=flush)
+        sel = np.linspace(0, nq - 1, check).astype(int)
+        t["spot_check_ok"] = spot_check(ix, offsets, None, q[sel], 1, ids[sel], d[sel], cnt[sel])
+        t["queries_per_pass"] = qb
+        t["pairs_per_s"] = n * nq / (t["ms"] * 1e-3)
+        t["queries_per_s"] = nq / (t["ms"] * 1e-3)
+        t["scan_pairs_per_s"] = n * nq / (t["scan_kernel_ms"] * 1e-3)
+        out["variants"].append(t)
+        if best is None or t["ms"] < best["ms"]:
+            best = t
+    ceil = alu_ceiling_pairs_per_s(m, sm_mhz)
+    out.update(value=best["pairs_per_s"], unit="vector-query pairs/s", queries_per_s=best["queries_per_s"], ms=best["ms"],
+               e2e_ms=best["e2e_ms"], queries_per_pass=best["queries_per_pass"], dominant_kernel="scan_flat_kernel",
+               kernel_share_of_batch=best["scan_kernel_ms"] / best["ms"],
+               roofline=dict(bound="alu", achieved=best["scan_pairs_per_s"], peak=ceil, unit="pairs/s",
+                             frac=best["scan_pairs_per_s"] / ceil,
+                             note=f"peak = {SM_COUNT} SMs x {ALU_LANES_PER_CLK} ALU lanes x {sm_mhz:.0f} MHz / "
+                                  f"{m / 2 + m / 4 + m / 8:g} ALU-pipe ops per pair"),
+               spot_check_ok=all(v["spot_check_ok"] for v in out["variants"]))
+    ix.close()
+    del flush
+    return out
+
+
+def leg_ivf(qadc, torch, dev, stream, name, n, dim, m, K, ma, keep, nq, seed, check=4):
+    rng = np.random.default_rng(seed)
+    cb = rng.standard_normal((m, 16, dim // m)).astype(np.float32)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    sizes = rng.multinomial(n, np.ones(K) / K)
+    offsets = np.zeros(K + 1, np.int64); offsets[1:] = np.cumsum(sizes)
+    labels = rng.permutation(n).astype(np.uint32)
+    codes = rng.integers(0, 256, (n, m // 2), dtype=np.uint8)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    ix = qadc.Index(dev.index, stream.cuda_stream)
+    ix.set_pq(dim, m, cb); ix.set_coarse(cents)
+    t0 = time.perf_counter()
+    ix.load_ivf(codes, labels, offsets, keep)
+    load_s = time.perf_counter() - t0
+    t, (ids, d, cnt) = time_search(torch, ix, stream, dev, q, ma)
+    sel = np.linspace(0, nq - 1, check).astype(int)
+    ok = spot_check(ix, offsets, labels, q[sel], ma, ids[sel], d[sel], cnt[sel])
+    scanned = float(ma) * n / K
+    out = dict(config=name, n_vectors=n, dim=dim, m=m, K=K, nprobe=ma, keep=keep, queries=nq, r=R,
+               value=scanned * nq / (t["ms"] * 1e-3), unit="vectors scanned/s", queries_per_s=nq / (t["ms"] * 1e-3),
+               ms=t["ms"], e2e_ms=t["e2e_ms"], scan_kernel_ms=t["scan_kernel_ms"], stage_ms=t["stage_ms"],
+               launches=t["launches"], dominant_kernel="scan_ivf_kernel", kernel_share_of_batch=t["scan_kernel_ms"] / t["ms"],
+               bound="per-(query, probe) int8 tables (256 B) against ~%d B of codes per list: table pipeline + "
+                     "list scan, integer issue" % int(scanned / ma * m / 2),
+               load_seconds=load_s, spot_check_ok=ok)
+    ix.close()
+    return out
+
+
+def leg_config5_sharded(qadc, torch, dist, sharding, codes_torch, codes_torch_at, dev, stream, rank, world, n_total, nq, steps=3, check=4):
+    """BASELINE config 5: Deep1B-shaped IVF-65536, 96-d, PQ 16x4 (sq_dim 6), nprobe 128.  Lists are dealt to the
+    GPUs in contiguous runs of K/world lists (their sizes are multinomial, so the shards are balanced to < 1 %),
+    every shard holds a replica of all keep-prefixes, the coarse cells are split over the ranks (one all-gather of
+    nq x nprobe keys), the per-shard top-r lists are merged after one more all-gather.  List p owns the global
+    vector indices [offsets[p], offsets[p+1]) and labels are the global indices."""
+    DIM, M, K, MA, KEEP = 96, 16, 65536, 128, 0.0005
+    rng = np.random.default_rng(77)
+    cb = rng.standard_normal((M, 16, DIM // M)).astype(np.float32)
+    cents = (2 * rng.standard_normal((K, DIM))).astype(np.float32)
+    queries = rng.standard_normal((nq, DIM)).astype(np.float32)
+    sizes = rng.multinomial(n_total, np.ones(K) / K).astype(np.int64)
+    offsets = np.zeros(K + 1, np.int64); offsets[1:] = np.cumsum(sizes)
+    p_lo, p_cnt = sharding.coarse_range(K, rank, world)          # same contiguous split for lists and coarse cells
+    p_hi = p_lo + p_cnt
+    v_lo, v_hi = int(offsets[p_lo]), int(offsets[p_hi])
+    t0 = time.perf_counter()
+    ix = qadc.Index(dev.index, stream.cuda_stream)
+    ix.set_pq(DIM, M, cb); ix.set_coarse(cents)
+    local_sizes = np.zeros(K, np.uint32); local_sizes[p_lo:p_hi] = sizes[p_lo:p_hi]
+    ix.begin_database(local_sizes, True)
+    codes = codes_torch(v_lo, v_hi, dev)
+    labels = torch.arange(v_lo, v_hi, dtype=torch.int64, device=dev).to(torch.int32)
+    stream.synchronize()
+    ix.upload_database_device(codes.data_ptr(), labels.data_ptr())
+    del codes, labels
+    if world > 1:
+        # replicated keep-prefixes: the first start_size(size) codes of EVERY list, gathered on the device
+        starts = np.array([sharding.start_size(int(s), KEEP) for s in sizes], np.int64)
+        idx = np.concatenate([np.arange(offsets[p], offsets[p] + starts[p]) for p in range(K)]) if K else np.zeros(0, np.int64)
+        # the prefix codes from their global indices (the generator is a pure function of the index)
+        pre = codes_torch_at(torch.from_numpy(idx).to(dev))
+        stream.synchronize()
+        ix.set_prefixes_device(pre.data_ptr(), starts.astype(np.uint32))
+        del pre
+    ix.finalize(KEEP)
+    build_s = time.perf_counter() - t0
+
+    d_q = torch.from_numpy(queries).to(dev)
+    d_ids = torch.empty((nq, R), dtype=torch.int32, device=dev); d_d = torch.empty((nq, R), dtype=torch.int8, device=dev)
+    d_cnt = torch.empty(nq, dtype=torch.int32, device=dev); d_keys = torch.empty((nq, R), dtype=torch.int64, device=dev)
+    o_ids, o_d, o_cnt = torch.empty_like(d_ids), torch.empty_like(d_d), torch.empty_like(d_cnt)
+    d_assign = torch.empty((nq, MA), dtype=torch.int32, device=dev)
+    d_part = torch.empty((nq, MA), dtype=torch.int64, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def step(record=False):
+        if record: ev[0].record(stream)
+        if world > 1:
+            sharding.sharded_coarse_assign(ix, d_q, nq, MA, K, rank, world, d_part, d_assign)
+            if record: ev[1].record(stream)
+            ix.search_assigned_device(d_q.data_ptr(), d_assign.data_ptr(), nq, MA, R, d_ids.data_ptr(), d_d.data_ptr(),
+                                      d_cnt.data_ptr(), d_keys.data_ptr())
+            if record: ev[2].record(stream)
+            gk, gi = sharding.all_gather_topk(d_keys, d_ids)
+            if record: ev[3].record(stream)
+            ix.merge_shards_device(gk.data_ptr(), gi.data_ptr(), world, nq, R, o_ids.data_ptr(), o_d.data_ptr(), o_cnt.data_ptr())
+        else:
+            if record: ev[1].record(stream)
+            ix.search_device(d_q.data_ptr(), nq, MA, R, o_ids.data_ptr(), o_d.data_ptr(), o_cnt.data_ptr(), d_keys.data_ptr())
+            if record: ev[2].record(stream); ev[3].record(stream)
+        if record: ev[4].record(stream)
+
+    for _ in range(2):
+        step()
+    ix.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    step(record=True)
+    torch.cuda.synchronize(dev)
+    stage = dict(coarse_assign_incl_allgather=ev[0].elapsed_time(ev[1]), tables_and_list_scan=ev[1].elapsed_time(ev[2]),
+                 topk_allgather=ev[2].elapsed_time(ev[3]), shard_merge=ev[3].elapsed_time(ev[4]))
+    if world > 1:
+        t = torch.tensor([ms] + list(stage.values()), device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        vals = [float(x) for x in t.tolist()]
+        ms, stage = vals[0], dict(zip(stage.keys(), vals[1:]))
+    # verification on every rank: per-vector distances of this shard's probed lists for a few queries (independent
+    # kernel), canonical local top-r with numpy, gathered and merged on the host == the device result
+    sel = np.linspace(0, nq - 1, check).astype(int)
+    res_ids = o_ids.cpu().numpy().view(np.uint32)[sel]; res_d = o_d.cpu().numpy()[sel]; res_c = o_cnt.cpu().numpy()[sel]
+    assign_full = None
+    if world > 1:
+        assign_full = d_assign.cpu().numpy()[sel]
+    tabs = ix.build_tables(queries[sel], MA, R, assign_in=assign_full)
+    keys_local = np.full((check, R), np.iinfo(np.int64).max, np.int64)
+    ids_local = np.zeros((check, R), np.int64)
+    for s in range(check):
+        dist_l, rank_l, pos_l, id_l = [], [], [], []
+        for a_i, p in enumerate(tabs["assign"][s]):
+            if not (p_lo <= p < p_hi) or sizes[p] == 0:
+                continue
+            dd = ix.dump_distances(int(p), tabs["qtables"][s, a_i])
+            keep = np.nonzero(dd < 127)[0]
+            dist_l.append(dd[keep].astype(np.int64)); rank_l.append(np.full(len(keep), a_i, np.int64)); pos_l.append(keep.astype(np.int64))
+            id_l.append(keep.astype(np.int64) + offsets[p])
+        if dist_l:
+            dd, rr, pp, ii = (np.concatenate(x) for x in (dist_l, rank_l, pos_l, id_l))
+            k = (dd << 48) | (rr << 32) | pp
+            order = np.argsort(k, kind="stable")[:R]
+            keys_local[s, :len(order)] = k[order]; ids_local[s, :len(order)] = ii[order]
+    kl = torch.from_numpy(keys_local).to(dev); il = torch.from_numpy(ids_local).to(dev)
+    if world > 1:
+        gk = sharding.all_gather_keys(kl).cpu().numpy(); gi = sharding.all_gather_keys(il).cpu().numpy()
+    else:
+        gk, gi = keys_local[None], ids_local[None]
+    ok = True
+    for s in range(check):
+        k = gk[:, s].reshape(-1); i = gi[:, s].reshape(-1)
+        order = np.argsort(k, kind="stable")[:R]
+        real = k[order] != np.iinfo(np.int64).max
+        n = int(real.sum())
+        ok = ok and res_c[s] == n and np.array_equal(res_ids[s][:n], i[order][:n].astype(np.uint32)) \
+            and np.array_equal(res_d[s][:n].astype(np.int64), k[order][:n] >> 48)
+    if world > 1:
+        t = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MIN); ok = bool(t.item())
+    scanned = float(MA) * n_total / K
+    out = dict(config="5: Deep1B-shaped IVF-65536 PQ 16x4 (96-d), nprobe 128, inverted lists sharded over the GPUs",
+               n_vectors=n_total, n_gpus=world, queries=nq, r=R, keep=KEEP, ms=ms, queries_per_s=nq / (ms * 1e-3),
+               value=scanned * nq / (ms * 1e-3), unit="vectors scanned/s (all GPUs)", stage_ms=stage,
+               build_seconds=build_s, verify=dict(queries=check, ok=ok,
+                                                  method="per-shard canonical top-r from qadc_dump_distances + numpy, gathered, merged on the host"))
+    ix.close()
+    return out
+
+
+def main():
+    import torch
+    import qadc_b200
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    which = sys.argv[1:] or ["1", "2", "3"]
+    for w in which:
+        if w == "1":
+            r = leg_flat(qadc_b200, torch, dev, stream, "1: SIFT1M-shaped flat PQ 16x4, 10k queries", 10 ** 6, 128, 16, 0.01, 10000, (1, 2, 4), 1235, 1965.0)
+        elif w == "2":
+            r = leg_ivf(qadc_b200, torch, dev, stream, "2: SIFT1M-shaped IVF-4096 PQ 16x4, nprobe 64, 10k queries", 10 ** 6, 128, 16, 4096, 64, 0.01, 10000, 1236)
+        elif w == "3":
+            r = leg_flat(qadc_b200, torch, dev, stream, "3: Deep10M-shaped flat PQ 32x4, 10k queries", 10 ** 7, 96, 32, 0.001, 10000, (1, 2), 1237, 1965.0, check=2)
+        else:
+            continue
+        print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()
