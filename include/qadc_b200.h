@@ -162,6 +162,31 @@ int qadc_merge_shards_device(qadc_ctx* ctx, const uint64_t* d_keys, const uint32
                              int G, int nq, int r, uint32_t* d_out_ids, int8_t* d_out_dists,
                              int32_t* d_out_counts, uint64_t* d_out_keys);
 
+/* ---- one database over several GPUs of one box, one host process ----------------- */
+/* The reference scans with one thread on one CPU (query_common.hpp:351-365); this is what replaces it when
+ * the database is sharded: a qadc_multi owns one context per listed device, shards the database itself
+ * (flat: contiguous runs of 256-vector blocks; inverted lists: whole lists, longest first; the keep-prefixes
+ * replicated on every shard), and per query batch exchanges the per-shard coarse candidates (inverted lists)
+ * and the per-shard top-r lists with NCCL all-gathers over NVLink before merging them on the first device.
+ * Results are bit-identical to the single-GPU ones.  A device ordinal listed more than once = several virtual
+ * shards on one GPU (NCCL rejects that; the gather is then done with same-device copies) — for tests. */
+typedef struct qadc_multi qadc_multi;
+int qadc_multi_create(const int* devices, int n, qadc_multi** out);
+void qadc_multi_destroy(qadc_multi* m);
+const char* qadc_multi_last_error(const qadc_multi* m);   /* m == NULL: last qadc_multi_create failure */
+int qadc_multi_device_count(const qadc_multi* m);
+int qadc_multi_uses_nccl(const qadc_multi* m);
+qadc_ctx* qadc_multi_context(qadc_multi* m, int g);        /* shard g's context (options, parity entry points) */
+int qadc_multi_set_pq(qadc_multi* m, int dim, int mm, int bits, const float* codebooks, const float* rotation);
+int qadc_multi_set_coarse(qadc_multi* m, int K, const float* centroids);
+/* scanner_4::prepare_database (db_query_4.cpp:98-228) for all shards: sizes[p], part_codes[p] (row-major) and
+ * part_labels[p] (inverted lists; NULL for a flat database) as base_db::get_partition hands them out. */
+int qadc_multi_load(qadc_multi* m, int partition_count, const uint32_t* sizes, const uint8_t* const* part_codes,
+                    const uint32_t* const* part_labels, float keep);
+/* = qadc_search over the sharded database (host buffers in and out). */
+int qadc_multi_search(qadc_multi* m, const float* queries, int nq, int ma, int r, uint32_t* out_ids, int8_t* out_dists,
+                      int32_t* out_counts, qadc_metrics* metrics);
+
 /* ---- parity entry points (host buffers) ------------------------------------------------ */
 /* Stage T: assignment, float tables, bounds and int8 tables for a batch.  assign_in
  * (nq*ma, optional) injects a coarse assignment instead of computing it.  Any output may

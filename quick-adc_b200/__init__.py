@@ -89,6 +89,22 @@ def load_library(build_if_missing=True):
     L.qadc_download_codes.argtypes = [vp, i32, vp]
     L.qadc_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.qadc_encode.argtypes = [vp, vp, u32, vp, vp]
+    L.qadc_multi_create.argtypes = [vp, i32, C.POINTER(vp)]
+    L.qadc_multi_destroy.argtypes = [vp]
+    L.qadc_multi_destroy.restype = None
+    L.qadc_multi_last_error.argtypes = [vp]
+    L.qadc_multi_last_error.restype = C.c_char_p
+    L.qadc_multi_device_count.argtypes = [vp]
+    L.qadc_multi_uses_nccl.argtypes = [vp]
+    L.qadc_multi_context.argtypes = [vp, i32]
+    L.qadc_multi_context.restype = vp
+    L.qadc_multi_set_pq.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.qadc_multi_set_coarse.argtypes = [vp, i32, vp]
+    L.qadc_multi_load.argtypes = [vp, i32, vp, vp, vp, f32]
+    L.qadc_multi_search.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    for name in ("qadc_multi_create", "qadc_multi_device_count", "qadc_multi_uses_nccl", "qadc_multi_set_pq",
+                 "qadc_multi_set_coarse", "qadc_multi_load", "qadc_multi_search"):
+        getattr(L, name).restype = i32
     for name in ("qadc_set_prefixes", "qadc_upload_database", "qadc_upload_partitions", "qadc_create", "qadc_set_pq", "qadc_set_coarse", "qadc_begin_database", "qadc_upload_codes",
                  "qadc_set_position_base", "qadc_set_prefix", "qadc_finalize", "qadc_search", "qadc_search_device",
                  "qadc_synchronize", "qadc_last_launch_count", "qadc_last_scan_ms", "qadc_merge_shards_device",
@@ -336,3 +352,82 @@ class Index:
         out = np.empty((int(self.sizes[part_i]), self.m // 2), np.uint8)
         self._ck(self.lib.qadc_download_codes(self.h, part_i, _ptr(out)))
         return out
+
+
+class MultiIndex:
+    """One database sharded over several GPUs by ONE process (qadc_multi_*): what the db_query_4 CLI uses for
+    `-g 0,1,...`.  A device listed more than once = virtual shards on that GPU (tests on a single-GPU box)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        dv = np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        rc = self.lib.qadc_multi_create(_ptr(dv), len(dv), C.byref(h))
+        if rc:
+            raise QadcError(rc, self.lib.qadc_multi_last_error(None).decode())
+        self.h = h
+        self.dim = self.m = self.K = 0
+
+    def _ck(self, rc):
+        if rc:
+            raise QadcError(rc, self.lib.qadc_multi_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.qadc_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def uses_nccl(self):
+        return bool(self.lib.qadc_multi_uses_nccl(self.h))
+
+    def set_option(self, key, value):
+        for g in range(self.lib.qadc_multi_device_count(self.h)):
+            ctx = C.c_void_p(self.lib.qadc_multi_context(self.h, g))
+            if self.lib.qadc_set_option(ctx, key.encode(), int(value)):
+                raise QadcError(QADC_EINVAL, self.lib.qadc_last_error(ctx).decode())
+
+    def set_pq(self, dim, m, codebooks, rotation=None, bits=4):
+        cb = np.ascontiguousarray(codebooks, np.float32).reshape(-1)
+        rot = None if rotation is None else np.ascontiguousarray(rotation, np.float32).reshape(-1)
+        self._ck(self.lib.qadc_multi_set_pq(self.h, dim, m, bits, _ptr(cb), _ptr(rot)))
+        self.dim, self.m = dim, m
+
+    def set_coarse(self, centroids):
+        c = np.ascontiguousarray(centroids, np.float32)
+        self._ck(self.lib.qadc_multi_set_coarse(self.h, c.shape[0], _ptr(c)))
+        self.K = c.shape[0]
+
+    def _load(self, parts_codes, parts_labels, keep):
+        P = len(parts_codes)
+        sizes = np.array([c.shape[0] for c in parts_codes], np.uint32)
+        pc = (C.c_void_p * P)(*[c.ctypes.data if c.shape[0] else None for c in parts_codes])
+        pl = None
+        if parts_labels is not None:
+            pl = (C.c_void_p * P)(*[l.ctypes.data if l.shape[0] else None for l in parts_labels])
+        self._ck(self.lib.qadc_multi_load(self.h, P, _ptr(sizes), pc, pl, np.float32(keep)))
+
+    def load_flat(self, codes, keep):
+        self._load([np.ascontiguousarray(codes, np.uint8)], None, keep)
+
+    def load_ivf(self, codes, labels, offsets, keep):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        labels = np.ascontiguousarray(labels, np.uint32)
+        K = len(offsets) - 1
+        self._load([codes[offsets[p]:offsets[p + 1]] for p in range(K)], [labels[offsets[p]:offsets[p + 1]] for p in range(K)], keep)
+
+    def search(self, queries, ma, r, want_metrics=False):
+        q = np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        ids = np.empty((nq, r), np.uint32)
+        d = np.empty((nq, r), np.int8)
+        cnt = np.empty(nq, np.int32)
+        met = Metrics()
+        self._ck(self.lib.qadc_multi_search(self.h, _ptr(q), nq, ma, r, _ptr(ids), _ptr(d), _ptr(cnt), C.byref(met)))
+        return (ids, d, cnt, met) if want_metrics else (ids, d, cnt)

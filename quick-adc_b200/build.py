@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "qadc_capi.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("qadc_capi.cu", "qadc_device.cuh", "qadc_scan.cuh", "qadc_tables.cuh", "qadc_adc.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("qadc_capi.cu", "qadc_device.cuh", "qadc_scan.cuh", "qadc_tables.cuh", "qadc_adc.cuh", "qadc_multi.cuh")]
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "qadc_b200.h"))
 OUT = os.path.join(HERE, "libqadc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -24,7 +24,7 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
     extra = os.environ.get("QADC_NVCC_EXTRA", "").split()
-    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, "-ldl"]
     subprocess.check_call(cmd)
     return OUT
 

@@ -1270,3 +1270,5 @@ int qadc_set_option(qadc_ctx* ctx, const char* key, long value) {
 }
 
 }  // extern "C"
+
+#include "qadc_multi.cuh"

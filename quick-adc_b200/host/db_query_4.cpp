@@ -1,24 +1,28 @@
 // db_query_4 — drop-in CLI of the reference's Quick ADC query tool (db_query_4.cpp:312-414) on
-// top of the B200 path:  db_query_4 [-r R] [-m MA] [-k KEEP_PERCENT] [-b BATCH_SIZE] [-g GPU]
+// top of the B200 path:  db_query_4 [-r R] [-m MA] [-k KEEP_PERCENT] [-b BATCH_SIZE] [-g GPU[,GPU...]]
 //                                   [-o results.bin] db_file query_file groundtruth_file
+// -g takes one device ordinal or a comma-separated list (-g 0,1,2,3,4,5,6,7): the database is then sharded over
+// those GPUs by this one process (qadc_multi_*: NCCL all-gather of the per-GPU top-r lists + merge).
 // Same defaults (r=100, ma=1, keep=1 %, batch=1 -> here "all queries in one batch", since the
 // GPU engine is always batched) and the same CSV on stdout.  -o dumps the per-query results
 // (r uint32 ids then r int8 distances per query, ascending by distance) for tests.
 #include <unistd.h>
 
 #include <cstdio>
+#include <cstdlib>
+#include <strings.h>
 
 #include "query_common.hpp"
 
 struct cmdargs : query_args {
     float keep;
     int batch_size;
-    int gpu;
+    std::vector<int> gpus;
     const char* out_file;
 };
 
 static void usage() {
-    std::cerr << "Usage: db_query_4 [-r R] [-m MA] [-k KEEP_PERCENT] [-b BATCH_SIZE] [-g GPU] [-o results.bin] "
+    std::cerr << "Usage: db_query_4 [-r R] [-m MA] [-k KEEP_PERCENT] [-b BATCH_SIZE] [-g GPU[,GPU...]] [-o results.bin] "
               << "[db_file] [query_file] [groundtruth_file]" << std::endl;
     std::exit(1);
 }
@@ -30,7 +34,7 @@ static void parse_args(cmdargs& args, int argc, char* argv[]) {
     args.r = 100;
     args.keep = 1 * ONE_PERCENT;
     args.batch_size = 1;
-    args.gpu = 0;
+    args.gpus.assign(1, 0);
     args.out_file = nullptr;
     while ((opt = getopt(argc, argv, "r:m:b:k:g:o:")) != -1) {
         switch (opt) {
@@ -38,7 +42,18 @@ static void parse_args(cmdargs& args, int argc, char* argv[]) {
         case 'm': args.ma = std::atoi(optarg); break;
         case 'b': args.batch_size = std::atoi(optarg); break;
         case 'k': args.keep = std::atof(optarg) * ONE_PERCENT; break;
-        case 'g': args.gpu = std::atoi(optarg); break;
+        case 'g': {
+            args.gpus.clear();
+            for (const char* p = optarg; *p;) {
+                char* end;
+                args.gpus.push_back(static_cast<int>(std::strtol(p, &end, 10)));
+                if (end == p) usage();
+                p = (*end == ',') ? end + 1 : end;
+                if (*end && *end != ',') usage();
+            }
+            if (args.gpus.empty()) usage();
+            break;
+        }
         case 'o': args.out_file = optarg; break;
         default: usage();
         }
@@ -52,6 +67,13 @@ static void parse_args(cmdargs& args, int argc, char* argv[]) {
 int main(int argc, char* argv[]) {
     cmdargs args;
     parse_args(args, argc, argv);
+    // stdout carries the reference's CSV and nothing else: NCCL's own banner / debug lines (NCCL_DEBUG) go to stderr
+    // (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so a VERSION request is raised to WARN)
+    if (args.gpus.size() > 1) {
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+        const char* lvl = std::getenv("NCCL_DEBUG");
+        if (lvl && strcasecmp(lvl, "VERSION") == 0) setenv("NCCL_DEBUG", "WARN", 1);
+    }
     std::cerr << "Database file: " << args.db_file << std::endl;
     std::unique_ptr<base_db> db = load_database(args.db_file);
     if (db->pq->sq_bits != 4) {
@@ -60,7 +82,7 @@ int main(int argc, char* argv[]) {
     }
     query_metrics total_metrics;
     double total_recall = 0;
-    std::unique_ptr<scanner_gpu_4> scanner(new scanner_gpu_4(args.keep, args.gpu));
+    std::unique_ptr<scanner_gpu_4> scanner(new scanner_gpu_4(args.keep, args.gpus));
     nns_engine_gpu engine(std::move(scanner), *db, args.ma, args.r, args.batch_size == 1 ? -1 : args.batch_size);
     std::vector<unsigned> keys;
     std::vector<std::int8_t> vals;

@@ -48,47 +48,81 @@ struct query_args {
     std::exit(1);
 }
 
-// Scanner concept (db_query_4.cpp:73-310): owns the device copy of the database.
+[[noreturn]] inline void qadc_multi_die(qadc_multi* mm, const char* what) {
+    std::cerr << what << ": " << qadc_multi_last_error(mm) << std::endl;
+    std::exit(1);
+}
+
+// Scanner concept (db_query_4.cpp:73-310): owns the device copy of the database — on one GPU (a qadc_ctx) or
+// sharded over several GPUs of the box by this one process (a qadc_multi: contiguous runs of a flat database /
+// whole inverted lists per GPU, NCCL all-gather of the per-shard top-r lists, merge on the first device).
 struct scanner_gpu_4 {
     typedef kv_binheap<unsigned, std::int8_t> BhType;
-    qadc_ctx* ctx = nullptr;
+    qadc_ctx* ctx = nullptr;        // one device
+    qadc_multi* multi = nullptr;    // several devices
     float keep;
     explicit scanner_gpu_4(float keep_, int device = 0) : keep(keep_) {
         if (qadc_create(device, nullptr, &ctx) != QADC_OK) qadc_die(nullptr, "qadc_create");
     }
-    ~scanner_gpu_4() { qadc_destroy(ctx); }
+    scanner_gpu_4(float keep_, const std::vector<int>& devices) : keep(keep_) {
+        if (devices.size() == 1) {
+            if (qadc_create(devices[0], nullptr, &ctx) != QADC_OK) qadc_die(nullptr, "qadc_create");
+        } else if (qadc_multi_create(devices.data(), static_cast<int>(devices.size()), &multi) != QADC_OK) {
+            qadc_multi_die(nullptr, "qadc_multi_create");
+        }
+    }
+    ~scanner_gpu_4() { qadc_destroy(ctx); qadc_multi_destroy(multi); }
     scanner_gpu_4(const scanner_gpu_4&) = delete;
 
-    // scanner_4::prepare_database (db_query_4.cpp:210-228): copies every partition to the device
+    // scanner_4::prepare_database (db_query_4.cpp:210-228): copies every partition to the device(s)
     // (re-laid out there) and frees the database's own copy (:190).
     void prepare_database(base_db& db) {
         const base_pq& pq = *db.pq;
-        if (qadc_set_pq(ctx, pq.dim, pq.sq_count, pq.sq_bits, pq.centroids_flat.data(), pq.rotation_ptr())) qadc_die(ctx, "qadc_set_pq");
         const int parts = db.partition_count();
-        if (db.coarse_centroids() && qadc_set_coarse(ctx, parts, db.coarse_centroids())) qadc_die(ctx, "qadc_set_coarse");
         std::vector<std::uint32_t> sizes(parts);
+        std::vector<const std::uint8_t*> part_codes(parts, nullptr);
+        std::vector<const std::uint32_t*> part_labels(parts, nullptr);
         const std::uint8_t* codes;
         unsigned* labels;
         unsigned size;
-        bool has_labels = false;
+        bool has_labels = false, any = false;
         for (int p = 0; p < parts; ++p) {
             db.get_partition(p, codes, labels, size);
             sizes[p] = size;
-            if (size == 0) std::cerr << "Warning: Partition " << p << " is empty" << std::endl;
-            else has_labels = has_labels || labels != nullptr;
-        }
-        if (qadc_begin_database(ctx, parts, sizes.data(), has_labels)) qadc_die(ctx, "qadc_begin_database");
-        for (int p = 0; p < parts; ++p) {
-            db.get_partition(p, codes, labels, size);
-            if (size == 0) continue;
-            if ((labels != nullptr) != has_labels) {
+            if (size == 0) { std::cerr << "Warning: Partition " << p << " is empty" << std::endl; continue; }
+            if (any && (labels != nullptr) != has_labels) {
                 std::cerr << "Cannot prepare database. Some partitions have labels and some have not" << std::endl;
                 std::exit(1);
             }
-            if (qadc_upload_codes(ctx, p, 0, size, codes, labels, 0)) qadc_die(ctx, "qadc_upload_codes");
-            db.free_partition(p);
+            any = true;
+            has_labels = labels != nullptr;
+            part_codes[p] = codes;
+            part_labels[p] = labels;
         }
-        if (qadc_finalize(ctx, keep)) qadc_die(ctx, "qadc_finalize");
+        if (multi) {
+            if (qadc_multi_set_pq(multi, pq.dim, pq.sq_count, pq.sq_bits, pq.centroids_flat.data(), pq.rotation_ptr())) qadc_multi_die(multi, "qadc_multi_set_pq");
+            if (db.coarse_centroids() && qadc_multi_set_coarse(multi, parts, db.coarse_centroids())) qadc_multi_die(multi, "qadc_multi_set_coarse");
+            if (qadc_multi_load(multi, parts, sizes.data(), part_codes.data(), has_labels ? part_labels.data() : nullptr, keep))
+                qadc_multi_die(multi, "qadc_multi_load");
+        } else {
+            if (qadc_set_pq(ctx, pq.dim, pq.sq_count, pq.sq_bits, pq.centroids_flat.data(), pq.rotation_ptr())) qadc_die(ctx, "qadc_set_pq");
+            if (db.coarse_centroids() && qadc_set_coarse(ctx, parts, db.coarse_centroids())) qadc_die(ctx, "qadc_set_coarse");
+            if (qadc_begin_database(ctx, parts, sizes.data(), has_labels)) qadc_die(ctx, "qadc_begin_database");
+            // one copy + one re-layout launch per run of partitions (65 536 inverted lists: not 65 536 launches)
+            if (qadc_upload_partitions(ctx, part_codes.data(), has_labels ? part_labels.data() : nullptr)) qadc_die(ctx, "qadc_upload_partitions");
+            if (qadc_finalize(ctx, keep)) qadc_die(ctx, "qadc_finalize");
+        }
+        for (int p = 0; p < parts; ++p) db.free_partition(p);
+    }
+
+    // one batch: nns_engine_batch::batch_process_queries + per-query scanner_4::query_scan
+    void search(const float* queries, int nq, int ma, int r, std::uint32_t* ids, std::int8_t* dists, std::int32_t* counts,
+                qadc_metrics* m) {
+        if (multi) {
+            if (qadc_multi_search(multi, queries, nq, ma, r, ids, dists, counts, m)) qadc_multi_die(multi, "qadc_multi_search");
+        } else if (qadc_search(ctx, queries, nq, ma, r, ids, dists, counts, m)) {
+            qadc_die(ctx, "qadc_search");
+        }
     }
 };
 
@@ -120,9 +154,8 @@ struct nns_engine_gpu {
             counts_.resize(batch_size_);
             qadc_metrics m;
             const int dim = db_.pq->dim;
-            if (qadc_search(scanner_->ctx, queries + static_cast<long>(batch_first_) * dim, batch_size_, ma_, r_, ids_.data(),
-                            dists_.data(), counts_.data(), &m))
-                qadc_die(scanner_->ctx, "qadc_search");
+            scanner_->search(queries + static_cast<long>(batch_first_) * dim, batch_size_, ma_, r_, ids_.data(), dists_.data(),
+                             counts_.data(), &m);
             // like nns_engine_batch, the batch-level phases are booked on the first query of the batch
             metrics.index_us = static_cast<std::uint64_t>(m.index_us);
             metrics.rotate_us = static_cast<std::uint64_t>(m.rotate_us);

@@ -138,14 +138,15 @@ def cli_keep(percent):
     return np.float32(np.float64(percent) * np.float64(np.float32(0.01)))
 
 
-def run_cli(cli, tmp_path, db_kwargs, queries, gt, r, ma, keep_percent, batch, archive=False):
+def run_cli(cli, tmp_path, db_kwargs, queries, gt, r, ma, keep_percent, batch, archive=False, gpus=None):
     from qadc_b200 import dbfile
     (dbfile.write_archive_db if archive else dbfile.write_qdb)(tmp_path / "db.qdb", **db_kwargs)
     dbfile.write_vecs(tmp_path / "q.fvecs", queries)
     dbfile.write_vecs(tmp_path / "gt.ivecs", gt)
     out = tmp_path / "res.bin"
-    p = subprocess.run([cli, "-r", str(r), "-m", str(ma), "-k", str(keep_percent), "-b", str(batch), "-o", str(out),
-                        str(tmp_path / "db.qdb"), str(tmp_path / "q.fvecs"), str(tmp_path / "gt.ivecs")],
+    p = subprocess.run([cli, "-r", str(r), "-m", str(ma), "-k", str(keep_percent), "-b", str(batch), "-o", str(out)]
+                       + (["-g", gpus] if gpus else []) +
+                       [str(tmp_path / "db.qdb"), str(tmp_path / "q.fvecs"), str(tmp_path / "gt.ivecs")],
                        capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     lines = p.stdout.strip().splitlines()
@@ -258,6 +259,39 @@ def test_db_build_then_query(cli, oracle, tmp_path, ivf):
     for qi in range(nq):
         for v in np.unique(d[qi]):
             assert set(ids[qi][d[qi] == v].tolist()) == set(exp["ids"][qi][exp["d"][qi] == v].tolist())
+
+
+def _device_list():
+    """Every GPU of the box when there are several (NCCL path), else three virtual shards on GPU 0."""
+    import torch
+    n = torch.cuda.device_count()
+    return ",".join(str(i) for i in range(n)) if n > 1 else "0,0,0"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ivf", [False, True])
+def test_cli_sharded_over_gpus_equals_one_gpu(cli, tmp_path, ivf):
+    """db_query_4 -g 0,1,...: the database sharded over the GPUs by the one CLI process (qadc_multi_*: NCCL
+    all-gather of the per-GPU top-r lists + merge) prints the same CSV fields and dumps byte-identical
+    results as the one-GPU run."""
+    rng = np.random.default_rng(41 + ivf)
+    dim, m, nq, r = 128, 16, 37, 100
+    cb = synth.make_pq(rng, dim, m)
+    q = synth.make_queries(rng, nq, dim)
+    if ivf:
+        n, K, ma = 60000, 96, 12
+        cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+        codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(3, 50))
+        kw = dict(dim=dim, m=m, codebooks=cb, codes=codes, centroids=cents, labels=labels, offsets=offsets)
+    else:
+        n, ma = 150000, 1
+        kw = dict(dim=dim, m=m, codebooks=cb, codes=synth.make_codes(rng, n, m))
+    gt = rng.integers(0, n, (nq, 1)).astype(np.int32)
+    (tmp_path / "one").mkdir(); (tmp_path / "many").mkdir()
+    f1, ids1, d1 = run_cli(cli, tmp_path / "one", kw, q, gt, r, ma, 5, 16)
+    f2, ids2, d2 = run_cli(cli, tmp_path / "many", kw, q, gt, r, ma, 5, 16, gpus=_device_list())
+    assert f1[:5] == f2[:5]                      # r, recall, ma, adc_type, keep
+    assert np.array_equal(d1, d2) and np.array_equal(ids1, ids2)
 
 
 # ---- db_query: the plain ADC tool ("next" row N4) -------------------------------------------------
