@@ -208,7 +208,7 @@ int qadc_download_codes(qadc_ctx* ctx, int part_i, uint8_t* out_codes);
 /* ---- "next" row N1: PQ encoder -------------------------------------------------------------- */
 /* Replaces base_pq::encode_multiple_vectors + multiple_set_bits_4 (quantizers.hpp:49-68,
  * :222-245) and, with a coarse quantiser set, index_db::assign_single_compute_residuals
- * (databases.hpp:252-268): rotates (OPQ, flat only) and encodes `count` host vectors
+ * (databases.hpp:252-268): rotates (OPQ; with inverted lists the residual is what is rotated) and encodes `count` host vectors
  * (count*dim floats) into row-major codes (count*m*bits/8 bytes; 8-bit quantisers: one byte per
  * sub-quantiser, multiple_set_bits_native<uint8_t>, quantizers.hpp:36-47).  out_assign (count, may be
  * NULL) receives the coarse cell of every vector when the context has a coarse quantiser; the

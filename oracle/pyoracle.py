@@ -336,6 +336,20 @@ class Ref:
           _opt(v), C.c_int(v.shape[0]), _opt(codes))
         return codes
 
+    def index_add_vectors(self, vectors, m, codebooks, centroids, rotation=None):
+        """index_db::add_vectors (databases.hpp:270-298), with an opq when `rotation` is given: (assign, codes) per vector."""
+        v = np.array(vectors, np.float32, order="C", copy=True)
+        n, dim = v.shape
+        assign = np.zeros(n, np.int32)
+        codes = np.zeros((n, m // 2), np.uint8)
+        f = self.lib.ref_index_add_vectors
+        f.restype = None
+        f(C.c_int(dim), C.c_int(m), _opt(np.ascontiguousarray(codebooks, np.float32).reshape(-1)),
+          _opt(None if rotation is None else np.ascontiguousarray(rotation, np.float32).reshape(-1)),
+          C.c_int(centroids.shape[0]), _opt(np.ascontiguousarray(centroids, np.float32)), _opt(v), C.c_uint(n),
+          _opt(assign), _opt(codes))
+        return assign, codes
+
     class Handle:
         def __init__(self, ref, ptr, m, dim):
             self.ref, self.ptr, self.m, self.dim = ref, ptr, m, dim

@@ -374,4 +374,26 @@ __attribute__((visibility("default"))) void ref_encode_bits(
     pq.encode_multiple_vectors(vectors, codes, count);
 }
 
+// index_db::add_vectors as shipped (databases.hpp:270-298), optionally with an opq (residual -> rotate -> encode,
+// quantizers.hpp:222-224, :289-301): per inserted vector the cell it went to and the code that was stored.
+// NOTE: modifies `vectors` in place (residuals, rotation) like the reference does.
+__attribute__((visibility("default"))) void ref_index_add_vectors(
+        int dim, int m, const float* codebooks, const float* rotation, int K, const float* centroids,
+        float* vectors, unsigned count, int* out_assign, std::uint8_t* out_codes) {
+    std::unique_ptr<base_pq> pq;
+    if (rotation) pq.reset(new opq(m, 4, dim, const_cast<float*>(codebooks), const_cast<float*>(rotation)));
+    else pq.reset(new base_pq(m, 4, dim, const_cast<float*>(codebooks)));
+    std::unique_ptr<float[]> cents(new float[(size_t)K * dim]);
+    std::copy(centroids, centroids + (size_t)K * dim, cents.get());
+    index_db db(std::move(pq), K, std::move(cents));
+    db.add_vectors(vectors, count, 0, 1);
+    const int cs = m / 2;
+    for (int p = 0; p < K; ++p)
+        for (size_t i = 0; i < db.labels[p].size(); ++i) {
+            const unsigned v = db.labels[p][i];
+            out_assign[v] = p;
+            std::copy(db.partitions[p].begin() + i * cs, db.partitions[p].begin() + (i + 1) * cs, out_codes + (size_t)v * cs);
+        }
+}
+
 }  // extern "C"

@@ -1101,17 +1101,20 @@ int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* ou
                 QCK(cudaMemcpyAsync(out_assign + off, d_assign, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
         }
         const float* d_in = d_x;
+        bool residual_done = false;
         if (ctx->d_rotation) {
-            if (ivf) return fail(ctx, QADC_EINVAL, "OPQ + inverted lists: rotate residuals is not implemented in qadc_encode");
+            // OPQ: rotate the vector — or, with inverted lists, its residual (residual -> rotate -> encode)
             const size_t tot = static_cast<size_t>(n) * dim;
-            rotate_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ctx->stream>>>(d_x, n, dim, ctx->d_rotation,
-                                                                                          ctx->b_tables.as<float>());
+            rotate_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ctx->stream>>>(
+                d_x, n, dim, ctx->d_rotation, ivf ? ctx->d_centroids : nullptr, d_assign, ctx->b_tables.as<float>());
             QCK(cudaGetLastError());
             d_in = ctx->b_tables.as<float>();
+            residual_done = ivf;
         }
         const size_t threads = static_cast<size_t>(n) * CS;
         encode_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(
-            d_in, n, dim, M, ctx->bits, ctx->d_codebooks, ivf ? ctx->d_centroids : nullptr, d_assign, ctx->b_dump.as<uint8_t>());
+            d_in, n, dim, M, ctx->bits, ctx->d_codebooks, (ivf && !residual_done) ? ctx->d_centroids : nullptr, d_assign,
+            ctx->b_dump.as<uint8_t>());
         QCK(cudaGetLastError());
         QCK(cudaMemcpyAsync(out_codes + static_cast<size_t>(off) * CS, ctx->b_dump.p, static_cast<size_t>(n) * CS,
                             cudaMemcpyDeviceToHost, ctx->stream));

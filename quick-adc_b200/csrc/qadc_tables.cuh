@@ -525,17 +525,22 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ v
     codes[t] = static_cast<uint8_t>(code);
 }
 
-// opq::rotate_multiple_vectors (quantizers.hpp:289-301): out = X * R^T, sequential fma over k.
+// opq::rotate_multiple_vectors (quantizers.hpp:289-301): out = X * R^T, sequential fma over k.  With `centroids` /
+// `assign` the residual x - centroid[assign[v]] is what is rotated (index_db::add_vectors with an opq:
+// assign_single_compute_residuals, then encode_multiple_vectors rotates, databases.hpp:252-298, quantizers.hpp:222-224).
 __global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ vectors, uint32_t count, int dim,
-                                                     const float* __restrict__ rotation, float* __restrict__ out) {
+                                                     const float* __restrict__ rotation, const float* __restrict__ centroids,
+                                                     const int32_t* __restrict__ assign, float* __restrict__ out) {
     const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= static_cast<size_t>(count) * dim) return;
     const size_t v = t / dim;
     const int j = static_cast<int>(t % dim);
     const float* x = vectors + v * dim;
     const float* row = rotation + static_cast<size_t>(j) * dim;
+    const float* cent = centroids ? centroids + static_cast<size_t>(assign[v]) * dim : nullptr;
     float s = 0.f;
-    for (int k = 0; k < dim; ++k) s = __fmaf_rn(x[k], __ldg(row + k), s);
+    if (cent) for (int k = 0; k < dim; ++k) s = __fmaf_rn(__fsub_rn(x[k], __ldg(cent + k)), __ldg(row + k), s);
+    else for (int k = 0; k < dim; ++k) s = __fmaf_rn(x[k], __ldg(row + k), s);
     out[t] = s;
 }
 

@@ -137,7 +137,7 @@ inline void index_db::save(std::ostream& os) const {
     }
 }
 
-inline std::unique_ptr<base_db> load_qdb(std::istream& in, const char* filename) {
+inline std::unique_ptr<base_db> load_qdb(std::istream& in, const char* filename, std::uint64_t file_bytes) {
     char magic[8];
     std::int32_t h[6];
     in.read(magic, 8);
@@ -147,6 +147,17 @@ inline std::unique_ptr<base_db> load_qdb(std::istream& in, const char* filename)
         std::exit(1);
     }
     const int kind = h[0], pq_kind = h[1], dim = h[2], m = h[3], bits = h[4], K = h[5];
+    // every header field is checked before it sizes an allocation (a corrupt file must say so, not crash):
+    // geometry like get_pq below, every array bounded by the file length
+    const bool geometry_ok = (kind == 0 || kind == 1) && (pq_kind == 0 || pq_kind == 1) && m > 0 && (bits == 4 || bits == 8) &&
+                             dim > 0 && dim <= (1 << 20) && dim % m == 0 && (m * bits) % 8 == 0 && K > 0 && (kind == 1 || K == 1);
+    const std::uint64_t fixed_bytes = geometry_ok ? ((static_cast<std::uint64_t>(dim) << bits) + (pq_kind ? static_cast<std::uint64_t>(dim) * dim : 0) +
+                                                     (kind ? static_cast<std::uint64_t>(K) * dim : 0)) * 4 + static_cast<std::uint64_t>(K) * 8
+                                                  : 0;
+    if (!geometry_ok || fixed_bytes > file_bytes) {
+        std::cerr << filename << ": corrupt .qdb header" << std::endl;
+        std::exit(1);
+    }
     std::unique_ptr<base_pq> pq;
     if (pq_kind == 1) pq.reset(new opq(m, bits, dim));
     else pq.reset(new base_pq(m, bits, dim));
@@ -157,8 +168,12 @@ inline std::unique_ptr<base_db> load_qdb(std::istream& in, const char* filename)
     if (kind == 0) {
         auto* f = new flat_db;
         db.reset(f);
-        std::uint64_t size;
+        std::uint64_t size = 0;
         in.read(reinterpret_cast<char*>(&size), 8);
+        if (!in || size > file_bytes / cs || size >= (std::uint64_t(1) << 32)) {
+            std::cerr << filename << ": corrupt .qdb size field" << std::endl;
+            std::exit(1);
+        }
         f->codes.resize(size * cs);
         in.read(reinterpret_cast<char*>(f->codes.data()), f->codes.size());
         f->codes_count = static_cast<unsigned>(size);
@@ -170,6 +185,12 @@ inline std::unique_ptr<base_db> load_qdb(std::istream& in, const char* filename)
         in.read(reinterpret_cast<char*>(x->centroids.data()), x->centroids.size() * sizeof(float));
         std::vector<std::uint64_t> sizes(K);
         in.read(reinterpret_cast<char*>(sizes.data()), 8 * static_cast<size_t>(K));
+        std::uint64_t total = 0;
+        for (int p = 0; p < K && in; ++p) total = (sizes[p] > file_bytes) ? file_bytes + 1 : total + sizes[p];
+        if (!in || total > file_bytes / (cs + 4)) {
+            std::cerr << filename << ": corrupt .qdb partition sizes" << std::endl;
+            std::exit(1);
+        }
         x->partitions.resize(K);
         x->labels.resize(K);
         for (int p = 0; p < K; ++p) {
@@ -224,7 +245,7 @@ template <typename T> inline void put_vector(std::ostream& os, const std::vector
 }
 template <typename T> inline bool get_vector(std::istream& in, std::vector<T>& v, std::uint64_t max_bytes) {
     const std::uint64_t n = get<std::uint64_t>(in);
-    if (!in || n * sizeof(T) > max_bytes) return false;
+    if (!in || n > max_bytes / sizeof(T)) return false;
     v.resize(n);
     in.read(reinterpret_cast<char*>(v.data()), static_cast<std::streamsize>(n * sizeof(T)));
     return static_cast<bool>(in);
@@ -337,7 +358,7 @@ inline std::unique_ptr<base_db> load_database(const char* filename) {
     in.read(magic, 8);
     in.clear();
     in.seekg(0);
-    if (std::memcmp(magic, "QADCDB1", 8) == 0) return load_qdb(in, filename);
+    if (std::memcmp(magic, "QADCDB1", 8) == 0) return load_qdb(in, filename, file_bytes);
     std::unique_ptr<base_db> db = load_archive(in, file_bytes);
     if (!db) {
         std::cerr << filename << " is not a database file (neither a flat_db/index_db cereal archive nor a .qdb container)" << std::endl;

@@ -96,6 +96,20 @@ def encode_case(ref, name, seed, dim, m, n, bits=4):
     print(name, "encoded", n)
 
 
+def add_vectors_case(ref, name, seed, dim, m, n, K, opq):
+    """index_db::add_vectors (databases.hpp:270-298) with a plain PQ or an OPQ (residual -> rotate -> encode)."""
+    rng = np.random.default_rng(seed)
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    x = (cents[rng.integers(0, K, n)] + rng.standard_normal((n, dim))).astype(np.float32)
+    out = dict(dim=dim, m=m, codebooks=cb, centroids=cents, vectors=x)
+    if opq:
+        out["rotation"] = np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32)
+    out["ref_assign"], out["ref_codes"] = ref.index_add_vectors(x, m, cb, cents, out.get("rotation"))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "cells used", len(np.unique(out["ref_assign"])))
+
+
 def archive_case(ref, name, seed, dim, m, n, K):
     """Database files as the reference writes them (flatdb_create.cpp:49-53): flat/index x pq/opq.
     Field order = the reference's save() members; field bytes = oracle/shims/cereal (cereal 1.2.2's
@@ -158,6 +172,10 @@ def main():
                      ("encode_8x8", dict(seed=112, dim=64, m=8, n=300, bits=8))):
         if want(name):
             encode_case(ref, name, **kw)
+    for name, kw in (("add_ivf_pq", dict(seed=120, dim=64, m=16, n=600, K=40, opq=False)),
+                     ("add_ivf_opq", dict(seed=121, dim=64, m=16, n=600, K=40, opq=True))):
+        if want(name):
+            add_vectors_case(ref, name, **kw)
     # n = 3003: not a multiple of 16 -> exercises the pad-lane duplicate quirk
     if want("flat_m16"):
         flat_case(ref, "flat_m16", seed=101, dim=128, m=16, n=3003, nq=8, r=20, keep=0.05)

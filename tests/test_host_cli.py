@@ -33,6 +33,20 @@ def test_cli_rejects_non_database(cli, tmp_path):
     assert p.returncode == 1 and "is not a database file" in p.stderr
 
 
+def test_cli_rejects_corrupt_qdb_headers(cli, tmp_path):
+    """Every header field of a .qdb file is validated before it sizes an allocation (m = 0, absurd sizes ...)."""
+    import struct
+    good = struct.pack("8s6i", b"QADCDB1\0", 0, 0, 64, 16, 4, 1)
+    for bad in (struct.pack("8s6i", b"QADCDB1\0", 0, 0, 64, 0, 4, 1),            # m = 0
+                struct.pack("8s6i", b"QADCDB1\0", 0, 0, 64, 16, 31, 1),           # huge bits
+                struct.pack("8s6i", b"QADCDB1\0", 1, 0, 64, 16, 4, 1 << 30),      # absurd partition count
+                good + b"\0" * (64 * 16 * 4) + struct.pack("Q", 1 << 40)):         # absurd vector count
+        f = tmp_path / "bad.qdb"
+        f.write_bytes(bad)
+        p = subprocess.run([cli, str(f), str(f), str(f)], capture_output=True, text=True)
+        assert p.returncode == 1 and "corrupt .qdb" in p.stderr, p.stderr
+
+
 # ---- database files: the reference's archive layout and the .qdb container --------------------
 ARCHIVE_KINDS = [(ivf, opq) for ivf in (False, True) for opq in (False, True)]
 
@@ -206,8 +220,8 @@ def test_cli_ivf_matches_oracle(cli, oracle, tmp_path, archive):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ivf", [False, True])
-def test_db_build_then_query(cli, oracle, tmp_path, ivf):
+@pytest.mark.parametrize("ivf,use_opq", [(False, False), (True, False), (True, True)])
+def test_db_build_then_query(cli, oracle, tmp_path, ivf, use_opq):
     """floats -> db_build (GPU encoder, the reference's flatdb_create/db_add chain) -> db_query_4:
     same results as the oracle's encoder + search on the same inputs.  The inverted-list case goes
     through a file in the reference's archive layout, the flat one through a .qdb container."""
@@ -218,7 +232,9 @@ def test_db_build_then_query(cli, oracle, tmp_path, ivf):
     cb = synth.make_pq(rng, dim, m)
     base = rng.standard_normal((n, dim)).astype(np.float32)
     q = synth.make_queries(rng, nq, dim)
-    dbfile.write_pq_data(tmp_path / "q.pq.data", dim, m, cb)
+    rot = np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32) if use_opq else None
+    qfile = tmp_path / ("q.opq.data" if use_opq else "q.pq.data")     # OPQ + inverted lists: the README's flagship index
+    dbfile.write_pq_data(qfile, dim, m, cb, rot)
     dbfile.write_vecs(tmp_path / "base.fvecs", base)
     dbfile.write_vecs(tmp_path / "q.fvecs", q)
     cmd = [os.path.join(HOST, "db_build")]
@@ -226,21 +242,24 @@ def test_db_build_then_query(cli, oracle, tmp_path, ivf):
         cents = base[rng.permutation(n)[:K]].copy()
         dbfile.write_vecs(tmp_path / "cents.fvecs", cents)
         cmd += ["-c", str(tmp_path / "cents.fvecs")]
-    cmd += [str(tmp_path / "q.pq.data"), str(tmp_path / "base.fvecs"), dbname]
+    cmd += [str(qfile), str(tmp_path / "base.fvecs"), dbname]
     p = subprocess.run(cmd, capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
-    assert ("Indexed DB (partitions=20)" if ivf else "Flat DB") in p.stderr and "pq (dim=64, sq=16x4)" in p.stderr
+    assert ("Indexed DB (partitions=20)" if ivf else "Flat DB") in p.stderr and ("opq" if use_opq else "pq") + " (dim=64, sq=16x4)" in p.stderr
     # expected database built with the oracle: assignment, residual codes, insertion order per cell
     keep = cli_keep(10)
     if ivf:
         assign, _ = oracle.coarse_assign(base, cents, 1)
         assign = assign[:, 0]
-        codes_all = oracle.encode((base - cents[assign]).astype(np.float32), m, cb)
+        resid = (base - cents[assign]).astype(np.float32)
+        codes_all = oracle.encode(oracle.rotate(resid, rot) if use_opq else resid, m, cb)
         order = np.argsort(assign, kind="stable")
         offsets = np.zeros(K + 1, np.int64)
         offsets[1:] = np.cumsum(np.bincount(assign, minlength=K))
         db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes_all[order], labels=order.astype(np.uint32),
                   keep=keep, offsets=offsets)
+        if use_opq:
+            db["rotation"] = rot
         exp = oracle.search(db, q, ma, r, want_tables=False)
     else:
         db = dict(dim=dim, m=m, codebooks=cb, codes=oracle.encode(base, m, cb), keep=keep, offsets=np.array([0, n], np.int64))
