@@ -263,6 +263,8 @@ def run_ours(args):
     ix.set_option("time_scan", 1)
     if args.flat_filter is not None:
         ix.set_option("flat_filter", args.flat_filter)
+    if args.flat_ring is not None:
+        ix.set_option("flat_ring", args.flat_ring)
 
     # device-resident buffers (the `value` leg)
     d_q = torch.from_numpy(queries).to(dev)
@@ -475,6 +477,7 @@ def main():
     ap.add_argument("--queries", type=int, default=16)
     ap.add_argument("--qb", type=int, default=1, help="queries per pass of the flat scan (0 = library default)")
     ap.add_argument("--flat-filter", type=int, default=None, help="0: exact lookup core only (A/B against the pre-filter)")
+    ap.add_argument("--flat-ring", type=int, default=None, help="1: per-warp TMA rings (scan_flat_wr_kernel), 0: CTA-wide ring")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verify", type=int, default=2, help="queries cross-checked at full size after timing (every N)")
     ap.add_argument("--no-configs", action="store_true", help="skip the informational `configs` legs (BASELINE configs 1-3 / 5)")

@@ -237,7 +237,9 @@ int qadc_adc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, 
 /* ---- tuning knobs (bench / tests) ------------------------------------------------------ */
 /* key: "flat_qb" (queries per pass of the flat scan: 1,2,4,8), "flat_chunks" (CTAs along
  * the database, 0 = auto), "flat_filter" (1 = default: clamped byte-lane pre-filter in front of the exact
- * lookup core of the one-query-per-pass flat scan, 0 = exact core only; same results), "ivf_sb_per_item" (256-vector blocks per work item of the inverted-list
+ * lookup core of the one-query-per-pass flat scan, 0 = exact core only; same results), "ivf_fused" (1 = default:
+ * one kernel per query batch builds the float tables of an inverted-list search in shared memory, bounds and
+ * quantises them there; 0 = the separate table / prefix / quantise kernels; same results), "ivf_sb_per_item" (256-vector blocks per work item of the inverted-list
  * scan, default 8), "time_scan" (1: record CUDA events around the scan kernel for
  * qadc_last_scan_ms).  Unknown key -> QADC_EINVAL. */
 int qadc_set_option(qadc_ctx* ctx, const char* key, long value);

@@ -74,7 +74,8 @@ struct qadc_ctx {
     int* d_err = nullptr;
     int* h_err = nullptr;   // pinned
     // options / accounting
-    long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1;
+    long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1, opt_ivf_fused = 1, opt_flat_ring = 0;
+    bool sbound_seeded = false;   // the fused inverted-list table kernel already wrote the shared bounds of this batch
     int ivf_sb_per_item = 8;   // superblocks per work item of the IVF scan (option "ivf_sb_per_item")
     int launches = 0;
     cudaEvent_t ev[8] = {};
@@ -172,14 +173,36 @@ int launch_flat(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
     return QADC_OK;
 }
 
+template <int NW, int NSW>
+int launch_flat_wr(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
+    using Cfg = WarpRingCfg<NW, NSW>;
+    const size_t smem = Cfg::smem_bytes(a.cap);
+    if (smem > kMaxSmem) return QADC_ENOMEM;
+    auto kern = scan_flat_wr_kernel<NW, NSW>;
+    QCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid(chunks, a.nq);
+    kern<<<grid, Cfg::kThreads, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    return QADC_OK;
+}
+
 struct FlatVariant {
     int m, qb, nw, ns;
     int (*launch)(qadc_ctx*, FlatScanArgs, int);
     size_t (*smem)(int cap);
+    int wr;   // 1: per-warp rings (scan_flat_wr_kernel), chosen with option "flat_ring"
 };
-#define QADC_FLAT_VARIANT(M, QB, NW, NS) {M, QB, NW, NS, launch_flat<M, QB, NW, NS>, FlatCfg<M, QB, NW, NS>::smem_bytes}
+#define QADC_FLAT_VARIANT(M, QB, NW, NS) {M, QB, NW, NS, launch_flat<M, QB, NW, NS>, FlatCfg<M, QB, NW, NS>::smem_bytes, 0}
+#ifndef QADC_NWR
+#define QADC_NWR 16   // warps of the per-warp-ring kernel
+#endif
+#ifndef QADC_NSWR
+#define QADC_NSWR 4   // superblocks in flight per warp
+#endif
 // in order of preference per (m, qb): 15 consumer warps when the lists fit, else 8
 const FlatVariant kFlatVariants[] = {
+    {16, 1, QADC_NWR, QADC_NSWR, launch_flat_wr<QADC_NWR, QADC_NSWR>, WarpRingCfg<QADC_NWR, QADC_NSWR>::smem_bytes, 1},
     QADC_FLAT_VARIANT(16, 1, QADC_NW1, QADC_NS1), QADC_FLAT_VARIANT(16, 1, 8, 4),
     QADC_FLAT_VARIANT(16, 2, 15, 3), QADC_FLAT_VARIANT(16, 2, 8, 4),
     QADC_FLAT_VARIANT(16, 4, 15, 3), QADC_FLAT_VARIANT(16, 4, 8, 4),
@@ -203,7 +226,7 @@ int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     pl.v = nullptr;
     for (; qb >= 1 && !pl.v; qb >>= 1)
         for (const FlatVariant& v : kFlatVariants) {
-            if (v.m != M || v.qb != qb || pl.v) continue;
+            if (v.m != M || v.qb != qb || pl.v || (v.wr && !ctx->opt_flat_ring)) continue;
             for (int cap : caps)
                 if (!pl.v && v.smem(cap) <= static_cast<size_t>(kMaxSmem)) { pl.v = &v; pl.cap = cap; pl.qb = qb; pl.nw = v.nw; }
         }
@@ -266,7 +289,9 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
     const bool flat = (ctx->K == 0);
     int n_lists = 0;
     const PipeK pk = make_pipek();
-    int rc = seed_shared_bound(ctx, d_assign, d_qtables, nq, ma, r);
+    int rc = QADC_OK;
+    if (ctx->sbound_seeded) ctx->sbound_seeded = false;   // seeded by ivf_prepare_kernel for exactly this batch
+    else rc = seed_shared_bound(ctx, d_assign, d_qtables, nq, ma, r);
     if (rc) return rc;
     if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0[ctx->scan_seq % qadc_ctx::kScanRing], ctx->stream));
     if (flat) {
@@ -274,7 +299,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         rc = plan_flat(ctx, nq, r, pl);
         if (rc) return rc;
         // the NW warp lists of a CTA are merged inside the kernel when they fit a CTA-wide sort in the tile ring
-        const size_t ring_keys = static_cast<size_t>(pl.v->ns) * pl.nw * sb_bytes(M) / 8;
+        const size_t ring_keys = static_cast<size_t>(pl.v->ns) * pl.nw * sb_bytes(M) / 8;   // same product for both ring layouts
         const bool cta_merge = static_cast<size_t>(next_pow2(pl.nw * r)) <= std::min<size_t>(ring_keys, 4096);
         n_lists = cta_merge ? pl.chunks : pl.chunks * pl.nw;
         ENSURE(ctx->b_lists, static_cast<size_t>(nq) * n_lists * r * 8);
@@ -327,13 +352,30 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
 }
 
 // Stage T on device buffers. d_assign_in may be null (then assignment is computed).
+template <int M, int DSQ>
+int launch_ivf_prepare(qadc_ctx* ctx, const IvfPrepArgs& a, int nq, size_t smem) {
+    auto kern = ivf_prepare_kernel<M, DSQ>;
+    QCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<nq, 256, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    return QADC_OK;
+}
+
 int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, const int32_t* d_assign_in,
-                  bool record_events) {
+                  bool record_events, bool want_float_tables = false) {
     const int M = ctx->m, dim = ctx->dim;
     const bool flat = (ctx->K == 0);
     const size_t nqa = static_cast<size_t>(nq) * ma;
+    // inverted lists: the whole pipeline after the assignment in one kernel, tables resident in shared memory
+    const size_t fused_smem = ivf_prep_smem_bytes(M, ma, dim);
+    // (two CTAs per SM or it loses to the separate kernels: measured 6.3 vs 5.7 ms on config 5, nprobe 128, where the
+    // tables of one query take 128 KB; opt_ivf_fused = 2 forces it whenever it fits)
+    const size_t fused_limit = ctx->opt_ivf_fused >= 2 ? static_cast<size_t>(kMaxSmem) - 2048 : 100 * 1024;
+    const bool fused = !flat && ctx->opt_ivf_fused && fused_smem <= fused_limit &&
+                       static_cast<uint64_t>(ma) * ctx->max_start <= (1u << 16);
     ENSURE(ctx->b_assign, nqa * 4);
-    ENSURE(ctx->b_tables, nqa * M * 16 * 4);
+    if (!fused || want_float_tables) ENSURE(ctx->b_tables, nqa * M * 16 * 4);
     ENSURE(ctx->b_tmin, nqa * 4);
     ENSURE(ctx->b_qmax, static_cast<size_t>(nq) * 4);
     ENSURE(ctx->b_qmin, static_cast<size_t>(nq) * 4);
@@ -362,6 +404,40 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         }
     }
     if (record_events) QCK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (fused) {
+        ENSURE(ctx->b_sbound, static_cast<size_t>(nq) * 4);
+        IvfPrepArgs pa;
+        pa.queries = d_queries; pa.dim = dim; pa.codebooks = ctx->d_codebooks; pa.rotation = ctx->d_rotation;
+        pa.centroids = ctx->d_centroids; pa.assign = d_assign; pa.ma = ma; pa.r = r;
+        pa.starts = ctx->d_starts; pa.start_off = ctx->d_start_off; pa.start_size = ctx->d_start_size;
+        pa.tables_out = want_float_tables ? ctx->b_tables.as<float>() : nullptr;
+        pa.qtables = ctx->b_qtables.as<int8_t>(); pa.qmin = ctx->b_qmin.as<float>(); pa.qmax = ctx->b_qmax.as<float>();
+        pa.shared_bound = ctx->b_sbound.as<int>(); pa.err = ctx->d_err;
+        int rc;
+        const int dsq = dim / M;
+#define QADC_PREP(MM, DD) rc = launch_ivf_prepare<MM, DD>(ctx, pa, nq, fused_smem)
+        if (M == 16) {
+            switch (dsq) {
+                case 2: QADC_PREP(16, 2); break;
+                case 4: QADC_PREP(16, 4); break;
+                case 6: QADC_PREP(16, 6); break;
+                case 8: QADC_PREP(16, 8); break;
+                default: QADC_PREP(16, 0); break;
+            }
+        } else {
+            switch (dsq) {
+                case 2: QADC_PREP(32, 2); break;
+                case 3: QADC_PREP(32, 3); break;
+                case 4: QADC_PREP(32, 4); break;
+                default: QADC_PREP(32, 0); break;
+            }
+        }
+#undef QADC_PREP
+        if (rc) return rc;
+        ctx->sbound_seeded = true;
+        if (record_events) QCK(cudaEventRecord(ctx->ev[2], ctx->stream));
+        return QADC_OK;
+    }
     // 2+3. residual, rotation, float tables
     {
         dim3 tgrid((ma + 7) / 8, nq);
@@ -988,8 +1064,9 @@ int qadc_build_tables(qadc_ctx* ctx, const float* queries, int nq, int ma, int r
         d_ain = ctx->b_ids.as<int32_t>();
     }
     ctx->launches = 0;
-    rc = tables_device(ctx, ctx->b_queries.as<float>(), nq, ma, r, d_ain, false);
+    rc = tables_device(ctx, ctx->b_queries.as<float>(), nq, ma, r, d_ain, false, out_tables != nullptr);
     if (rc) return rc;
+    ctx->sbound_seeded = false;   // no scan follows this call
     QCK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_assign) QCK(cudaMemcpyAsync(out_assign, ctx->b_assign.p, nqa * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_tables) QCK(cudaMemcpyAsync(out_tables, ctx->b_tables.p, nqa * td * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1263,6 +1340,8 @@ int qadc_set_option(qadc_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "flat_qb")) ctx->opt_flat_qb = value;
     else if (!strcmp(key, "flat_chunks")) ctx->opt_flat_chunks = value;
     else if (!strcmp(key, "flat_filter")) ctx->opt_flat_filter = value != 0;
+    else if (!strcmp(key, "ivf_fused")) ctx->opt_ivf_fused = value;
+    else if (!strcmp(key, "flat_ring")) ctx->opt_flat_ring = value != 0;
     else if (!strcmp(key, "ivf_sb_per_item")) {
         if (value < 1 || value > (1 << 20)) return fail(ctx, QADC_EINVAL, "ivf_sb_per_item out of range");
         ctx->ivf_sb_per_item = static_cast<int>(value);

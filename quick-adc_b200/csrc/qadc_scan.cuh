@@ -550,6 +550,208 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 }
 
 // ------------------------------------------------------------------------------------------
+// Flat scan, one query per pass, 16x4 codes, PER-WARP rings: grid = (chunks, queries), NW warps per CTA, no producer
+// warp.  Warp w owns superblocks sb0 + w, sb0 + w + NW, ... of the CTA's chunk (the CTA still sweeps its chunk
+// front to back, so HBM sees 148 sequential streams) and feeds ITSELF: its elected lane keeps NSW one-superblock
+// TMA bulk copies in flight into the warp's own shared-memory slots (one mbarrier per slot) and re-arms a slot as
+// soon as the warp has copied that superblock into registers.  Compared with the CTA-wide ring of scan_flat_kernel
+// (one producer warp, a stage is refilled only when ALL 15 consumer warps have released it) a slow warp no longer
+// holds back the prefetch of the others — ncu showed 16 % of the warp time of that kernel waiting at the `full`
+// barrier with HBM at 86 % of its measured peak — and the 16th warp computes instead of producing.
+// The lookup / pre-filter / candidate machinery is the register-table path of scan_flat_kernel.
+// ------------------------------------------------------------------------------------------
+template <int NW, int NSW>
+struct WarpRingCfg {
+    static constexpr int M = 16, kQuads = 4, kSbBytes = 2048;
+    static constexpr int kRingBytes = NW * NSW * kSbBytes;
+    static constexpr int kThreads = NW * 32;
+    // rings | table | per-warp filter tables | barriers | histogram + counters | list counts/bounds, rounded to 16 bytes
+    static constexpr int kFixedBytes = ((kRingBytes + M * 16 + NW * M * 16 + NW * NSW * 8 + (128 + 2) * 4 + NW * 8) + 15) / 16 * 16;
+    static size_t smem_bytes(int cap) { return static_cast<size_t>(kFixedBytes) + static_cast<size_t>(NW) * cap * 8; }
+};
+
+template <int NW, int NSW>
+__global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScanArgs a) {
+    using Cfg = WarpRingCfg<NW, NSW>;
+    constexpr int M = 16;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* rings = smem;                                                                 // [NW][NSW][2048]
+    uint4* qtab = reinterpret_cast<uint4*>(rings + Cfg::kRingBytes);                       // [M]
+    uint4* ftab = qtab + M;                                                                // [NW][M]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ftab + NW * M);                           // [NW][NSW]
+    int* hist = reinterpret_cast<int*>(full + NW * NSW);                                   // [128]
+    int* hist_total = hist + 128;
+    int* hist_next = hist_total + 1;
+    int* cnt = hist_next + 1;                                                              // [NW]
+    int* bnd = cnt + NW;
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem + Cfg::kFixedBytes);                // [NW][cap]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sb0 = min(blockIdx.x * a.sb_per_chunk, a.n_sb);
+    const uint32_t sb1 = min(sb0 + a.sb_per_chunk, a.n_sb);
+    const int q = blockIdx.y;
+    const PipeK pk = a.k;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NW * NSW; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < M; i += blockDim.x) qtab[i] = reinterpret_cast<const uint4*>(a.qtabs)[static_cast<size_t>(q) * M + i];
+    for (int i = threadIdx.x; i < NW * a.cap; i += blockDim.x) lists[i] = kEmptyKey;
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) { cnt[i] = 0; bnd[i] = 127; }
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x == 0) { *hist_total = 0; *hist_next = a.r; }
+    __syncthreads();
+
+    WarpList wl{lists + static_cast<size_t>(warp) * a.cap, cnt + warp, bnd + warp};
+    const int halves = (a.cap < a.r + kSbVec) ? 2 : 1;
+    const int compact_at = min(a.cap - kSbVec / halves, 2 * a.r);
+    int* sbound = a.shared_bound + q;
+
+    // this warp's superblocks: sb0 + warp + i * NW, i < n_mine
+    const uint32_t first = sb0 + warp;
+    const uint32_t n_mine = (first < sb1) ? (sb1 - first + NW - 1) / NW : 0;
+    const uint32_t ring_a = smem_u32(rings) + warp * (NSW * Cfg::kSbBytes);
+    const uint32_t full_a = smem_u32(full) + warp * (NSW * 8);
+    const uint8_t* src0 = a.codes + static_cast<size_t>(first) * Cfg::kSbBytes;
+    auto issue = [&](uint32_t i, uint32_t slot) {   // elected lane: arm the slot's barrier and start the copy of superblock i
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_a + slot * 8), "r"(Cfg::kSbBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ring_a + slot * Cfg::kSbBytes),
+                     "l"(src0 + static_cast<size_t>(i) * (NW * Cfg::kSbBytes)), "r"(Cfg::kSbBytes), "r"(full_a + slot * 8)
+                     : "memory");
+    };
+    if (lane == 0)
+        for (uint32_t i = 0; i < min(n_mine, static_cast<uint32_t>(NSW)); ++i) issue(i, i);
+
+    uint4 treg[M];
+    uint4* my_ftab = ftab + warp * M;
+    int lb = 127, gb = load_shared_bound(sbound);
+    int bound = min(lb, gb + 1);
+    uint32_t f_start = 0;
+    bool filt_on = a.use_filter != 0;
+    int ctl = 0;
+    auto load_table = [&]() {
+        if (filt_on) {
+            const int t_f = bound - 1;
+            f_start = filt_start(t_f);
+            const uint32_t cap4 = static_cast<uint32_t>(filt_cap(t_f, M)) * 0x01010101u;
+            __syncwarp();
+            if (lane < M) {
+                const uint4 t = qtab[lane];
+                my_ftab[lane] = make_uint4(__vminu4(t.x, cap4), __vminu4(t.y, cap4), __vminu4(t.z, cap4), __vminu4(t.w, cap4));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < M; ++j) treg[j] = my_ftab[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < M; ++j) treg[j] = qtab[j];
+        }
+    };
+    load_table();
+    int gb_pending = bound - 1;
+    uint32_t phase = 0;
+
+    auto body = [&](const uint32_t slot, const uint32_t i) {   // one superblock
+        mbar_wait_a(full_a + slot * 8, phase);
+        const uint32_t src = ring_a + slot * Cfg::kSbBytes + lane * 16;
+        uint4 w[4];
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) w[qd] = lds128(src + qd * 512);
+        __syncwarp();
+        if (lane == 0 && i + NSW < n_mine) issue(i + NSW, slot);   // the words are in registers: refill the slot at once
+        bool reload = false;
+        if (slot == 0) {
+            // once per ring revolution: the shared bound read one revolution ago (never waited for), the filter's
+            // pass-rate score decays, a tighter clamped table is built when the bound has moved enough
+            bound = min(bound, gb_pending + 1);
+            load_shared_bound_now(gb_pending, sbound);
+            ctl = filt_on ? max(ctl - NSW, 0) : ctl - NSW;
+            if (filt_on) reload = bound + 3 <= 127 - static_cast<int>(f_start & 0xffu);
+            else if (ctl <= 0 && a.use_filter) { filt_on = true; ctl = 0; reload = true; }
+        }
+        GroupAcc g;
+        bool mine = false;
+        if (filt_on) {
+            FiltAcc f{f_start, f_start};
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                filt_word(w[qd].x, treg[4 * qd], f, pk);
+                filt_word(w[qd].y, treg[4 * qd + 1], f, pk);
+                filt_word(w[qd].z, treg[4 * qd + 2], f, pk);
+                filt_word(w[qd].w, treg[4 * qd + 3], f, pk);
+            }
+            if (__any_sync(0xffffffffu, filt_any(f))) {
+                ctl += 6;
+                if (ctl > 96) { filt_on = false; ctl = 256; reload = true; }   // ~1 superblock in 6 passes the filter
+#pragma unroll
+                for (int p = 0; p < M / 2; ++p) {
+                    const uint4 t0 = qtab[2 * p], t1 = qtab[2 * p + 1];
+                    const uint4& wq = w[p >> 1];
+                    scan_pair(p == 0, madd((p & 1) ? wq.z : wq.x, 0u, pk), madd((p & 1) ? wq.w : wq.y, 0u, pk), t0, t1, g, pk, bound);
+                }
+                mine = any_below(g);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < M / 2; ++p) {
+                const uint4& wq = w[p >> 1];
+                scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, treg[2 * p], treg[2 * p + 1], g, pk, bound);
+            }
+            mine = any_below(g);
+        }
+        if (__any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
+            const uint32_t sb = first + i * NW;
+            lb = bound; gb = bound - 1;
+            for (int half = 0; half < halves; ++half) {
+                const int before = *wl.count;
+                __syncwarp();
+                const bool my_turn = halves == 1 || (lane >> 4) == half;
+                if (mine && my_turn) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl, hist);
+                __syncwarp();
+                const int now = *wl.count;
+                const int hb = hist_update(hist, hist_total, hist_next, now - before, a.r, lane, sbound);
+                if (hb < gb) gb = hb;
+                if (now >= compact_at) {
+                    wl.compact(a.cap, a.r, lane, sbound);
+                    lb = *wl.bound;
+                }
+            }
+            bound = min(bound, min(lb, gb + 1));
+            reload = true;
+        }
+        if (reload) load_table();
+    };
+
+    // (Unrolling the NSW slots so that every address is base + immediate was measured 20 % SLOWER: the four copies of
+    // the body no longer fit the instruction cache — `no_instruction` stalls 0.75 per issue.)
+    uint32_t slot = 0;
+    for (uint32_t i = 0; i < n_mine; ++i) {
+        body(slot, i);
+        if (++slot == NSW) { slot = 0; phase ^= 1; }
+    }
+
+    // ---- final: one sorted list per CTA (the NW warp lists merged in the idle ring) or one per warp ----
+    wl.compact(a.cap, a.r, lane, sbound);
+    const bool cta_merge = a.n_lists == static_cast<int>(gridDim.x);
+    if (!cta_merge) {
+        store_list(wl, a.lists + (static_cast<size_t>(q) * a.n_lists + blockIdx.x * NW + warp) * a.r, a.r, lane);
+        return;
+    }
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(rings);
+    int n_sort = 64;
+    while (n_sort < NW * a.r) n_sort <<= 1;
+    __syncthreads();   // every warp has consumed its ring
+    for (int i = lane; i < a.r; i += 32) scratch[warp * a.r + i] = wl.keys[i];
+    for (int i = NW * a.r + threadIdx.x; i < n_sort; i += NW * 32) scratch[i] = kEmptyKey;
+    __syncthreads();
+    bitonic_sort_u64(scratch, n_sort, threadIdx.x, NW * 32, BlockSync());
+    uint64_t* dst = a.lists + (static_cast<size_t>(q) * a.n_lists + blockIdx.x) * a.r;
+    for (int i = threadIdx.x; i < a.r; i += NW * 32) dst[i] = scratch[i];
+}
+
+// ------------------------------------------------------------------------------------------
 // IVF scan: grid = (probe chunks, queries).  The CTA cuts the inverted lists of its probes into
 // work items of `sb_per_item` superblocks, numbered in canonical order (probe rank, position),
 // and its warps claim them from a shared counter: a warp therefore still visits its vectors in
@@ -845,7 +1047,39 @@ __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(const MergeA
     __syncthreads();
     const int total = a.L * a.r;
     const int step = kMergeCap / 2;   // inputs per round; buffer holds <= r <= cap/2 before a round
-    for (int base = 0; base < total; base += step) {
+    int first_base = 0;
+    if (a.init_bound) {
+        // Fast path: with the scan's final shared bound as the filter only r-and-a-few keys survive, so one pass
+        // without per-round barriers collects them all (148 lists x 100 keys: 15 rounds of load -> barrier -> barrier
+        // cost 87 us per step of the 1e9 scan); if they do not fit the buffer the streaming rounds below start over.
+        const unsigned long long bk0 = bound_key;
+        for (int i = tid; i < total; i += kMergeThreads) {
+            const int l = i / a.r, e = i % a.r;
+            const size_t src = a.shard_major ? (static_cast<size_t>(l) * a.nq + q) * a.r + e
+                                             : (static_cast<size_t>(q) * a.L + l) * a.r + e;
+            const uint64_t k = a.in_keys[src];
+            if (k < bk0) {
+                const int slot = atomicAdd(&count, 1);
+                if (slot < kMergeCap) { keys[slot] = k; vals[slot] = static_cast<uint32_t>(src); }
+            }
+        }
+        __syncthreads();
+        const int c = count;
+        __syncthreads();
+        if (c <= kMergeCap) {
+            int n_sort = 64;
+            while (n_sort < c) n_sort <<= 1;
+            bitonic_sort_u64_u32(keys, vals, n_sort, tid, kMergeThreads, BlockSync());
+            if (tid == 0) count = min(c, a.r);
+            __syncthreads();
+            first_base = total;   // nothing left to stream
+        } else {
+            for (int i = tid; i < kMergeCap; i += kMergeThreads) { keys[i] = kEmptyKey; vals[i] = 0; }
+            if (tid == 0) count = 0;
+            __syncthreads();
+        }
+    }
+    for (int base = first_base; base < total; base += step) {
         const unsigned long long bk = bound_key;
         for (int i = base + tid; i < min(base + step, total); i += kMergeThreads) {
             const int l = i / a.r, e = i % a.r;

@@ -142,46 +142,49 @@ struct BlockMinValues {
 // (d, c) ascending.  Two kernels: a shared-memory / register tiled distance kernel (64 queries x
 // 128 centroids per CTA, every (q,c) sum still strictly in dimension order, so results are
 // bit-identical to the oracle) and a per-query streaming selection.
-constexpr int kCoarseTQ = 64;    // queries per CTA
+constexpr int kCoarseTQ = 128;   // queries per CTA
 constexpr int kCoarseTC = 128;   // centroids per CTA
 constexpr int kCoarseTD = 16;    // dimensions per shared-memory slab
 
-// 16 x 16 threads; thread (ty, tx) owns queries 4*ty..4*ty+3 and centroids tx, tx+16, ..., tx+112
-// (a 4 x 8 register tile: 12 shared loads per 64 sub+fma).  The slab row stride of 17 words keeps
-// both the query reads (two rows per warp, broadcast) and the centroid reads (17*tx mod 32 distinct)
-// free of bank conflicts.  Every (q, c) sum still runs strictly in dimension order.
-__global__ void __launch_bounds__(256) coarse_dist_kernel(const float* __restrict__ queries, int nq, int dim,
-                                                          const float* __restrict__ centroids, int K,
-                                                          float* __restrict__ dist) {   // [nq][K]
-    __shared__ float sq[kCoarseTQ][kCoarseTD + 1];
-    __shared__ float sc[kCoarseTC][kCoarseTD + 1];
+// 16 x 16 threads; thread (ty, tx) owns queries 8*ty..8*ty+7 and centroids 8*tx..8*tx+7: an 8 x 8 register tile, fed
+// per dimension by four 128-bit shared-memory loads (the slabs are stored dimension-major, [d][query] and
+// [d][centroid], so a thread's 8 operands are contiguous; the query loads are warp broadcasts, the centroid loads
+// of the 16 tx values cover 512 contiguous bytes) for 64 sub + 64 fma.  The direct form costs two FP32 operations
+// per element and cannot use the tensor cores, but it is the arithmetic the oracle pins: every (q, c) sum runs
+// strictly in dimension order.  (The 4 x 8 tile with scalar loads this replaces ran at 58 % of the FP32 pipe.)
+__global__ void __launch_bounds__(256, 2) coarse_dist_kernel(const float* __restrict__ queries, int nq, int dim,
+                                                             const float* __restrict__ centroids, int K,
+                                                             float* __restrict__ dist) {   // [nq][K]
+    __shared__ __align__(16) float sq[kCoarseTD][kCoarseTQ + 4];
+    __shared__ __align__(16) float sc[kCoarseTD][kCoarseTC + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int q0 = blockIdx.x * kCoarseTQ, c0 = blockIdx.y * kCoarseTC;
-    float acc[4][8];
+    float acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
     for (int d0 = 0; d0 < dim; d0 += kCoarseTD) {
         const int dn = min(kCoarseTD, dim - d0);
         __syncthreads();
+        // stage: consecutive threads read consecutive dimensions of one row (coalesced), store transposed
         for (int i = tid; i < kCoarseTQ * kCoarseTD; i += 256) {
             const int r = i / kCoarseTD, c = i % kCoarseTD;
-            sq[r][c] = (q0 + r < nq && c < dn) ? queries[static_cast<size_t>(q0 + r) * dim + d0 + c] : 0.f;
+            sq[c][r] = (q0 + r < nq && c < dn) ? queries[static_cast<size_t>(q0 + r) * dim + d0 + c] : 0.f;
         }
         for (int i = tid; i < kCoarseTC * kCoarseTD; i += 256) {
             const int r = i / kCoarseTD, c = i % kCoarseTD;
-            sc[r][c] = (c0 + r < K && c < dn) ? __ldg(centroids + static_cast<size_t>(c0 + r) * dim + d0 + c) : 0.f;
+            sc[c][r] = (c0 + r < K && c < dn) ? __ldg(centroids + static_cast<size_t>(c0 + r) * dim + d0 + c) : 0.f;
         }
         __syncthreads();
+#pragma unroll 4
         for (int d = 0; d < dn; ++d) {
-            float x[4], y[8];
+            const float4 xa = *reinterpret_cast<const float4*>(&sq[d][8 * ty]), xb = *reinterpret_cast<const float4*>(&sq[d][8 * ty + 4]);
+            const float4 ya = *reinterpret_cast<const float4*>(&sc[d][8 * tx]), yb = *reinterpret_cast<const float4*>(&sc[d][8 * tx + 4]);
+            const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const float y[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = sq[4 * ty + i][d];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) y[k] = sc[tx + 16 * k][d];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float diff = __fsub_rn(x[i], y[k]);
@@ -190,13 +193,17 @@ __global__ void __launch_bounds__(256) coarse_dist_kernel(const float* __restric
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int q = q0 + 4 * ty + i;
+    for (int i = 0; i < 8; ++i) {
+        const int q = q0 + 8 * ty + i;
         if (q < nq) {
+            float* row = dist + static_cast<size_t>(q) * K + c0 + 8 * tx;
+            if (c0 + 8 * tx + 7 < K && (K & 3) == 0) {
+                *reinterpret_cast<float4*>(row) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                *reinterpret_cast<float4*>(row + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int c = c0 + tx + 16 * k;
-                if (c < K) dist[static_cast<size_t>(q) * K + c] = acc[i][k];
+                for (int k = 0; k < 8; ++k)
+                    if (c0 + 8 * tx + k < K) row[k] = acc[i][k];
             }
         }
     }
@@ -486,6 +493,273 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_probes_kernel(const P
     }
     if (tid == 0)
         a.qmax[q] = (count == a.r) ? __uint_as_float(static_cast<uint32_t>(keys[a.r - 1] >> 32)) : 3.402823466e+38f;
+}
+
+// (int) trunc of the correctly rounded quotient t / delta (what QuantizerMAX computes, db_query_4.cpp:44-55) for
+// 0 <= t < qmax - qmin, i.e. a quotient below 128.  t * (1/delta) is within ~2e-5 of the true quotient there, so unless
+// it falls within 1e-3 of an integer its floor IS the result; only those rare entries pay for the IEEE division.
+__device__ __forceinline__ int quantize_entry(float t, float delta, float inv_delta) {
+    const float p = __fmul_rn(t, inv_delta);
+    const float fl = floorf(p);
+    const float frac = __fsub_rn(p, fl);
+    if (frac > 1e-3f && frac < 0.999f) return static_cast<int>(fl);
+    return static_cast<int>(__fdiv_rn(t, delta));
+}
+
+// ---- inverted lists: the whole per-query table pipeline in ONE kernel, tables resident in shared memory ----------
+// grid = queries, 256 threads.  For one query: residual -> (rotation) -> float tables of all ma probes (shared memory,
+// ma * M * 64 bytes) -> float ADC of the probes' keep-prefixes against them, r-th smallest = qmax (block radix
+// select) -> qmin = min entry (clamped at 0) -> int8 tables (written once to global memory for the scan, kept in
+// shared memory too) -> int8 distances of the same prefix vectors -> the query's shared bound (r-th smallest).
+// Replaces tables_kernel + prefix_scan(_probes)_kernel + quantize_kernel + prefix_hist_kernel + prefix_bound_kernel and
+// their round trips of the float tables through HBM (config 5: 3.9 GB per 10 000-query batch).  Every float operation
+// is the one the separate kernels (and oracle/qadc_oracle.c) perform, in the same order: bit-identical results.
+struct IvfPrepArgs {
+    const float* queries; int dim;
+    const float* codebooks; const float* rotation; const float* centroids;
+    const int32_t* assign; int ma, r;
+    const uint8_t* starts; const uint64_t* start_off; const uint32_t* start_size;
+    float* tables_out;      // [nq][ma][M*16] or null
+    int8_t* qtables;        // [nq][ma][M*16]
+    float* qmin; float* qmax; int* shared_bound; int* err;
+};
+
+__host__ __device__ inline size_t ivf_prep_smem_bytes(int m, int ma, int dim) {
+    size_t b = static_cast<size_t>(ma) * m * 16 * 4;          // float tables, later the int8 tables in their first quarter
+    b += static_cast<size_t>(8) * 2 * dim * 4;                // per-warp residual + rotated copy
+    b += static_cast<size_t>(ma + 1) * 4 + static_cast<size_t>(ma) * 8;   // prefix offsets, first prefix vector of each probe
+    b += 2 * kSelCap * 4;                                     // value buffers of the radix select
+    return b + 64;
+}
+
+template <int M, int DSQ>
+__global__ void __launch_bounds__(256) ivf_prepare_kernel(const IvfPrepArgs a) {
+    constexpr int CS = M / 2, TE = M * 16;
+    extern __shared__ __align__(16) uint8_t ps[];
+    float* tab = reinterpret_cast<float*>(ps);                                   // [ma][TE]
+    float* resbuf = tab + static_cast<size_t>(a.ma) * TE;                         // [8][2*dim]
+    uint64_t* pfirst = reinterpret_cast<uint64_t*>(resbuf + 16 * a.dim);          // [ma] (8-byte aligned: TE, dim*16 floats)
+    int* poff = reinterpret_cast<int*>(pfirst + a.ma);                           // [ma + 1]
+    uint32_t* vb0 = reinterpret_cast<uint32_t*>(poff + a.ma + 1);
+    uint32_t* vb1 = vb0 + kSelCap;
+    __shared__ int count, hist[256], state[2];
+    __shared__ unsigned int bound;
+    __shared__ float red[8];
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dim = a.dim, ma = a.ma;
+    const float* query = a.queries + static_cast<size_t>(q) * dim;
+
+    // ---- 1. float tables (the arithmetic of tables_kernel) ----
+    // One warp per probe, no block barrier: lane l owns the table entries e = l, l + 32, ... (sub-quantiser e >> 4,
+    // centroid e & 15) of every probe its warp handles, so (for the specialised sub-vector sizes) its codebook rows
+    // live in registers for the whole query; the probe's residual sits in the warp's shared-memory slot; the next
+    // probe's centroid components are prefetched while the current entries are computed.
+    float local_min = 3.402823466e+38f;
+    {
+        constexpr int EPL = TE / 32;                  // entries per lane and probe: 8 (16x4) or 16 (32x4)
+        constexpr bool kRegCb = DSQ != 0 && EPL * DSQ <= 64;
+        constexpr int CBR = kRegCb ? DSQ : 1;
+        const int dsq = DSQ ? DSQ : dim / M, blocks = dsq / 8, rem = dsq % 8;
+        float cbr[kRegCb ? EPL : 1][CBR];
+        if constexpr (kRegCb) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k)
+#pragma unroll
+                for (int l = 0; l < DSQ; ++l) cbr[k][l] = __ldg(a.codebooks + static_cast<size_t>(lane + 32 * k) * DSQ + l);
+        }
+        float* res = resbuf + static_cast<size_t>(warp) * 2 * dim;
+        float* rot = res + dim;
+        const int32_t* my_assign = a.assign + static_cast<size_t>(q) * ma;
+        constexpr int PF = 8;                          // prefetched centroid components per lane (dim <= 256)
+        const bool pf = dim <= 32 * PF;
+        float qv[PF], cn[PF];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            const int d = lane + 32 * i;
+            qv[i] = (pf && d < dim) ? query[d] : 0.f;
+            cn[i] = (pf && d < dim && warp < ma) ? __ldg(a.centroids + static_cast<size_t>(my_assign[warp]) * dim + d) : 0.f;
+        }
+        for (int a_i = warp; a_i < ma; a_i += 8) {
+            const size_t qa = static_cast<size_t>(q) * ma + a_i;
+            __syncwarp();   // every lane is done with the previous probe's residual
+            if (pf) {
+#pragma unroll
+                for (int i = 0; i < PF; ++i) {
+                    const int d = lane + 32 * i;
+                    if (d < dim) res[d] = __fsub_rn(qv[i], cn[i]);
+                }
+                if (a_i + 8 < ma) {
+                    const float* cnext = a.centroids + static_cast<size_t>(my_assign[a_i + 8]) * dim;
+#pragma unroll
+                    for (int i = 0; i < PF; ++i) {
+                        const int d = lane + 32 * i;
+                        if (d < dim) cn[i] = __ldg(cnext + d);
+                    }
+                }
+            } else {
+                const float* cent = a.centroids + static_cast<size_t>(my_assign[a_i]) * dim;
+                for (int i = lane; i < dim; i += 32) res[i] = __fsub_rn(query[i], __ldg(cent + i));
+            }
+            __syncwarp();
+            const float* x = res;
+            if (a.rotation) {
+                for (int j = lane; j < dim; j += 32) {
+                    const float* row = a.rotation + static_cast<size_t>(j) * dim;
+                    float s = 0.f;
+                    for (int k = 0; k < dim; ++k) s = __fmaf_rn(res[k], __ldg(row + k), s);
+                    rot[j] = s;
+                }
+                __syncwarp();
+                x = rot;
+            }
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const int e = lane + 32 * k;
+                const float* xa = x + (e >> 4) * dsq;
+                const float* b = a.codebooks + static_cast<size_t>(e) * dsq;
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int bl = 0; bl < blocks; ++bl) {
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) {
+                        const float bv = kRegCb ? cbr[kRegCb ? k : 0][(bl * 8 + l) % CBR] : __ldg(b + bl * 8 + l);
+                        const float diff = __fsub_rn(xa[bl * 8 + l], bv);
+                        acc[l] = __fmaf_rn(diff, diff, acc[l]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = __fadd_rn(acc[i], acc[i + 4]);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) acc[i] = __fadd_rn(acc[i], acc[i + 2]);
+                float norm = __fadd_rn(acc[0], acc[1]);
+#pragma unroll
+                for (int i = 0; i < rem; ++i) {
+                    const float bv = kRegCb ? cbr[kRegCb ? k : 0][(blocks * 8 + i) % CBR] : __ldg(b + blocks * 8 + i);
+                    const float diff = __fsub_rn(bv, xa[blocks * 8 + i]);
+                    norm = __fmaf_rn(diff, diff, norm);
+                }
+                tab[static_cast<size_t>(a_i) * TE + e] = norm;
+                if (a.tables_out) a.tables_out[qa * TE + e] = norm;
+                local_min = fminf(local_min, norm);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) local_min = fminf(local_min, __shfl_xor_sync(0xffffffffu, local_min, o));
+    if (lane == 0) red[warp] = local_min;
+    // ---- 2. where each probe's keep-prefix starts in the flattened item space ----
+    if (warp == 0) {
+        int running = 0;
+        for (int base = 0; base < ma; base += 32) {
+            const int i = base + lane;
+            int n = 0;
+            if (i < ma) {
+                const int p = a.assign[static_cast<size_t>(q) * ma + i];
+                n = static_cast<int>(a.start_size[p]);
+                pfirst[i] = a.start_off[p];
+            }
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (i < ma) poff[i + 1] = running + incl;
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) poff[0] = 0;
+    }
+    BlockMinValues top{{vb0, vb1}, &count, hist, state, &bound, 0};
+    top.init(tid);   // (a block barrier: tables, red[], poff[] are visible from here on)
+    const int total = poff[ma];
+    auto locate = [&](int item, int& probe, uint32_t (&w)[CS / 4]) {   // probe of a flattened item and its code words
+        int lo = 0, hi = ma;   // poff[lo] <= item < poff[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (poff[mid] <= item) lo = mid; else hi = mid;
+        }
+        probe = lo;
+        const uint8_t* c = a.starts + (pfirst[lo] + static_cast<uint32_t>(item - poff[lo])) * CS;
+        if constexpr (CS == 8) {
+            const uint2 v = *reinterpret_cast<const uint2*>(c);
+            w[0] = v.x; w[1] = v.y;
+        } else {
+            const uint4 v = *reinterpret_cast<const uint4*>(c);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        }
+    };
+    // ---- 3. float ADC of the prefixes (scan_4, query_common.hpp:59-90) -> qmax = r-th smallest ----
+    for (int base = 0; base < total; base += kSelCap / 2) {
+        for (int item = base + tid; item < min(base + kSelCap / 2, total); item += kSelThreads) {
+            int probe;
+            uint32_t w[CS / 4];
+            locate(item, probe, w);
+            const float* t = tab + static_cast<size_t>(probe) * TE;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < M; ++j) s = __fadd_rn(s, t[j * 16 + ((w[j >> 3] >> (4 * (j & 7))) & 15u)]);
+            top.push(__float_as_uint(s));
+        }
+        top.maybe_compact(a.r, tid, false);
+    }
+    top.maybe_compact(a.r, tid, true);
+    const float qmax = (count >= a.r) ? __uint_as_float(bound) : 3.402823466e+38f;
+    // ---- 4. bounds + int8 tables (QuantizerMAX, db_query_4.cpp:37-71, :256-284) ----
+    float qmin = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) qmin = fminf(qmin, red[w]);
+    if (qmin < 0.f) qmin = 0.f;
+    if (tid == 0) {
+        a.qmin[q] = qmin;
+        a.qmax[q] = qmax;
+        if (qmax > 1e30f) atomicExch(a.err, 1);
+    }
+    const float delta = __fdiv_rn(__fsub_rn(qmax, qmin), 127.0f);
+    const float inv_delta = __fdiv_rn(1.0f, delta);
+    int8_t* itab = reinterpret_cast<int8_t*>(tab);   // the int8 tables take over the first quarter of the float tables
+    const int entries = ma * TE;
+    int8_t* gq = a.qtables + static_cast<size_t>(q) * entries;
+    for (int base = 0; base < entries; base += 4 * kSelThreads) {   // a chunk's bytes land below the floats still to be read
+        const int e = base + 4 * tid;
+        char4 out = make_char4(0, 0, 0, 0);
+        if (e < entries) {
+            const float4 v = *reinterpret_cast<const float4*>(tab + e);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            int8_t qv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x = vv[i] < 0.f ? 0.f : vv[i];
+                qv[i] = (x >= qmax) ? static_cast<int8_t>(127) : static_cast<int8_t>(quantize_entry(__fsub_rn(x, qmin), delta, inv_delta));
+            }
+            out = make_char4(qv[0], qv[1], qv[2], qv[3]);
+        }
+        __syncthreads();
+        if (e < entries) {
+            *reinterpret_cast<char4*>(itab + e) = out;
+            *reinterpret_cast<char4*>(gq + e) = out;
+        }
+    }
+    // ---- 5. the query's shared bound: r-th smallest int8 distance among the same prefix vectors ----
+    hist[tid] = 0;
+    __syncthreads();
+    for (int item = tid; item < total; item += kSelThreads) {
+        int probe;
+        uint32_t w[CS / 4];
+        locate(item, probe, w);
+        const int8_t* t = itab + static_cast<size_t>(probe) * TE;
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) sum += t[j * 16 + ((w[j >> 3] >> (4 * (j & 7))) & 15u)];
+        atomicAdd(&hist[min(sum, 127)], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int cum = 0, b = 126;   // fewer than r prefix vectors below 127: everything below 127 may pass
+        for (int d = 0; d < 127; ++d) {
+            cum += hist[d];
+            if (cum >= a.r) { b = d; break; }
+        }
+        a.shared_bound[q] = b;
+    }
 }
 
 // ---- PQ encoder ("next" row N1) ---------------------------------------------------------------

@@ -119,6 +119,28 @@ def test_flat_scan_with_tables_bit_exact(qadc, oracle, n, m, nq, r, qb):
     ix.close()
 
 
+@pytest.mark.parametrize("n,nq,r,chunks,filt", [(300, 3, 10, 0, 1), (70001, 5, 100, 0, 1), (123457, 4, 100, 3, 1), (123457, 4, 100, 64, 0),
+                                                (1000, 2, 700, 0, 1), (50, 2, 100, 0, 1), (400000, 6, 100, 0, 1), (400000, 3, 1, 5, 1)])
+def test_flat_warp_ring_kernel_bit_exact(qadc, oracle, n, nq, r, chunks, filt):
+    """scan_flat_wr_kernel (per-warp TMA rings, option flat_ring = 1): canonical top-r bit-exact against the oracle, with
+    and without the pre-filter, across chunkings, tiny and ragged databases, r = 1 and the two-pass emit (r = 700)."""
+    rng = np.random.default_rng(n + nq + r)
+    m = 16
+    codes = synth.make_codes(rng, n, m)
+    ix = flat_index(qadc, 128, m, synth.make_pq(rng, 128, m), codes, 1.0)
+    ix.set_option("flat_ring", 1)
+    ix.set_option("flat_qb", 1)
+    ix.set_option("flat_chunks", chunks)
+    ix.set_option("flat_filter", filt)
+    qt = synth.make_qtables(rng, (nq, 1), m, hi=14, p_sat=0.05)
+    ids, d, cnt = ix.scan_with_tables(np.zeros((nq, 1), np.int32), qt, r)
+    offsets = np.array([0, n], np.int64)
+    for q in range(nq):
+        e_ids, e_d, e_cnt, _ = oracle.scan_with_tables(codes, None, offsets, np.zeros(1, np.int32), qt[q], r)
+        assert cnt[q] == e_cnt and np.array_equal(d[q], e_d) and np.array_equal(ids[q], e_ids)
+    ix.close()
+
+
 @pytest.mark.parametrize("chunks", [1, 3, 64])
 def test_flat_scan_independent_of_chunking(qadc, oracle, chunks):
     rng = np.random.default_rng(99)
@@ -640,6 +662,40 @@ def test_gpu_ivf_assign_encode(qadc, oracle):
     assert np.array_equal(assign, e_assign[:, 0])
     resid = (x - cents[assign]).astype(np.float32)
     assert np.array_equal(codes, oracle.encode(resid, m, cb))
+    ix.close()
+
+
+@pytest.mark.parametrize("m,dim,K,ma,opq", [(16, 128, 300, 24, False), (32, 96, 64, 64, False), (16, 96, 500, 128, True),
+                                            (16, 64, 40, 3, False)])
+def test_ivf_fused_table_pipeline_equals_separate_kernels(qadc, oracle, m, dim, K, ma, opq):
+    """ivf_prepare_kernel (tables, keep-prefix ADC, bounds, int8 tables and the shared-bound seed of a query in one
+    kernel, tables resident in shared memory) against the separate kernels it replaces and against the oracle:
+    assignment, float tables, qmin, qmax, int8 tables and search results bit for bit."""
+    rng = np.random.default_rng(1000 + m + K)
+    n, nq, r, keep = 60000, 33, 100, 0.08   # 3 probes, one of them possibly an empty list: still >= r prefix vectors
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(1, K - 1))
+    q = synth.make_queries(rng, nq, dim)
+    rot = np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32) if opq else None
+    ix = ivf_index(qadc, dim, m, cb, cents, codes, labels, offsets, keep, rot)
+    outs = []
+    for fused in (2, 0):   # 2: whenever the tables of a query fit shared memory (1 = only while two CTAs fit an SM)
+        ix.set_option("ivf_fused", fused)
+        t = ix.build_tables(q, ma, r)
+        assert t["rc"] == 0
+        outs.append((t, ix.search(q, ma, r)))
+    (t1, s1), (t0, s0) = outs
+    for k in ("assign", "tables", "qmin", "qmax", "qtables"):
+        assert np.array_equal(t1[k], t0[k]), k
+    for a, b in zip(s1, s0):
+        assert np.array_equal(a, b)
+    db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=keep, offsets=offsets)
+    if opq:
+        db["rotation"] = rot
+    exp = oracle.search(db, q, ma, r)
+    assert np.array_equal(t1["tables"], exp["tables"]) and np.array_equal(t1["qtables"], exp["qtables"])
+    assert np.array_equal(s1[0], exp["ids"]) and np.array_equal(s1[1], exp["d"]) and np.array_equal(s1[2], exp["count"])
     ix.close()
 
 
