@@ -74,7 +74,7 @@ struct qadc_ctx {
     int* d_err = nullptr;
     int* h_err = nullptr;   // pinned
     // options / accounting
-    long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1, opt_ivf_fused = 1, opt_flat_ring = 0;
+    long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1, opt_ivf_fused = 1, opt_flat_ring = 1;
     bool sbound_seeded = false;   // the fused inverted-list table kernel already wrote the shared bounds of this batch
     int ivf_sb_per_item = 8;   // superblocks per work item of the IVF scan (option "ivf_sb_per_item")
     int launches = 0;
