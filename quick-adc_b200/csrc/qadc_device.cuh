@@ -92,6 +92,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+// One lane of a converged warp (elect.sync): unlike `lane == 0` the compiler knows the branch holds a single thread,
+// so a TMA issue inside it needs no ELECT / R2UR.BROADCAST loop around the uniform-register operands.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t leader;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(leader));
+    return leader != 0;
+}
 // keeps a loop-invariant value in a register instead of letting the compiler rematerialise it
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
 

@@ -652,15 +652,26 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
     load_table();
     int gb_pending = bound - 1;
     uint32_t phase = 0;
+    uint32_t ring_r = ring_a + lane * 16, ring_w = ring_a, full_r = full_a;   // kept in registers: the compiler otherwise
+    pin(ring_r); pin(ring_w); pin(full_r);                                     // rebuilds them from the shared-window base
+    const uint8_t* refill = src0 + static_cast<size_t>(NSW) * (NW * Cfg::kSbBytes);   // source of superblock i + NSW
+    const uint32_t n_refill = n_mine > NSW ? n_mine - NSW : 0;                          // superblocks that have a successor to prefetch
 
     auto body = [&](const uint32_t slot, const uint32_t i) {   // one superblock
-        mbar_wait_a(full_a + slot * 8, phase);
-        const uint32_t src = ring_a + slot * Cfg::kSbBytes + lane * 16;
+        mbar_wait_a(full_r + slot * 8, phase);
+        const uint32_t src = ring_r + slot * Cfg::kSbBytes;
         uint4 w[4];
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) w[qd] = lds128(src + qd * 512);
         __syncwarp();
-        if (lane == 0 && i + NSW < n_mine) issue(i + NSW, slot);   // the words are in registers: refill the slot at once
+        if (i < n_refill && elect_one()) {   // the words are in registers: refill the slot at once
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_r + slot * 8), "r"(Cfg::kSbBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             ring_w + slot * Cfg::kSbBytes),
+                         "l"(refill), "r"(Cfg::kSbBytes), "r"(full_r + slot * 8)
+                         : "memory");
+        }
+        refill += NW * Cfg::kSbBytes;
         bool reload = false;
         if (slot == 0) {
             // once per ring revolution: the shared bound read one revolution ago (never waited for), the filter's
@@ -671,37 +682,8 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
             if (filt_on) reload = bound + 3 <= 127 - static_cast<int>(f_start & 0xffu);
             else if (ctl <= 0 && a.use_filter) { filt_on = true; ctl = 0; reload = true; }
         }
-        GroupAcc g;
-        bool mine = false;
-        if (filt_on) {
-            FiltAcc f{f_start, f_start};
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                filt_word(w[qd].x, treg[4 * qd], f, pk);
-                filt_word(w[qd].y, treg[4 * qd + 1], f, pk);
-                filt_word(w[qd].z, treg[4 * qd + 2], f, pk);
-                filt_word(w[qd].w, treg[4 * qd + 3], f, pk);
-            }
-            if (__any_sync(0xffffffffu, filt_any(f))) {
-                ctl += 6;
-                if (ctl > 96) { filt_on = false; ctl = 256; reload = true; }   // ~1 superblock in 6 passes the filter
-#pragma unroll
-                for (int p = 0; p < M / 2; ++p) {
-                    const uint4 t0 = qtab[2 * p], t1 = qtab[2 * p + 1];
-                    const uint4& wq = w[p >> 1];
-                    scan_pair(p == 0, madd((p & 1) ? wq.z : wq.x, 0u, pk), madd((p & 1) ? wq.w : wq.y, 0u, pk), t0, t1, g, pk, bound);
-                }
-                mine = any_below(g);
-            }
-        } else {
-#pragma unroll
-            for (int p = 0; p < M / 2; ++p) {
-                const uint4& wq = w[p >> 1];
-                scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, treg[2 * p], treg[2 * p + 1], g, pk, bound);
-            }
-            mine = any_below(g);
-        }
-        if (__any_sync(0xffffffffu, mine)) {   // rare: some vector of the superblock is a candidate
+        // rare: some vector of the superblock is a candidate
+        auto emit = [&](const GroupAcc& g, const bool mine) {
             const uint32_t sb = first + i * NW;
             lb = bound; gb = bound - 1;
             for (int half = 0; half < halves; ++half) {
@@ -720,6 +702,40 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
             }
             bound = min(bound, min(lb, gb + 1));
             reload = true;
+        };
+        if (filt_on) {
+            FiltAcc f{f_start, f_start};
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                filt_word(w[qd].x, treg[4 * qd], f, pk);
+                filt_word(w[qd].y, treg[4 * qd + 1], f, pk);
+                filt_word(w[qd].z, treg[4 * qd + 2], f, pk);
+                filt_word(w[qd].w, treg[4 * qd + 3], f, pk);
+            }
+            if (__any_sync(0xffffffffu, filt_any(f))) {
+                // some vector may be below the bound: exact sums, table read from shared memory (the words pass through an
+                // opaque IMAD so that ptxas does not keep the filter's selector registers alive for reuse here)
+                ctl += 6;
+                if (ctl > 96) { filt_on = false; ctl = 256; reload = true; }   // ~1 superblock in 6 passes the filter
+                GroupAcc g;
+#pragma unroll
+                for (int p = 0; p < M / 2; ++p) {
+                    const uint4 t0 = qtab[2 * p], t1 = qtab[2 * p + 1];
+                    const uint4& wq = w[p >> 1];
+                    scan_pair(p == 0, madd((p & 1) ? wq.z : wq.x, 0u, pk), madd((p & 1) ? wq.w : wq.y, 0u, pk), t0, t1, g, pk, bound);
+                }
+                const bool mine = any_below(g);
+                if (__any_sync(0xffffffffu, mine)) emit(g, mine);
+            }
+        } else {
+            GroupAcc g;
+#pragma unroll
+            for (int p = 0; p < M / 2; ++p) {
+                const uint4& wq = w[p >> 1];
+                scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, treg[2 * p], treg[2 * p + 1], g, pk, bound);
+            }
+            const bool mine = any_below(g);
+            if (__any_sync(0xffffffffu, mine)) emit(g, mine);
         }
         if (reload) load_table();
     };
