@@ -1069,14 +1069,23 @@ __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(const MergeA
         // without per-round barriers collects them all (148 lists x 100 keys: 15 rounds of load -> barrier -> barrier
         // cost 87 us per step of the 1e9 scan); if they do not fit the buffer the streaming rounds below start over.
         const unsigned long long bk0 = bound_key;
-        for (int i = tid; i < total; i += kMergeThreads) {
-            const int l = i / a.r, e = i % a.r;
-            const size_t src = a.shard_major ? (static_cast<size_t>(l) * a.nq + q) * a.r + e
-                                             : (static_cast<size_t>(q) * a.L + l) * a.r + e;
-            const uint64_t k = a.in_keys[src];
-            if (k < bk0) {
-                const int slot = atomicAdd(&count, 1);
-                if (slot < kMergeCap) { keys[slot] = k; vals[slot] = static_cast<uint32_t>(src); }
+        constexpr int U = 8;   // loads in flight per thread: the keys come from L2 / HBM, one dependent load per turn is latency-bound
+        for (int base = tid; base < total; base += kMergeThreads * U) {
+            uint64_t k[U];
+            size_t src[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kMergeThreads;
+                const int l = i / a.r, e = i % a.r;
+                src[u] = a.shard_major ? (static_cast<size_t>(l) * a.nq + q) * a.r + e : (static_cast<size_t>(q) * a.L + l) * a.r + e;
+                k[u] = i < total ? a.in_keys[src[u]] : kEmptyKey;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k[u] < bk0) {
+                    const int slot = atomicAdd(&count, 1);
+                    if (slot < kMergeCap) { keys[slot] = k[u]; vals[slot] = static_cast<uint32_t>(src[u]); }
+                }
             }
         }
         __syncthreads();
