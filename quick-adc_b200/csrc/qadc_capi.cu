@@ -173,12 +173,12 @@ int launch_flat(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
     return QADC_OK;
 }
 
-template <int NW, int NSW>
+template <int NW, int NSW, int NPS>
 int launch_flat_wr(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
-    using Cfg = WarpRingCfg<NW, NSW>;
+    using Cfg = WarpRingCfg<NW, NSW, NPS>;
     const size_t smem = Cfg::smem_bytes(a.cap);
     if (smem > kMaxSmem) return QADC_ENOMEM;
-    auto kern = scan_flat_wr_kernel<NW, NSW>;
+    auto kern = scan_flat_wr_kernel<NW, NSW, NPS>;
     QCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     dim3 grid(chunks, a.nq);
     kern<<<grid, Cfg::kThreads, smem, ctx->stream>>>(a);
@@ -191,18 +191,21 @@ struct FlatVariant {
     int m, qb, nw, ns;
     int (*launch)(qadc_ctx*, FlatScanArgs, int);
     size_t (*smem)(int cap);
-    int wr;   // 1: per-warp rings (scan_flat_wr_kernel), chosen with option "flat_ring"
+    int wr;   // > 0: per-warp rings (scan_flat_wr_kernel), chosen with option "flat_ring"; the value is the superblocks per ring slot
 };
 #define QADC_FLAT_VARIANT(M, QB, NW, NS) {M, QB, NW, NS, launch_flat<M, QB, NW, NS>, FlatCfg<M, QB, NW, NS>::smem_bytes, 0}
 #ifndef QADC_NWR
 #define QADC_NWR 16   // warps of the per-warp-ring kernel
 #endif
 #ifndef QADC_NSWR
-#define QADC_NSWR 4   // superblocks in flight per warp
+#define QADC_NSWR 4   // ring slots per warp
+#endif
+#ifndef QADC_NPSR
+#define QADC_NPSR 1   // superblocks per ring slot (one TMA copy and one barrier per slot)
 #endif
 // in order of preference per (m, qb): 15 consumer warps when the lists fit, else 8
 const FlatVariant kFlatVariants[] = {
-    {16, 1, QADC_NWR, QADC_NSWR, launch_flat_wr<QADC_NWR, QADC_NSWR>, WarpRingCfg<QADC_NWR, QADC_NSWR>::smem_bytes, 1},
+    {16, 1, QADC_NWR, QADC_NSWR * QADC_NPSR, launch_flat_wr<QADC_NWR, QADC_NSWR, QADC_NPSR>, WarpRingCfg<QADC_NWR, QADC_NSWR, QADC_NPSR>::smem_bytes, QADC_NPSR},
     QADC_FLAT_VARIANT(16, 1, QADC_NW1, QADC_NS1), QADC_FLAT_VARIANT(16, 1, 8, 4),
     QADC_FLAT_VARIANT(16, 2, 15, 3), QADC_FLAT_VARIANT(16, 2, 8, 4),
     QADC_FLAT_VARIANT(16, 4, 15, 3), QADC_FLAT_VARIANT(16, 4, 8, 4),
@@ -232,13 +235,13 @@ int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
         }
     if (!pl.v) return fail(ctx, QADC_EINVAL, "r too large for the scan kernel's shared-memory lists");
     const uint32_t n_sb = static_cast<uint32_t>(ctx->total_sb);
-    const int tile_sb = pl.nw;
+    const int tile_sb = pl.nw * std::max(1, pl.v->wr);
     const int qgroups = (nq + pl.qb - 1) / pl.qb;
     long chunks = ctx->opt_flat_chunks;
     // up to ~16 waves of CTAs (the tail of the last wave then costs a few percent), fewer for small
     // shards so that a CTA still streams >= ~600 tiles and its ~20 us of setup/merge stays small
     if (chunks <= 0) {
-        const long n_tiles = (n_sb + tile_sb - 1) / tile_sb;
+        const long n_tiles = (n_sb + pl.nw - 1) / pl.nw;
         int waves = 16;
         while (waves > 1 && n_tiles / std::max<long>(1, (static_cast<long>(waves) * ctx->sm_count + qgroups - 1) / qgroups) < 600)
             waves >>= 1;

@@ -560,19 +560,20 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 // barrier with HBM at 86 % of its measured peak — and the 16th warp computes instead of producing.
 // The lookup / pre-filter / candidate machinery is the register-table path of scan_flat_kernel.
 // ------------------------------------------------------------------------------------------
-template <int NW, int NSW>
+template <int NW, int NSW, int NPS = 1>
 struct WarpRingCfg {
     static constexpr int M = 16, kQuads = 4, kSbBytes = 2048;
-    static constexpr int kRingBytes = NW * NSW * kSbBytes;
+    static constexpr int kSlotBytes = NPS * kSbBytes;   // a ring slot holds NPS consecutive superblocks (one TMA copy, one barrier)
+    static constexpr int kRingBytes = NW * NSW * kSlotBytes;
     static constexpr int kThreads = NW * 32;
     // rings | table | per-warp filter tables | barriers | histogram + counters | list counts/bounds, rounded to 16 bytes
     static constexpr int kFixedBytes = ((kRingBytes + M * 16 + NW * M * 16 + NW * NSW * 8 + (128 + 2) * 4 + NW * 8) + 15) / 16 * 16;
     static size_t smem_bytes(int cap) { return static_cast<size_t>(kFixedBytes) + static_cast<size_t>(NW) * cap * 8; }
 };
 
-template <int NW, int NSW>
+template <int NW, int NSW, int NPS = 1>
 __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScanArgs a) {
-    using Cfg = WarpRingCfg<NW, NSW>;
+    using Cfg = WarpRingCfg<NW, NSW, NPS>;
     constexpr int M = 16;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* rings = smem;                                                                 // [NW][NSW][2048]
@@ -608,17 +609,25 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
     const int compact_at = min(a.cap - kSbVec / halves, 2 * a.r);
     int* sbound = a.shared_bound + q;
 
-    // this warp's superblocks: sb0 + warp + i * NW, i < n_mine
-    const uint32_t first = sb0 + warp;
-    const uint32_t n_mine = (first < sb1) ? (sb1 - first + NW - 1) / NW : 0;
-    const uint32_t ring_a = smem_u32(rings) + warp * (NSW * Cfg::kSbBytes);
+    // this warp's units (NPS consecutive superblocks each): unit warp + i * NW of the chunk, i < n_mine; only the last
+    // unit of the database can be short
+    const uint32_t n_units = (sb1 - sb0 + NPS - 1) / NPS;
+    const uint32_t first = sb0 + warp * NPS;
+    const uint32_t n_mine = (static_cast<uint32_t>(warp) < n_units) ? (n_units - warp + NW - 1) / NW : 0;
+    const uint32_t ring_a = smem_u32(rings) + warp * (NSW * Cfg::kSlotBytes);
     const uint32_t full_a = smem_u32(full) + warp * (NSW * 8);
     const uint8_t* src0 = a.codes + static_cast<size_t>(first) * Cfg::kSbBytes;
-    auto issue = [&](uint32_t i, uint32_t slot) {   // elected lane: arm the slot's barrier and start the copy of superblock i
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_a + slot * 8), "r"(Cfg::kSbBytes) : "memory");
+    auto unit_bytes = [&](uint32_t i) -> uint32_t {   // bytes of this warp's unit i
+        if (NPS == 1) return Cfg::kSbBytes;
+        const uint32_t sb = first + i * (NW * NPS);
+        return min(static_cast<uint32_t>(NPS), sb1 - sb) * Cfg::kSbBytes;
+    };
+    auto issue = [&](uint32_t i, uint32_t slot) {   // elected lane: arm the slot's barrier and start the copy of unit i
+        const uint32_t bytes = unit_bytes(i);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_a + slot * 8), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         ring_a + slot * Cfg::kSbBytes),
-                     "l"(src0 + static_cast<size_t>(i) * (NW * Cfg::kSbBytes)), "r"(Cfg::kSbBytes), "r"(full_a + slot * 8)
+                         ring_a + slot * Cfg::kSlotBytes),
+                     "l"(src0 + static_cast<size_t>(i) * (NW * Cfg::kSlotBytes)), "r"(bytes), "r"(full_a + slot * 8)
                      : "memory");
     };
     if (lane == 0)
@@ -654,90 +663,98 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
     uint32_t phase = 0;
     uint32_t ring_r = ring_a + lane * 16, ring_w = ring_a, full_r = full_a;   // kept in registers: the compiler otherwise
     pin(ring_r); pin(ring_w); pin(full_r);                                     // rebuilds them from the shared-window base
-    const uint8_t* refill = src0 + static_cast<size_t>(NSW) * (NW * Cfg::kSbBytes);   // source of superblock i + NSW
-    const uint32_t n_refill = n_mine > NSW ? n_mine - NSW : 0;                          // superblocks that have a successor to prefetch
+    const uint8_t* refill = src0 + static_cast<size_t>(NSW) * (NW * Cfg::kSlotBytes);   // source of unit i + NSW
+    const uint32_t n_refill = n_mine > NSW ? n_mine - NSW : 0;                            // units that have a successor to prefetch
 
-    auto body = [&](const uint32_t slot, const uint32_t i) {   // one superblock
+    auto body = [&](const uint32_t slot, const uint32_t i) {   // one unit = NPS superblocks behind one barrier
         mbar_wait_a(full_r + slot * 8, phase);
-        const uint32_t src = ring_r + slot * Cfg::kSbBytes;
-        uint4 w[4];
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) w[qd] = lds128(src + qd * 512);
-        __syncwarp();
-        if (i < n_refill && elect_one()) {   // the words are in registers: refill the slot at once
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_r + slot * 8), "r"(Cfg::kSbBytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             ring_w + slot * Cfg::kSbBytes),
-                         "l"(refill), "r"(Cfg::kSbBytes), "r"(full_r + slot * 8)
-                         : "memory");
-        }
-        refill += NW * Cfg::kSbBytes;
         bool reload = false;
-        if (slot == 0) {
-            // once per ring revolution: the shared bound read one revolution ago (never waited for), the filter's
-            // pass-rate score decays, a tighter clamped table is built when the bound has moved enough
-            bound = min(bound, gb_pending + 1);
-            load_shared_bound_now(gb_pending, sbound);
-            ctl = filt_on ? max(ctl - NSW, 0) : ctl - NSW;
-            if (filt_on) reload = bound + 3 <= 127 - static_cast<int>(f_start & 0xffu);
-            else if (ctl <= 0 && a.use_filter) { filt_on = true; ctl = 0; reload = true; }
-        }
-        // rare: some vector of the superblock is a candidate
-        auto emit = [&](const GroupAcc& g, const bool mine) {
-            const uint32_t sb = first + i * NW;
-            lb = bound; gb = bound - 1;
-            for (int half = 0; half < halves; ++half) {
-                const int before = *wl.count;
+        const uint32_t nsb = (NPS == 1) ? 1u : min(static_cast<uint32_t>(NPS), sb1 - (first + i * (NW * NPS)));
+#pragma unroll 1
+        for (uint32_t h = 0; h < nsb; ++h) {
+            const uint32_t src = ring_r + slot * Cfg::kSlotBytes + h * Cfg::kSbBytes;
+            uint4 w[4];
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) w[qd] = lds128(src + qd * 512);
+            if (NPS == 1 || h + 1 == nsb) {
                 __syncwarp();
-                const bool my_turn = halves == 1 || (lane >> 4) == half;
-                if (mine && my_turn) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl, hist);
-                __syncwarp();
-                const int now = *wl.count;
-                const int hb = hist_update(hist, hist_total, hist_next, now - before, a.r, lane, sbound);
-                if (hb < gb) gb = hb;
-                if (now >= compact_at) {
-                    wl.compact(a.cap, a.r, lane, sbound);
-                    lb = *wl.bound;
+                if (i < n_refill && elect_one()) {   // the unit's words are in registers: refill the slot at once
+                    const uint32_t bytes = unit_bytes(i + NSW);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_r + slot * 8), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     ring_w + slot * Cfg::kSlotBytes),
+                                 "l"(refill), "r"(bytes), "r"(full_r + slot * 8)
+                                 : "memory");
                 }
             }
-            bound = min(bound, min(lb, gb + 1));
-            reload = true;
-        };
-        if (filt_on) {
-            FiltAcc f{f_start, f_start};
+            // rare: some vector of the superblock is a candidate
+            auto emit = [&](const GroupAcc& g, const bool mine) {
+                const uint32_t sb = first + i * (NW * NPS) + h;
+                lb = bound; gb = bound - 1;
+                for (int half = 0; half < halves; ++half) {
+                    const int before = *wl.count;
+                    __syncwarp();
+                    const bool my_turn = halves == 1 || (lane >> 4) == half;
+                    if (mine && my_turn) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl, hist);
+                    __syncwarp();
+                    const int now = *wl.count;
+                    const int hb = hist_update(hist, hist_total, hist_next, now - before, a.r, lane, sbound);
+                    if (hb < gb) gb = hb;
+                    if (now >= compact_at) {
+                        wl.compact(a.cap, a.r, lane, sbound);
+                        lb = *wl.bound;
+                    }
+                }
+                bound = min(bound, min(lb, gb + 1));
+                reload = true;
+            };
+            if (filt_on) {
+                FiltAcc f{f_start, f_start};
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                filt_word(w[qd].x, treg[4 * qd], f, pk);
-                filt_word(w[qd].y, treg[4 * qd + 1], f, pk);
-                filt_word(w[qd].z, treg[4 * qd + 2], f, pk);
-                filt_word(w[qd].w, treg[4 * qd + 3], f, pk);
-            }
-            if (__any_sync(0xffffffffu, filt_any(f))) {
-                // some vector may be below the bound: exact sums, table read from shared memory (the words pass through an
-                // opaque IMAD so that ptxas does not keep the filter's selector registers alive for reuse here)
-                ctl += 6;
-                if (ctl > 96) { filt_on = false; ctl = 256; reload = true; }   // ~1 superblock in 6 passes the filter
+                for (int qd = 0; qd < 4; ++qd) {
+                    filt_word(w[qd].x, treg[4 * qd], f, pk);
+                    filt_word(w[qd].y, treg[4 * qd + 1], f, pk);
+                    filt_word(w[qd].z, treg[4 * qd + 2], f, pk);
+                    filt_word(w[qd].w, treg[4 * qd + 3], f, pk);
+                }
+                if (__any_sync(0xffffffffu, filt_any(f))) {
+                    // some vector may be below the bound: exact sums, table read from shared memory (the words pass through an
+                    // opaque IMAD so that ptxas does not keep the filter's selector registers alive for reuse here)
+                    ctl += 6;
+                    if (ctl > 96) { filt_on = false; ctl = 256; reload = true; }   // ~1 superblock in 6 passes the filter
+                    GroupAcc g;
+#pragma unroll
+                    for (int p = 0; p < M / 2; ++p) {
+                        const uint4 t0 = qtab[2 * p], t1 = qtab[2 * p + 1];
+                        const uint4& wq = w[p >> 1];
+                        scan_pair(p == 0, madd((p & 1) ? wq.z : wq.x, 0u, pk), madd((p & 1) ? wq.w : wq.y, 0u, pk), t0, t1, g, pk, bound);
+                    }
+                    const bool mine = any_below(g);
+                    if (__any_sync(0xffffffffu, mine)) emit(g, mine);
+                }
+            } else {
                 GroupAcc g;
 #pragma unroll
                 for (int p = 0; p < M / 2; ++p) {
-                    const uint4 t0 = qtab[2 * p], t1 = qtab[2 * p + 1];
                     const uint4& wq = w[p >> 1];
-                    scan_pair(p == 0, madd((p & 1) ? wq.z : wq.x, 0u, pk), madd((p & 1) ? wq.w : wq.y, 0u, pk), t0, t1, g, pk, bound);
+                    scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, treg[2 * p], treg[2 * p + 1], g, pk, bound);
                 }
                 const bool mine = any_below(g);
                 if (__any_sync(0xffffffffu, mine)) emit(g, mine);
             }
-        } else {
-            GroupAcc g;
-#pragma unroll
-            for (int p = 0; p < M / 2; ++p) {
-                const uint4& wq = w[p >> 1];
-                scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, treg[2 * p], treg[2 * p + 1], g, pk, bound);
+            if (slot == 0 && (NPS == 1 || h == 0)) {
+                // once per ring revolution: the shared bound read one revolution ago (never waited for), the filter's
+                // pass-rate score decays, a tighter clamped table is built when the bound has moved enough
+                bound = min(bound, gb_pending + 1);
+                load_shared_bound_now(gb_pending, sbound);
+                ctl = filt_on ? max(ctl - NSW * NPS, 0) : ctl - NSW * NPS;
+                if (filt_on) reload |= bound + 3 <= 127 - static_cast<int>(f_start & 0xffu);
+                else if (ctl <= 0 && a.use_filter) { filt_on = true; ctl = 0; reload = true; }
             }
-            const bool mine = any_below(g);
-            if (__any_sync(0xffffffffu, mine)) emit(g, mine);
+            // before the next superblock: a filter that was switched on or off needs its own tables
+            if (reload) { load_table(); reload = false; }
         }
-        if (reload) load_table();
+        refill += NW * Cfg::kSlotBytes;
     };
 
     // (Unrolling the NSW slots so that every address is base + immediate was measured 20 % SLOWER: the four copies of
