@@ -134,6 +134,29 @@ int qadc_search_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, in
 int qadc_search_assigned_device(qadc_ctx* ctx, const float* d_queries, const int32_t* d_assign, int nq,
                                 int ma, int r, uint32_t* d_ids, int8_t* d_dists, int32_t* d_counts,
                                 uint64_t* d_keys);
+/* "Owner computes": the per-query table pipeline of SHARDED inverted lists, split around one exchange, so that no
+ * shard builds tables or scans keep-prefixes for lists it does not hold (scanner_4::query_scan, db_query_4.cpp:245-284,
+ * whose bounds are one qmin/qmax per QUERY over all ma probes).  A shard answers for the partitions it owns
+ * (qadc_set_owned_partitions); it needs no replica of the other lists' prefixes.
+ *   1. qadc_tables_local_device: float tables of the OWNED probes of every query (kept in the context's scratch) and
+ *      this shard's share of the bounds, d_local[q][0] = min entry of those tables (FLT_MAX if it owns none),
+ *      d_local[q][1..r] = its r smallest keep-prefix distances (scan_4, query_common.hpp:59-90; FLT_MAX-padded).
+ *      d_local: nq * (r + 1) floats on the device.  nq <= 32768 per call.
+ *   2. the caller all-gathers d_local over the shards: d_gathered[g][q][r + 1], in any shard order.
+ *   3. qadc_search_bounded_device: qmin = min over shards, qmax = r-th smallest of the union (both order-independent
+ *      selections of values computed with the unsharded arithmetic, hence bit-identical to the unsharded bounds), int8
+ *      tables of the owned probes (QuantizerMAX, db_query_4.cpp:37-71), scan of the owned lists, per-shard canonical top-r
+ *      (same outputs as qadc_search_device; merge the shards with qadc_merge_shards_device).  Must follow step 1 of the
+ *      same batch on the same context.  A query whose union holds fewer than r prefix vectors reports QADC_EBOUND at the
+ *      next qadc_synchronize, like the unsharded search. */
+/* Which partitions this shard answers for (uint8 mask [partition_count], after qadc_begin_database; default: the
+ * partitions given a non-zero size).  Every partition must be owned by exactly one shard — including partitions that are
+ * empty everywhere, whose tables still take part in the query's qmin (db_query_4.cpp:256-260 runs over all ma tables). */
+int qadc_set_owned_partitions(qadc_ctx* ctx, const uint8_t* owned);
+int qadc_tables_local_device(qadc_ctx* ctx, const float* d_queries, const int32_t* d_assign, int nq, int ma, int r,
+                             float* d_local);
+int qadc_search_bounded_device(qadc_ctx* ctx, const float* d_gathered, int G, int nq, int ma, int r, uint32_t* d_ids,
+                               int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys);
 /* Sharded coarse assignment (index_db::assign_compute_residuals_mutiple -> find_k_neighbors,
  * databases.hpp:213-231, neighbors.cpp:30-76, split over the GPUs of one box): every rank ranks
  * the queries against the cells [c_first, c_first + c_count) only and returns its ma best as keys

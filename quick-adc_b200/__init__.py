@@ -74,6 +74,9 @@ def load_library(build_if_missing=True):
     L.qadc_search_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.qadc_search_assigned_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.qadc_coarse_partial_device.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.qadc_tables_local_device.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.qadc_set_owned_partitions.argtypes = [vp, vp]
+    L.qadc_search_bounded_device.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.qadc_coarse_merge_device.argtypes = [vp, vp, i32, i32, i32, vp]
     L.qadc_adc_load.argtypes = [vp, i32, vp, vp, vp]
     L.qadc_adc_search.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
@@ -110,7 +113,8 @@ def load_library(build_if_missing=True):
                  "qadc_synchronize", "qadc_last_launch_count", "qadc_last_scan_ms", "qadc_merge_shards_device",
                  "qadc_build_tables", "qadc_scan_with_tables", "qadc_dump_distances", "qadc_download_codes",
                  "qadc_set_option", "qadc_encode", "qadc_search_assigned_device", "qadc_coarse_partial_device",
-                 "qadc_coarse_merge_device", "qadc_adc_load", "qadc_adc_search"):
+                 "qadc_coarse_merge_device", "qadc_adc_load", "qadc_adc_search", "qadc_tables_local_device",
+                 "qadc_search_bounded_device", "qadc_set_owned_partitions"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -263,6 +267,21 @@ class Index:
         self._ck(self.lib.qadc_search_assigned_device(self.h, _ptr(int(d_queries)), _ptr(int(d_assign)), nq, ma, r,
                                                       _ptr(int(d_ids)), _ptr(int(d_dists)), _ptr(int(d_counts)),
                                                       _ptr(None if d_keys is None else int(d_keys))))
+
+    def set_owned_partitions(self, owned):
+        """Owner-computes: boolean mask [partition_count] of the partitions this shard answers for (empty ones included)."""
+        o = np.ascontiguousarray(np.asarray(owned).astype(np.uint8))
+        self._ck(self.lib.qadc_set_owned_partitions(self.h, _ptr(o)))
+
+    def tables_local_device(self, d_queries, d_assign, nq, ma, r, d_local):
+        """Owner-computes step 1: tables of the owned probes; d_local [nq][r+1] floats = (min entry, r smallest prefix distances)."""
+        self._ck(self.lib.qadc_tables_local_device(self.h, _ptr(int(d_queries)), _ptr(int(d_assign)), nq, ma, r, _ptr(int(d_local))))
+
+    def search_bounded_device(self, d_gathered, G, nq, ma, r, d_ids, d_dists, d_counts, d_keys=None):
+        """Owner-computes step 3: bounds from the gathered [G][nq][r+1] shares, int8 tables, scan of the owned lists."""
+        self._ck(self.lib.qadc_search_bounded_device(self.h, _ptr(int(d_gathered)), G, nq, ma, r, _ptr(int(d_ids)),
+                                                     _ptr(int(d_dists)), _ptr(int(d_counts)),
+                                                     _ptr(None if d_keys is None else int(d_keys))))
 
     def coarse_partial_device(self, d_queries, nq, ma, c_first, c_count, d_out_keys):
         """This rank's ma best cells among [c_first, c_first + c_count) as uint64 keys [nq][ma]."""

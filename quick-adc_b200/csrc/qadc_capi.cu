@@ -60,6 +60,7 @@ struct qadc_ctx {
     uint32_t* d_labels = nullptr;
     uint64_t *d_sb_off = nullptr, *d_label_off = nullptr, *d_start_off = nullptr;
     uint32_t *d_size = nullptr, *d_pos_base = nullptr, *d_start_size = nullptr;
+    uint32_t* d_owned = nullptr;   // [parts] 1 = this shard answers for the partition ("owner computes"); default: size > 0
     uint8_t* d_starts = nullptr;
     uint32_t max_start = 0;
     // plain-ADC database (db_query path): row-major codes, independent of the Quick ADC layout above
@@ -70,7 +71,9 @@ struct qadc_ctx {
     DevBuf b_adc_dists;
     // scratch
     DevBuf staging, b_queries, b_assign, b_tables, b_tmin, b_qmax, b_qmin, b_qtables, b_lists, b_plists, b_ids,
-        b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound, b_cdist;
+        b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound, b_cdist, b_qmin_raw;
+    int local_nq = 0, local_ma = 0, local_r = 0;   // batch whose tables qadc_tables_local_device left in the scratch
+    bool local_mode = false;                        // scan_device runs for qadc_search_bounded_device: only owned probes have tables
     int* d_err = nullptr;
     int* h_err = nullptr;   // pinned
     // options / accounting
@@ -123,13 +126,13 @@ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 void free_db(qadc_ctx* c) {
     cudaFree(c->d_codes); cudaFree(c->d_labels); cudaFree(c->d_sb_off); cudaFree(c->d_label_off);
-    cudaFree(c->d_start_off); cudaFree(c->d_size); cudaFree(c->d_pos_base); cudaFree(c->d_start_size);
+    cudaFree(c->d_start_off); cudaFree(c->d_owned); cudaFree(c->d_size); cudaFree(c->d_pos_base); cudaFree(c->d_start_size);
     cudaFree(c->d_starts);
     for (auto p : c->h_explicit_prefix)
         if (p && !c->d_prefix_block) cudaFree(p);
     cudaFree(c->d_prefix_block); c->d_prefix_block = nullptr;
     c->d_codes = nullptr; c->d_labels = nullptr; c->d_sb_off = c->d_label_off = c->d_start_off = nullptr;
-    c->d_size = c->d_pos_base = c->d_start_size = nullptr; c->d_starts = nullptr;
+    c->d_size = c->d_pos_base = c->d_start_size = c->d_owned = nullptr; c->d_starts = nullptr;
     c->h_explicit_prefix.clear(); c->h_explicit_count.clear();
     c->begun = c->finalized = false;
 }
@@ -267,6 +270,7 @@ int seed_shared_bound(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qt
     pa.assign = d_assign; pa.qtabs = d_qtables; pa.ma = ma;
     pa.nsplit = (ctx->K == 0) ? static_cast<int>(std::min<uint32_t>(64, std::max<uint32_t>(1, ctx->max_start / 8192))) : 1;
     pa.hist = ctx->b_hist.as<unsigned int>();
+    pa.owned_size = ctx->local_mode ? ctx->d_owned : nullptr;
     dim3 grid(pa.nsplit, nq);
     if (ctx->m == 16) prefix_hist_kernel<16><<<grid, 256, 0, ctx->stream>>>(pa);
     else prefix_hist_kernel<32><<<grid, 256, 0, ctx->stream>>>(pa);
@@ -450,7 +454,7 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
                 cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dim * 64);
             kernel<<<tgrid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(
                 d_queries, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
-                ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), 4);
+                ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), 4, nullptr);
         };
         switch (dim / M) {   // same arithmetic in every instantiation; the common sub-vector sizes unroll
             case 2: launch_tables(tables_kernel<2>); break;
@@ -498,6 +502,20 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
     quantize_kernel<<<nq, 256, 0, ctx->stream>>>(
         ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), ctx->b_qmax.as<float>(), ma, M,
         ctx->b_qtables.as<int8_t>(), ctx->b_qmin.as<float>(), ctx->d_err);
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    return QADC_OK;
+}
+
+template <typename K>
+int launch_tables_kernel(qadc_ctx* ctx, K kernel, dim3 grid, const float* d_queries, const int32_t* d_assign, int ma,
+                                const uint32_t* part_size) {
+    const int dim = ctx->dim;
+    if (static_cast<size_t>(dim) * 64 > 48 * 1024)
+        QCK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dim * 64));
+    kernel<<<grid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(d_queries, dim, ctx->m, ctx->d_codebooks, ctx->d_rotation,
+                                                                        ctx->d_centroids, d_assign, ma, ctx->b_tables.as<float>(),
+                                                                        ctx->b_tmin.as<float>(), 4, part_size);
     ctx->launches++;
     QCK(cudaGetLastError());
     return QADC_OK;
@@ -652,7 +670,27 @@ int qadc_begin_database(qadc_ctx* ctx, int partition_count, const uint32_t* size
     QCK(cudaMemcpy(ctx->d_sb_off, ctx->h_sb_off.data(), P * 8, cudaMemcpyHostToDevice));
     QCK(cudaMemcpy(ctx->d_label_off, ctx->h_label_off.data(), P * 8, cudaMemcpyHostToDevice));
     QCK(cudaMemcpy(ctx->d_size, ctx->h_size.data(), P * 4, cudaMemcpyHostToDevice));
+    {   // default ownership: the partitions that hold vectors here
+        std::vector<uint32_t> owned(P);
+        for (int p = 0; p < P; ++p) owned[p] = sizes[p] ? 1u : 0u;
+        QCK(cudaMalloc(&ctx->d_owned, P * 4));
+        QCK(cudaMemcpy(ctx->d_owned, owned.data(), P * 4, cudaMemcpyHostToDevice));
+    }
     ctx->begun = true;
+    return QADC_OK;
+}
+
+int qadc_set_owned_partitions(qadc_ctx* ctx, const uint8_t* owned) {
+    if (!ctx || !ctx->begun) return fail(ctx, QADC_ESTATE, "qadc_begin_database must be called first");
+    if (!owned) return fail(ctx, QADC_EINVAL, "null mask");
+    QCK(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> o(ctx->parts);
+    for (int p = 0; p < ctx->parts; ++p) {
+        if (!owned[p] && ctx->h_size[p]) return fail(ctx, QADC_EINVAL, "a partition that holds vectors on this shard must be owned by it");
+        o[p] = owned[p] ? 1u : 0u;
+    }
+    QCK(cudaStreamSynchronize(ctx->stream));
+    QCK(cudaMemcpy(ctx->d_owned, o.data(), o.size() * 4, cudaMemcpyHostToDevice));
     return QADC_OK;
 }
 
@@ -927,6 +965,93 @@ int qadc_search_assigned_device(qadc_ctx* ctx, const float* d_queries, const int
     if (!ctx) return QADC_EINVAL;
     if (!d_assign) return fail(ctx, QADC_EINVAL, "null assignment");
     return search_device_impl(ctx, d_queries, d_assign, nq, ma, r, d_ids, d_dists, d_counts, d_keys);
+}
+
+// ---- "owner computes": the table pipeline of sharded inverted lists, split around one exchange -------------------
+int qadc_tables_local_device(qadc_ctx* ctx, const float* d_queries, const int32_t* d_assign, int nq, int ma, int r,
+                             float* d_local) {
+    int rc = check_search_args(ctx, nq, ma, r);
+    if (rc) return rc;
+    if (ctx->K == 0) return fail(ctx, QADC_ESTATE, "qadc_tables_local_device needs inverted lists");
+    if (!d_queries || !d_assign || !d_local) return fail(ctx, QADC_EINVAL, "null buffer");
+    if (nq > kMaxBatch) return fail(ctx, QADC_EINVAL, "more than 32768 queries per call: split the batch");
+    QCK(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    ctx->local_nq = 0;
+    const int M = ctx->m;
+    const size_t nqa = static_cast<size_t>(nq) * ma;
+    ENSURE(ctx->b_assign, nqa * 4);
+    ENSURE(ctx->b_tables, nqa * M * 16 * 4);
+    ENSURE(ctx->b_tmin, nqa * 4);
+    ENSURE(ctx->b_qmax, static_cast<size_t>(nq) * 4);
+    ENSURE(ctx->b_qmin, static_cast<size_t>(nq) * 4);
+    ENSURE(ctx->b_qmin_raw, static_cast<size_t>(nq) * 4);
+    ENSURE(ctx->b_qtables, nqa * M * 16);
+    int32_t* assign = ctx->b_assign.as<int32_t>();
+    QCK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    QCK(cudaMemcpyAsync(assign, d_assign, nqa * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    QCK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    const dim3 tgrid((ma + 7) / 8, nq);
+    switch (ctx->dim / M) {
+        case 2: rc = launch_tables_kernel(ctx, tables_kernel<2>, tgrid, d_queries, assign, ma, ctx->d_owned); break;
+        case 3: rc = launch_tables_kernel(ctx, tables_kernel<3>, tgrid, d_queries, assign, ma, ctx->d_owned); break;
+        case 4: rc = launch_tables_kernel(ctx, tables_kernel<4>, tgrid, d_queries, assign, ma, ctx->d_owned); break;
+        case 6: rc = launch_tables_kernel(ctx, tables_kernel<6>, tgrid, d_queries, assign, ma, ctx->d_owned); break;
+        case 8: rc = launch_tables_kernel(ctx, tables_kernel<8>, tgrid, d_queries, assign, ma, ctx->d_owned); break;
+        case 12: rc = launch_tables_kernel(ctx, tables_kernel<12>, tgrid, d_queries, assign, ma, ctx->d_owned); break;
+        case 16: rc = launch_tables_kernel(ctx, tables_kernel<16>, tgrid, d_queries, assign, ma, ctx->d_owned); break;
+        default: rc = launch_tables_kernel(ctx, tables_kernel<0>, tgrid, d_queries, assign, ma, ctx->d_owned); break;
+    }
+    if (rc) return rc;
+    PrefixArgs pa;
+    pa.starts = ctx->d_starts; pa.start_off = ctx->d_start_off; pa.start_size = ctx->d_start_size;
+    pa.assign = assign; pa.tables = ctx->b_tables.as<float>(); pa.ma = ma; pa.r = r; pa.M = M;
+    pa.qmax = nullptr; pa.nsplit = 1; pa.lists = nullptr;
+    pa.local_out = d_local; pa.tmin = ctx->b_tmin.as<float>(); pa.owned_size = ctx->d_owned;
+    if (ctx->max_start <= 128) {
+        if (M == 16) prefix_scan_probes_kernel<16><<<nq, kSelThreads, 0, ctx->stream>>>(pa);
+        else prefix_scan_probes_kernel<32><<<nq, kSelThreads, 0, ctx->stream>>>(pa);
+    } else {
+        if (M == 16) prefix_scan_kernel<16><<<dim3(1, nq), kSelThreads, 0, ctx->stream>>>(pa);
+        else prefix_scan_kernel<32><<<dim3(1, nq), kSelThreads, 0, ctx->stream>>>(pa);
+    }
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    QCK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    ctx->local_nq = nq; ctx->local_ma = ma; ctx->local_r = r;
+    return QADC_OK;
+}
+
+int qadc_search_bounded_device(qadc_ctx* ctx, const float* d_gathered, int G, int nq, int ma, int r, uint32_t* d_ids,
+                               int8_t* d_dists, int32_t* d_counts, uint64_t* d_keys) {
+    if (!ctx) return QADC_EINVAL;
+    if (ctx->local_nq != nq || ctx->local_ma != ma || ctx->local_r != r || nq <= 0)
+        return fail(ctx, QADC_ESTATE, "qadc_search_bounded_device must follow qadc_tables_local_device of the same batch");
+    if (!d_gathered || !d_ids || !d_dists || !d_counts || G <= 0) return fail(ctx, QADC_EINVAL, "bad arguments");
+    const size_t csmem = static_cast<size_t>(G) * r * 4;
+    if (csmem > static_cast<size_t>(kMaxSmem) - 4096) return fail(ctx, QADC_EINVAL, "G * r too large");
+    QCK(cudaSetDevice(ctx->device));
+    ctx->local_nq = 0;
+    const int M = ctx->m;
+    if (csmem > 40 * 1024)
+        QCK(cudaFuncSetAttribute(bounds_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(csmem)));
+    bounds_combine_kernel<<<nq, kSelThreads, csmem, ctx->stream>>>(d_gathered, G, nq, r, ctx->b_qmin_raw.as<float>(),
+                                                                  ctx->b_qmax.as<float>());
+    QCK(cudaGetLastError());
+    quantize_kernel<<<nq, 256, 0, ctx->stream>>>(ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), ctx->b_qmax.as<float>(), ma, M,
+                                                 ctx->b_qtables.as<int8_t>(), ctx->b_qmin.as<float>(), ctx->d_err,
+                                                 ctx->b_qmin_raw.as<float>(), ctx->b_assign.as<int32_t>(), ctx->d_owned);
+    QCK(cudaGetLastError());
+    ctx->launches += 2;
+    QCK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->local_mode = true;
+    const int rc = scan_device(ctx, ctx->b_assign.as<int32_t>(), ctx->b_qtables.as<int8_t>(), nq, ma, r, d_ids, d_dists, d_counts,
+                               d_keys);
+    ctx->local_mode = false;
+    if (rc) return rc;
+    QCK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    QCK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return QADC_OK;
 }
 
 int qadc_coarse_partial_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int c_first, int c_count,
@@ -1291,7 +1416,7 @@ int qadc_adc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, 
                     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dim * 64);
                 kernel<<<tgrid, 256, static_cast<size_t>(dim) * 8 * 8, ctx->stream>>>(
                     d_q, dim, M, ctx->d_codebooks, ctx->d_rotation, flat ? nullptr : ctx->d_centroids, d_assign, ma,
-                    ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), bits);
+                    ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), bits, nullptr);
             };
             switch (dim / M) {
                 case 2: launch_tables(tables_kernel<2>); break;

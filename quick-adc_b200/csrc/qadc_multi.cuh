@@ -38,7 +38,7 @@ struct qadc_multi {
     bool loaded = false;
     // per-device scratch
     struct Shard {
-        DevBuf q, ids, dists, counts, keys, gkeys, gids, assign, ckeys, gckeys, oids, odists, ocounts;
+        DevBuf q, ids, dists, counts, keys, gkeys, gids, assign, ckeys, gckeys, oids, odists, ocounts, local, glocal;
     };
     std::vector<Shard> sh;
     cudaEvent_t ev[6] = {};   // on device 0's stream: start, coarse done, search done, gather done, merge done, d2h done
@@ -154,7 +154,7 @@ void qadc_multi_destroy(qadc_multi* mm) {
         cudaStreamSynchronize(mm->ctx[g]->stream);
         for (DevBuf* b : {&mm->sh[g].q, &mm->sh[g].ids, &mm->sh[g].dists, &mm->sh[g].counts, &mm->sh[g].keys, &mm->sh[g].gkeys,
                           &mm->sh[g].gids, &mm->sh[g].assign, &mm->sh[g].ckeys, &mm->sh[g].gckeys, &mm->sh[g].oids,
-                          &mm->sh[g].odists, &mm->sh[g].ocounts})
+                          &mm->sh[g].odists, &mm->sh[g].ocounts, &mm->sh[g].local, &mm->sh[g].glocal})
             cudaFree(b->p);
     }
     if (mm->use_nccl)
@@ -229,16 +229,7 @@ int qadc_multi_load(qadc_multi* mm, int partition_count, const uint32_t* sizes, 
             owner[p] = g;
             load[g] += sizes[p];
         }
-        // replicated keep-prefixes of ALL lists
-        std::vector<uint32_t> counts(P);
-        uint64_t total = 0;
-        for (int p = 0; p < P; ++p) { counts[p] = start_size(sizes[p]); total += counts[p]; }
-        std::vector<uint8_t> pre(total * CS);
-        uint64_t at = 0;
-        for (int p = 0; p < P; ++p) {
-            if (counts[p]) memcpy(pre.data() + at * CS, part_codes[p], counts[p] * CS);
-            at += counts[p];
-        }
+        // no prefix replicas: the table pipeline is "owner computes" (qadc_tables_local_device / qadc_search_bounded_device)
         std::vector<uint32_t> lsizes(P);
         std::vector<const uint8_t*> lcodes(P);
         std::vector<const uint32_t*> llabels(P);
@@ -250,8 +241,12 @@ int qadc_multi_load(qadc_multi* mm, int partition_count, const uint32_t* sizes, 
                 llabels[p] = mine ? part_labels[p] : nullptr;
             }
             MCTX(g, qadc_begin_database(mm->ctx[g], P, lsizes.data(), 1));
+            if (G > 1) {   // empty lists too have exactly one owner (their tables take part in qmin)
+                std::vector<uint8_t> mask(P);
+                for (int p = 0; p < P; ++p) mask[p] = owner[p] == g ? 1 : 0;
+                MCTX(g, qadc_set_owned_partitions(mm->ctx[g], mask.data()));
+            }
             MCTX(g, qadc_upload_partitions(mm->ctx[g], lcodes.data(), llabels.data()));
-            if (G > 1 && total) MCTX(g, qadc_set_prefixes(mm->ctx[g], pre.data(), counts.data(), 0));
             MCTX(g, qadc_finalize(mm->ctx[g], keep));
         }
     }
@@ -283,6 +278,8 @@ int qadc_multi_search(qadc_multi* mm, const float* queries, int nq, int ma, int 
                 rc = rc ? rc : mensure(mm, g, s.assign, static_cast<size_t>(nq) * ma * 4);
                 rc = rc ? rc : mensure(mm, g, s.ckeys, static_cast<size_t>(nq) * ma * 8);
                 rc = rc ? rc : mensure(mm, g, s.gckeys, static_cast<size_t>(nq) * ma * 8 * G);
+                rc = rc ? rc : mensure(mm, g, s.local, static_cast<size_t>(std::min(nq, 32768)) * (r + 1) * 4);
+                rc = rc ? rc : mensure(mm, g, s.glocal, static_cast<size_t>(std::min(nq, 32768)) * (r + 1) * 4 * G);
             }
         }
         if (g == 0 && G > 1) {
@@ -317,12 +314,36 @@ int qadc_multi_search(qadc_multi* mm, const float* queries, int nq, int ma, int 
     MCK(cudaEventRecord(mm->ev[1], mm->ctx[0]->stream));
     for (int g = 0; g < G; ++g) {
         auto& s = mm->sh[g];
-        if (ivf && G > 1)
-            MCTX(g, qadc_search_assigned_device(mm->ctx[g], s.q.as<float>(), s.assign.as<int32_t>(), nq, ma, r, s.ids.as<uint32_t>(),
-                                                s.dists.as<int8_t>(), s.counts.as<int32_t>(), s.keys.as<uint64_t>()));
-        else
+        if (!(ivf && G > 1))
             MCTX(g, qadc_search_device(mm->ctx[g], s.q.as<float>(), nq, ma, r, s.ids.as<uint32_t>(), s.dists.as<int8_t>(),
                                        s.counts.as<int32_t>(), s.keys.as<uint64_t>()));
+    }
+    if (ivf && G > 1) {
+        // "owner computes": every device builds tables and scans keep-prefixes for the probes whose lists it holds, the
+        // devices exchange (min entry, r smallest prefix distances) per query, then bounds + int8 tables + list scan
+        constexpr int kSub = 32768;
+        for (int q0 = 0; q0 < nq; q0 += kSub) {
+            const int n = std::min(kSub, nq - q0);
+            const size_t lbytes = static_cast<size_t>(n) * (r + 1) * 4;
+            std::vector<const void*> send(G);
+            std::vector<void*> recv(G);
+            for (int g = 0; g < G; ++g) {
+                auto& s = mm->sh[g];
+                MCTX(g, qadc_tables_local_device(mm->ctx[g], s.q.as<float>() + static_cast<size_t>(q0) * mm->dim,
+                                                 s.assign.as<int32_t>() + static_cast<size_t>(q0) * ma, n, ma, r, s.local.as<float>()));
+                send[g] = s.local.p; recv[g] = s.glocal.p;
+            }
+            int rc = multi_all_gather(mm, send, recv, lbytes);
+            if (rc) return rc;
+            for (int g = 0; g < G; ++g) {
+                auto& s = mm->sh[g];
+                MCTX(g, qadc_search_bounded_device(mm->ctx[g], s.glocal.as<float>(), G, n, ma, r,
+                                                   s.ids.as<uint32_t>() + static_cast<size_t>(q0) * r, s.dists.as<int8_t>() + static_cast<size_t>(q0) * r,
+                                                   s.counts.as<int32_t>() + q0, s.keys.as<uint64_t>() + static_cast<size_t>(q0) * r));
+            }
+            if (!mm->use_nccl && q0 + kSub < nq)   // virtual shards: the share buffers are reused by the next sub-batch
+                for (int g = 0; g < G; ++g) MCK(cudaStreamSynchronize(mm->ctx[g]->stream));
+        }
     }
     MCK(cudaSetDevice(mm->devices[0]));
     MCK(cudaEventRecord(mm->ev[2], mm->ctx[0]->stream));

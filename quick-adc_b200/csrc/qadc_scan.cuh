@@ -947,6 +947,7 @@ struct PrefixBoundArgs {
     const int8_t* qtabs;       // [nq][ma][M*16]
     int ma, nsplit;
     unsigned int* hist;        // [nq][128], zeroed
+    const uint32_t* owned_size = nullptr;   // "owner computes": [K] sizes on this device; probes of lists held elsewhere have no table here
 };
 
 template <int M>
@@ -963,7 +964,7 @@ __global__ void __launch_bounds__(256) prefix_hist_kernel(const PrefixBoundArgs 
     const uint32_t vstep = single ? 256u : 32u, vfirst = single ? tid : lane;
     for (int ar = single ? 0 : warp; ar < a.ma; ar += single ? 1 : 8) {
         const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
-        const uint32_t n = a.start_size[p];
+        const uint32_t n = (a.owned_size && a.owned_size[p] == 0) ? 0u : a.start_size[p];
         const uint32_t v0 = static_cast<uint32_t>(static_cast<uint64_t>(n) * split / a.nsplit);
         const uint32_t v1 = static_cast<uint32_t>(static_cast<uint64_t>(n) * (split + 1) / a.nsplit);
         if (v1 == v0) continue;   // warp-uniform

@@ -306,13 +306,20 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ q
                                                      const float* __restrict__ rotation,    // or null
                                                      const float* __restrict__ centroids,   // or null (flat)
                                                      const int32_t* __restrict__ assign, int ma,
-                                                     float* __restrict__ tables, float* __restrict__ tmin, int ncl) {
+                                                     float* __restrict__ tables, float* __restrict__ tmin, int ncl,
+                                                     const uint32_t* __restrict__ part_size) {
     // ncl = log2(entries per sub-quantiser): 4 for Quick ADC, 8 for the plain 8-bit ADC tables
+    // part_size != null ("owner computes", sharded inverted lists): only probes whose list lives on this device get a
+    // table; the others report tmin = FLT_MAX and leave their slot untouched.
     extern __shared__ __align__(16) float sm[];   // 8 warps x 2 x dim
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.y, a_i = blockIdx.x * 8 + warp;
     if (a_i >= ma) return;
     const size_t qa = static_cast<size_t>(q) * ma + a_i;
+    if (part_size && part_size[assign[qa]] == 0) {
+        if (lane == 0) tmin[qa] = 3.402823466e+38f;
+        return;
+    }
     float* res = sm + static_cast<size_t>(warp) * 2 * dim;
     float* rot = res + dim;
     const float* query = queries + static_cast<size_t>(q) * dim;
@@ -387,7 +394,27 @@ struct PrefixArgs {
     int ma, r, M, nsplit;
     uint32_t* lists;                // [nq][nsplit][r] float bits, FLT_MAX-padded (nsplit > 1)
     float* qmax;                    // [nq], written directly when nsplit == 1
+    // "owner computes" (sharded inverted lists, nsplit == 1): instead of qmax the kernel writes this device's share of
+    // the query's bounds, local_out[q][0] = min entry of its tables (min over tmin[q][*]), local_out[q][1..r] = its r
+    // smallest prefix distances (FLT_MAX-padded); the shards' shares are combined by bounds_combine_kernel.
+    float* local_out = nullptr;
+    const float* tmin = nullptr;    // [nq][ma]
+    const uint32_t* owned_size = nullptr;   // [K] partition sizes on this device: a probe whose list is elsewhere is skipped
 };
+
+// local_out[q][0] of PrefixArgs: block-wide min over the query's per-probe table minima
+__device__ __forceinline__ void write_local_min(const PrefixArgs& a, int q, int tid, float* red) {
+    float mn = 3.402823466e+38f;
+    for (int i = tid; i < a.ma; i += kSelThreads) mn = fminf(mn, a.tmin[static_cast<size_t>(q) * a.ma + i]);
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = mn;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kSelThreads / 32; ++w) mn = fminf(mn, red[w]);
+        a.local_out[static_cast<size_t>(q) * (a.r + 1)] = mn;
+    }
+}
 
 template <int M>
 __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixArgs a) {
@@ -401,7 +428,7 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixAr
     top.init(tid);
     for (int ar = 0; ar < a.ma; ++ar) {
         const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
-        const uint32_t n = a.start_size[p];
+        const uint32_t n = (a.owned_size && a.owned_size[p] == 0) ? 0u : a.start_size[p];
         const uint32_t v0 = static_cast<uint32_t>(static_cast<uint64_t>(n) * split / a.nsplit);
         const uint32_t v1 = static_cast<uint32_t>(static_cast<uint64_t>(n) * (split + 1) / a.nsplit);
         if (v1 == v0) continue;   // block-uniform
@@ -433,7 +460,11 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixAr
     // (FLT_MAX when the prefix is too short)
     const int c = count;
     const uint32_t* res = top.buf[top.cur];
-    if (a.nsplit == 1) {
+    if (a.local_out) {
+        float* dst = a.local_out + static_cast<size_t>(q) * (a.r + 1) + 1;
+        for (int i = tid; i < a.r; i += kSelThreads) dst[i] = (i < c) ? __uint_as_float(res[i]) : 3.402823466e+38f;
+        write_local_min(a, q, tid, reinterpret_cast<float*>(hist));
+    } else if (a.nsplit == 1) {
         if (tid == 0) a.qmax[q] = (c >= a.r) ? __uint_as_float(bound) : 3.402823466e+38f;
     } else {
         uint32_t* dst = a.lists + (static_cast<size_t>(q) * a.nsplit + split) * a.r;
@@ -470,9 +501,10 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_probes_kernel(const P
         const uint8_t* codes = nullptr;
         if (ar < a.ma) {
             const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
-            n = a.start_size[p];
+            n = (a.owned_size && a.owned_size[p] == 0) ? 0u : a.start_size[p];
             codes = a.starts + a.start_off[p] * CS;
-            for (int i = lane; i < M * 16; i += 32) tab[warp][i] = a.tables[(static_cast<size_t>(q) * a.ma + ar) * M * 16 + i];
+            if (n)
+                for (int i = lane; i < M * 16; i += 32) tab[warp][i] = a.tables[(static_cast<size_t>(q) * a.ma + ar) * M * 16 + i];
         }
         __syncwarp();
         for (uint32_t v = lane; v < n; v += 32) {   // n <= 128 (host guarantees max_start <= 128 for this kernel)
@@ -491,8 +523,38 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_probes_kernel(const P
         }
         top.maybe_compact(a.r, tid, a0 + 8 >= a.ma);
     }
-    if (tid == 0)
+    if (a.local_out) {   // the list is sorted after the forced compaction; unused slots hold kEmptyKey
+        float* dst = a.local_out + static_cast<size_t>(q) * (a.r + 1) + 1;
+        const int c = count;
+        for (int i = tid; i < a.r; i += kSelThreads)
+            dst[i] = (i < c) ? __uint_as_float(static_cast<uint32_t>(keys[i] >> 32)) : 3.402823466e+38f;
+        write_local_min(a, q, tid, &tab[0][0]);
+    } else if (tid == 0) {
         a.qmax[q] = (count == a.r) ? __uint_as_float(static_cast<uint32_t>(keys[a.r - 1] >> 32)) : 3.402823466e+38f;
+    }
+}
+
+// ---- "owner computes": the shards' bound shares -> the query's qmin / qmax ---------------------------------------
+// gathered[g][q][0] = min table entry on shard g, [1..r] = its r smallest prefix distances (FLT_MAX-padded).
+// qmin = min over shards (the min over all ma tables, db_query_4.cpp:256-260), qmax = the r-th smallest of the union
+// (= the r-th smallest prefix distance over all probed lists, query_scan_start, db_query_4.cpp:230-242): both are
+// order-independent selections of values every shard computed with the unsharded arithmetic, so they are bit-identical
+// to the unsharded bounds.  grid = queries, dynamic shared memory G * r * 4 bytes.
+__global__ void __launch_bounds__(kSelThreads) bounds_combine_kernel(const float* __restrict__ gathered, int G, int nq, int r,
+                                                                    float* __restrict__ qmin_raw, float* __restrict__ qmax) {
+    extern __shared__ uint32_t cvals[];
+    __shared__ int hist[256], state[2];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    float mn = 3.402823466e+38f;
+    for (int g = 0; g < G; ++g) {
+        const float* src = gathered + (static_cast<size_t>(g) * nq + q) * (r + 1);
+        mn = fminf(mn, src[0]);
+        for (int i = tid; i < r; i += kSelThreads) cvals[g * r + i] = __float_as_uint(src[1 + i]);
+    }
+    __syncthreads();
+    int n_less;
+    const uint32_t b = block_radix_select(cvals, G * r, r, hist, state, tid, n_less);
+    if (tid == 0) { qmin_raw[q] = mn; qmax[q] = __uint_as_float(b); }   // FLT_MAX when fewer than r prefix vectors exist
 }
 
 // (int) trunc of the correctly rounded quotient t / delta (what QuantizerMAX computes, db_query_4.cpp:44-55) for
@@ -825,11 +887,16 @@ __global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ v
 __global__ void __launch_bounds__(256) quantize_kernel(float* __restrict__ tables, const float* __restrict__ tmin,
                                                        const float* __restrict__ qmax_in, int ma, int M,
                                                        int8_t* __restrict__ qtables, float* __restrict__ qmin_out,
-                                                       int* __restrict__ err) {
+                                                       int* __restrict__ err, const float* __restrict__ qmin_in = nullptr,
+                                                       const int32_t* __restrict__ assign = nullptr,
+                                                       const uint32_t* __restrict__ part_size = nullptr) {
+    // qmin_in / assign / part_size ("owner computes"): the query's minimum comes from bounds_combine_kernel and only the
+    // tables of probes whose list lives on this device exist
     __shared__ float red[8];
     const int q = blockIdx.x, tid = threadIdx.x;
-    float mn = 3.402823466e+38f;
-    for (int a = tid; a < ma; a += 256) mn = fminf(mn, tmin[static_cast<size_t>(q) * ma + a]);
+    float mn = qmin_in ? qmin_in[q] : 3.402823466e+38f;
+    if (!qmin_in)
+        for (int a = tid; a < ma; a += 256) mn = fminf(mn, tmin[static_cast<size_t>(q) * ma + a]);
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     if ((tid & 31) == 0) red[tid >> 5] = mn;
     __syncthreads();
@@ -846,6 +913,7 @@ __global__ void __launch_bounds__(256) quantize_kernel(float* __restrict__ table
     const size_t base = static_cast<size_t>(q) * ma * M * 16;
     const int total = ma * M * 16;
     for (int e = tid * 4; e < total; e += 256 * 4) {   // M*16 is a multiple of 4
+        if (part_size && part_size[assign[static_cast<size_t>(q) * ma + e / (M * 16)]] == 0) continue;
         float4 v = *reinterpret_cast<float4*>(tables + base + e);
         float vv[4] = {v.x, v.y, v.z, v.w};
         char4 out;

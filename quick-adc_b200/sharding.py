@@ -2,11 +2,14 @@
 
 Flat: contiguous ranges of whole 256-vector superblocks, so that global position =
 shard offset + local position and the canonical order is preserved.  IVF: whole lists are
-assigned to GPUs (greedy by size); a list is never split.  Every shard keeps a replica of
-the keep-prefixes, so all shards derive identical quantisation bounds without a collective;
-the exchange steps are one all-gather of the per-shard top-r (key, id) lists and, for inverted
-lists, one all-gather of the per-shard coarse candidates (the coarse quantizer's cells are split
-into contiguous ranges, so ranking the queries against K cells costs K/G per GPU).
+assigned to GPUs (greedy by size); a list is never split.  A flat shard keeps a replica of
+the keep-prefix, so all shards derive identical quantisation bounds without a collective.
+Inverted lists use "owner computes": a shard builds tables and scans keep-prefixes only for the
+probes whose lists it holds and the shards exchange (min table entry, r smallest prefix
+distances) per query, from which every shard derives the same qmin/qmax (owner_computes_search).
+The other exchange steps are one all-gather of the per-shard top-r (key, id) lists and one
+all-gather of the per-shard coarse candidates (the coarse quantizer's cells are split into
+contiguous ranges, so ranking the queries against K cells costs K/G per GPU).
 """
 import numpy as np
 
@@ -83,3 +86,22 @@ def all_gather_topk(keys, ids, group=None):
     dist.all_gather_into_tensor(gk, keys.contiguous(), group=group)   # concatenation along dim 0
     dist.all_gather_into_tensor(gi, ids.contiguous(), group=group)
     return gk.view((world,) + tuple(keys.shape)), gi.view((world,) + tuple(ids.shape))
+
+
+def owner_computes_search(index, d_queries, d_assign, nq, ma, r, d_local, d_ids, d_dists, d_counts, d_keys, group=None):
+    """Sharded inverted lists without replicated work (qadc_tables_local_device -> all-gather ->
+    qadc_search_bounded_device): this shard's tables and prefix distances for the probes it owns, one
+    all-gather of nq x (r + 1) floats per shard, then bounds, int8 tables, scan and local top-r.
+    d_local: float32 CUDA tensor [nq, r + 1] (scratch); the other tensors as for search_device.
+    At most 32768 queries per call."""
+    import torch
+    import torch.distributed as dist
+    index.tables_local_device(d_queries.data_ptr(), d_assign.data_ptr(), nq, ma, r, d_local.data_ptr())
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        gathered = torch.empty((world * nq, r + 1), dtype=torch.float32, device=d_local.device)
+        dist.all_gather_into_tensor(gathered, d_local, group=group)
+    else:
+        gathered = d_local
+    index.search_bounded_device(gathered.data_ptr(), world, nq, ma, r, d_ids.data_ptr(), d_dists.data_ptr(),
+                                d_counts.data_ptr(), None if d_keys is None else d_keys.data_ptr())

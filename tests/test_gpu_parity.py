@@ -533,6 +533,80 @@ def test_virtual_ivf_shards_merge_equals_single(qadc, oracle, G):
     mi.close()
 
 
+@pytest.mark.parametrize("G,keep,max_list", [(2, 0.05, None), (4, 0.05, None), (8, 0.3, None), (3, 0.9, 400)])
+def test_virtual_ivf_shards_owner_computes_equals_single(qadc, oracle, G, keep, max_list):
+    """"Owner computes" (qadc_tables_local_device -> all-gather -> qadc_search_bounded_device): every shard holds ONLY its
+    own lists (no prefix replicas), builds tables for the probes it owns and contributes (min entry, r smallest prefix
+    distances); bounds from the union, scan, shard merge == the unsharded search == the oracle, and qmin/qmax are
+    bit-identical to the unsharded ones.  keep 0.3 / 0.9: prefixes longer than 128 vectors (the CTA-wide prefix kernel)."""
+    import torch
+    from qadc_b200 import sharding
+    rng = np.random.default_rng(140 + G)
+    dim, m, n, K, ma, nq, r = 96, 16, 60000, 48, 10, 11, 50
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(9,))
+    if max_list:   # short lists so that keep 0.9 stays within the fused kernels' limits
+        keepv = np.concatenate([np.arange(offsets[p], min(offsets[p + 1], offsets[p] + max_list)) for p in range(K)])
+        sizes = np.minimum(np.diff(offsets), max_list)
+        codes, labels = codes[keepv], labels[keepv]
+        offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    q = synth.make_queries(rng, nq, dim)
+    db = dict(dim=dim, m=m, codebooks=cb, centroids=cents, codes=codes, labels=labels, keep=keep, offsets=offsets)
+    exp = oracle.search(db, q, ma, r, want_tables=True)
+    sizes = np.diff(offsets)
+    owner = sharding.ivf_list_owner(sizes, G)
+    dq = torch.from_numpy(q).cuda()
+    d_assign = torch.from_numpy(exp["assign"].astype(np.int32)).cuda()
+    shards = []
+    for g in range(G):
+        ix = qadc.Index(0)
+        ix.set_pq(dim, m, cb)
+        ix.set_coarse(cents)
+        ix.begin_database(np.where(owner == g, sizes, 0).astype(np.uint32), True)
+        ix.set_owned_partitions(owner == g)   # the empty list has an owner too: its tables count for qmin
+        for p in range(K):
+            if sizes[p] and owner[p] == g:
+                ix.upload_codes(p, 0, codes[offsets[p]:offsets[p + 1]], labels[offsets[p]:offsets[p + 1]])
+            elif sizes[p] and G == 4:   # prefix replicas of the other shards' lists may be present: they must be ignored
+                ix.set_prefix(p, codes[offsets[p]:offsets[p] + sharding.start_size(int(sizes[p]), keep)])
+        ix.finalize(keep)
+        shards.append(ix)
+    local = torch.empty((G, nq, r + 1), dtype=torch.float32, device="cuda")
+    for g, ix in enumerate(shards):
+        ix.tables_local_device(dq.data_ptr(), d_assign.data_ptr(), nq, ma, r, local[g].data_ptr())
+        ix.synchronize()
+    loc = local.cpu().numpy()
+    # the union's bounds are the unsharded bounds, bit for bit
+    assert np.array_equal(np.minimum(loc[:, :, 0].min(0), np.float32(3.4e38)).astype(np.float32), exp["qmin"])
+    allv = np.sort(np.concatenate([loc[g][:, 1:] for g in range(G)], axis=1), axis=1)
+    assert np.array_equal(allv[:, r - 1], exp["qmax"])
+    keys = torch.empty((G, nq, r), dtype=torch.int64, device="cuda")
+    ids = torch.empty((G, nq, r), dtype=torch.int32, device="cuda")
+    perm = torch.from_numpy(rng.permutation(G)).cuda()   # the gather order of the shards must not matter
+    gathered = local[perm].contiguous()
+    for g, ix in enumerate(shards):
+        d_tmp = torch.empty((nq, r), dtype=torch.int8, device="cuda")
+        c_tmp = torch.empty(nq, dtype=torch.int32, device="cuda")
+        ix.search_bounded_device(gathered.data_ptr(), G, nq, ma, r, ids[g].data_ptr(), d_tmp.data_ptr(), c_tmp.data_ptr(),
+                                 keys[g].data_ptr())
+        ix.synchronize()
+    with pytest.raises(qadc.QadcError):   # the second half without a first half of the same batch
+        shards[0].search_bounded_device(gathered.data_ptr(), G, nq, ma, r, ids[0].data_ptr(), d_tmp.data_ptr(), c_tmp.data_ptr())
+    for ix in shards:
+        ix.close()
+    mi = qadc.Index(0)
+    o_ids = torch.empty((nq, r), dtype=torch.int32, device="cuda")
+    o_d = torch.empty((nq, r), dtype=torch.int8, device="cuda")
+    o_c = torch.empty(nq, dtype=torch.int32, device="cuda")
+    mi.merge_shards_device(keys.data_ptr(), ids.data_ptr(), G, nq, r, o_ids.data_ptr(), o_d.data_ptr(), o_c.data_ptr())
+    mi.synchronize()
+    assert np.array_equal(o_ids.cpu().numpy().view(np.uint32), exp["ids"])
+    assert np.array_equal(o_d.cpu().numpy(), exp["d"])
+    assert np.array_equal(o_c.cpu().numpy(), exp["count"])
+    mi.close()
+
+
 @pytest.mark.parametrize("G,K,ma", [(2, 48, 10), (8, 1500, 64), (3, 5, 4)])
 def test_sharded_coarse_assignment_equals_unsharded(qadc, oracle, G, K, ma):
     """Cells split into G contiguous ranges: per-range top-ma keys (qadc_coarse_partial_device),

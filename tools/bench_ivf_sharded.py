@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--check", type=int, default=0, help="queries compared with an unsharded single-GPU index on rank 0")
     ap.add_argument("--replicated-coarse", action="store_true",
                     help="every rank ranks the queries against all K cells (no coarse exchange), for comparison")
+    ap.add_argument("--replicated-tables", action="store_true",
+                    help="round-1 pipeline: every rank builds the tables of all probes from replicated keep-prefixes")
     ap.add_argument("--as-rank-of", type=int, default=0, metavar="W",
                     help="single process: hold only rank 0's lists of a W-way sharding (per-GPU work of the W-GPU run, no exchange)")
     args = ap.parse_args()
@@ -66,6 +68,7 @@ def main():
         index.set_pq(DIM, M, cb)
         index.set_coarse(cents)
         index.begin_database(np.where(mine, sizes, 0).astype(np.uint32), True)
+        index.set_owned_partitions(mine)
         t0 = time.perf_counter()
         for p in range(Kc):
             n_p = int(sizes[p])
@@ -106,6 +109,9 @@ def main():
             ix.coarse_partial_device(d_q.data_ptr(), nq, ma, first, count, d_gath[g].data_ptr())
         ix.synchronize()
 
+    d_local = torch.empty((nq, R + 1), dtype=torch.float32, device=dev)
+    d_local_all = torch.empty((max(shards, 1), nq, R + 1), dtype=torch.float32, device=dev)
+
     def step():
         if split_coarse:
             if world > 1:
@@ -114,8 +120,18 @@ def main():
                 first, count = sharding.coarse_range(Kc, 0, shards)
                 ix.coarse_partial_device(d_q.data_ptr(), nq, ma, first, count, d_gath[0].data_ptr())
                 ix.coarse_merge_device(d_gath.data_ptr(), shards, nq, ma, d_assign.data_ptr())
-            ix.search_assigned_device(d_q.data_ptr(), d_assign.data_ptr(), nq, ma, R, d_ids.data_ptr(), d_d.data_ptr(),
-                                      d_cnt.data_ptr(), d_keys.data_ptr())
+            if args.replicated_tables:
+                ix.search_assigned_device(d_q.data_ptr(), d_assign.data_ptr(), nq, ma, R, d_ids.data_ptr(), d_d.data_ptr(),
+                                          d_cnt.data_ptr(), d_keys.data_ptr())
+            elif world > 1:
+                sharding.owner_computes_search(ix, d_q, d_assign, nq, ma, R, d_local, d_ids, d_d, d_cnt, d_keys)
+            else:
+                # --as-rank-of: the other shards' bound shares are stood in for by copies of this shard's (same work per
+                # GPU as the real run; the results are not those of the full database and are not checked)
+                ix.tables_local_device(d_q.data_ptr(), d_assign.data_ptr(), nq, ma, R, d_local_all[0].data_ptr())
+                d_local_all[1:] = d_local_all[0]
+                ix.search_bounded_device(d_local_all.data_ptr(), shards, nq, ma, R, d_ids.data_ptr(), d_d.data_ptr(),
+                                         d_cnt.data_ptr(), d_keys.data_ptr())
         else:
             ix.search_device(d_q.data_ptr(), nq, ma, R, d_ids.data_ptr(), d_d.data_ptr(), d_cnt.data_ptr(), d_keys.data_ptr())
         if world > 1:
@@ -162,7 +178,8 @@ def main():
     if rank == 0:
         scanned = float(ma) * N / Kc
         print(json.dumps({"config": "5: Deep1B-shaped IVF-%d PQ 16x4, nprobe %d, sharded lists" % (Kc, ma), "n_vectors": N,
-                          "n_gpus": world, "shards": shards, "coarse": "split" if split_coarse else "replicated", "queries": nq, "ms_per_batch": ms, "queries_per_s": nq / (ms * 1e-3),
+                          "n_gpus": world, "shards": shards, "coarse": "split" if split_coarse else "replicated",
+                          "tables": "replicated" if (args.replicated_tables or not split_coarse) else "owner computes", "queries": nq, "ms_per_batch": ms, "queries_per_s": nq / (ms * 1e-3),
                           "vectors_scanned_per_s": scanned * nq / (ms * 1e-3), "build_seconds": t_build, "stage_metrics": stages,
                           "matches_unsharded": ok}))
     if world > 1:

@@ -159,8 +159,11 @@ def leg_ivf(qadc, torch, dev, stream, name, n, dim, m, K, ma, keep, nq, seed, ch
 def leg_config5_sharded(qadc, torch, dist, sharding, codes_torch, codes_torch_at, dev, stream, rank, world, n_total, nq, steps=3, check=4):
     """BASELINE config 5: Deep1B-shaped IVF-65536, 96-d, PQ 16x4 (sq_dim 6), nprobe 128.  Lists are dealt to the
     GPUs in contiguous runs of K/world lists (their sizes are multinomial, so the shards are balanced to < 1 %),
-    every shard holds a replica of all keep-prefixes, the coarse cells are split over the ranks (one all-gather of
-    nq x nprobe keys), the per-shard top-r lists are merged after one more all-gather.  List p owns the global
+    the coarse cells are split over the ranks (one all-gather of nq x nprobe keys), every shard builds tables and
+    scans keep-prefixes only for the probes it owns and the shards exchange their bound shares (one all-gather of
+    nq x (r+1) floats: "owner computes"; QADC_IVF_REPLICATED_TABLES=1 selects the replicated pipeline of round 1),
+    the per-shard top-r lists are merged after one more all-gather.  The prefix replicas are still uploaded: the
+    verification below recomputes the int8 tables on every shard with the replicated pipeline (qadc_build_tables).  List p owns the global
     vector indices [offsets[p], offsets[p+1]) and labels are the global indices."""
     DIM, M, K, MA, KEEP = 96, 16, 65536, 128, 0.0005
     rng = np.random.default_rng(77)
@@ -177,6 +180,8 @@ def leg_config5_sharded(qadc, torch, dist, sharding, codes_torch, codes_torch_at
     ix.set_pq(DIM, M, cb); ix.set_coarse(cents)
     local_sizes = np.zeros(K, np.uint32); local_sizes[p_lo:p_hi] = sizes[p_lo:p_hi]
     ix.begin_database(local_sizes, True)
+    owned = np.zeros(K, bool); owned[p_lo:p_hi] = True
+    ix.set_owned_partitions(owned)
     codes = codes_torch(v_lo, v_hi, dev)
     labels = torch.arange(v_lo, v_hi, dtype=torch.int64, device=dev).to(torch.int32)
     stream.synchronize()
@@ -200,6 +205,8 @@ def leg_config5_sharded(qadc, torch, dist, sharding, codes_torch, codes_torch_at
     o_ids, o_d, o_cnt = torch.empty_like(d_ids), torch.empty_like(d_d), torch.empty_like(d_cnt)
     d_assign = torch.empty((nq, MA), dtype=torch.int32, device=dev)
     d_part = torch.empty((nq, MA), dtype=torch.int64, device=dev)
+    d_local = torch.empty((nq, R + 1), dtype=torch.float32, device=dev)
+    owner_computes = os.environ.get("QADC_IVF_REPLICATED_TABLES") != "1"
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 
     def step(record=False):
@@ -207,8 +214,11 @@ def leg_config5_sharded(qadc, torch, dist, sharding, codes_torch, codes_torch_at
         if world > 1:
             sharding.sharded_coarse_assign(ix, d_q, nq, MA, K, rank, world, d_part, d_assign)
             if record: ev[1].record(stream)
-            ix.search_assigned_device(d_q.data_ptr(), d_assign.data_ptr(), nq, MA, R, d_ids.data_ptr(), d_d.data_ptr(),
-                                      d_cnt.data_ptr(), d_keys.data_ptr())
+            if owner_computes:
+                sharding.owner_computes_search(ix, d_q, d_assign, nq, MA, R, d_local, d_ids, d_d, d_cnt, d_keys)
+            else:
+                ix.search_assigned_device(d_q.data_ptr(), d_assign.data_ptr(), nq, MA, R, d_ids.data_ptr(), d_d.data_ptr(),
+                                          d_cnt.data_ptr(), d_keys.data_ptr())
             if record: ev[2].record(stream)
             gk, gi = sharding.all_gather_topk(d_keys, d_ids)
             if record: ev[3].record(stream)
@@ -233,7 +243,7 @@ def leg_config5_sharded(qadc, torch, dist, sharding, codes_torch, codes_torch_at
     ms = e0.elapsed_time(e1) / steps
     step(record=True)
     torch.cuda.synchronize(dev)
-    stage = dict(coarse_assign_incl_allgather=ev[0].elapsed_time(ev[1]), tables_and_list_scan=ev[1].elapsed_time(ev[2]),
+    stage = dict(coarse_assign_incl_allgather=ev[0].elapsed_time(ev[1]), tables_bounds_exchange_and_list_scan=ev[1].elapsed_time(ev[2]),
                  topk_allgather=ev[2].elapsed_time(ev[3]), shard_merge=ev[3].elapsed_time(ev[4]))
     if world > 1:
         t = torch.tensor([ms] + list(stage.values()), device=dev)
@@ -283,7 +293,8 @@ def leg_config5_sharded(qadc, torch, dist, sharding, codes_torch, codes_torch_at
     out = dict(config="5: Deep1B-shaped IVF-65536 PQ 16x4 (96-d), nprobe 128, inverted lists sharded over the GPUs",
                n_vectors=n_total, n_gpus=world, queries=nq, r=R, keep=KEEP, ms=ms, queries_per_s=nq / (ms * 1e-3),
                value=scanned * nq / (ms * 1e-3), unit="vectors scanned/s (all GPUs)", stage_ms=stage,
-               build_seconds=build_s, verify=dict(queries=check, ok=ok,
+               build_seconds=build_s, table_pipeline="owner computes" if (owner_computes and world > 1) else "replicated",
+               verify=dict(queries=check, ok=ok,
                                                   method="per-shard canonical top-r from qadc_dump_distances + numpy, gathered, merged on the host"))
     ix.close()
     return out
