@@ -190,6 +190,20 @@ int launch_flat_wr(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
     return QADC_OK;
 }
 
+template <int M, int QB, int NW, int NSW>
+int launch_flat_wrq(qadc_ctx* ctx, FlatScanArgs a, int chunks) {
+    using Cfg = WarpRingBatchCfg<M, QB, NW, NSW>;
+    const size_t smem = Cfg::smem_bytes(a.cap);
+    if (smem > kMaxSmem) return QADC_ENOMEM;
+    auto kern = scan_flat_wrq_kernel<M, QB, NW, NSW>;
+    QCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid(chunks, (a.nq + QB - 1) / QB);
+    kern<<<grid, Cfg::kThreads, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    QCK(cudaGetLastError());
+    return QADC_OK;
+}
+
 struct FlatVariant {
     int m, qb, nw, ns;
     int (*launch)(qadc_ctx*, FlatScanArgs, int);
@@ -209,6 +223,8 @@ struct FlatVariant {
 // in order of preference per (m, qb): 15 consumer warps when the lists fit, else 8
 const FlatVariant kFlatVariants[] = {
     {16, 1, QADC_NWR, QADC_NSWR * QADC_NPSR, launch_flat_wr<QADC_NWR, QADC_NSWR, QADC_NPSR>, WarpRingCfg<QADC_NWR, QADC_NSWR, QADC_NPSR>::smem_bytes, QADC_NPSR},
+#define QADC_FLAT_WRQ(M, QB, NW, NSW) {M, QB, NW, NSW, launch_flat_wrq<M, QB, NW, NSW>, WarpRingBatchCfg<M, QB, NW, NSW>::smem_bytes, 1}
+    QADC_FLAT_WRQ(16, 2, 16, 4), QADC_FLAT_WRQ(16, 4, 16, 2), QADC_FLAT_WRQ(32, 1, 16, 2), QADC_FLAT_WRQ(32, 2, 16, 2),
     QADC_FLAT_VARIANT(16, 1, QADC_NW1, QADC_NS1), QADC_FLAT_VARIANT(16, 1, 8, 4),
     QADC_FLAT_VARIANT(16, 2, 15, 3), QADC_FLAT_VARIANT(16, 2, 8, 4),
     QADC_FLAT_VARIANT(16, 4, 15, 3), QADC_FLAT_VARIANT(16, 4, 8, 4),
@@ -222,7 +238,8 @@ struct FlatPlan { const FlatVariant* v; int qb, nw, chunks, cap; uint32_t sb_per
 int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     const int M = ctx->m;
     int qb = static_cast<int>(ctx->opt_flat_qb);
-    if (qb <= 0) qb = (nq >= 2) ? 2 : 1;   // measured best for batches (config 1: 676 vs 563 (1) / 502 (4) G pairs/s)
+    // measured on config 1 (1M x 16x4, 10 000 queries, per-warp-ring batched kernel): 709 (4) / 669 (2) / 511 (1) G pairs/s
+    if (qb <= 0) qb = (nq >= 4 && M == 16) ? 4 : (nq >= 2) ? 2 : 1;
     if (M == 32 && qb > 2) qb = 2;
     if (qb > 4) qb = 4;
     if (qb == 3) qb = 2;

@@ -103,6 +103,16 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(leader));
     return leader != 0;
 }
+// Orders the TMA refill of a ring slot behind the shared-memory loads that read the slot.  Returns 0, computed FROM the
+// last loaded word (times a run-time zero the compiler cannot see through), to be added to the refill's byte count: the
+// refill's operands then depend on the load, so the instruction stream cannot reach the refill while a load still sits in
+// the LSU queue.  (A storm of 128-bit table loads of the other warps can hold it there longer than an L2-hit TMA copy
+// takes: the batched kernel then saw code words of the NEXT superblock — found by the variant-agreement test.)
+__device__ __forceinline__ uint32_t zero_after_loads(uint32_t last_loaded_word, uint32_t runtime_zero) {
+    uint32_t d;
+    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(d) : "r"(last_loaded_word), "r"(runtime_zero));
+    return d;
+}
 // keeps a loop-invariant value in a register instead of letting the compiler rematerialise it
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
 
@@ -149,6 +159,27 @@ __device__ __forceinline__ void lut_pair(uint32_t w0, uint32_t w1, const uint4& 
                              fadd(prmt(t1.x, t1.y, w1), prmt(t1.z, t1.w, x1), k), k);
     const uint32_t pb = fadd(fadd(prmt(t0.x, t0.y, hi16(w0, k)), prmt(t0.z, t0.w, hi16(x0, k)), k),
                              fadd(prmt(t1.x, t1.y, hi16(w1, k)), prmt(t1.z, t1.w, hi16(x1, k)), k), k);
+    g.v[0] = __dp4a(pa, k.s0, FIRST ? start : g.v[0]); g.v[1] = __dp4a(pa, k.s1, FIRST ? start : g.v[1]);
+    g.v[2] = __dp4a(pa, k.s2, FIRST ? start : g.v[2]); g.v[3] = __dp4a(pa, k.s3, FIRST ? start : g.v[3]);
+    g.v[4] = __dp4a(pb, k.s0, FIRST ? start : g.v[4]); g.v[5] = __dp4a(pb, k.s1, FIRST ? start : g.v[5]);
+    g.v[6] = __dp4a(pb, k.s2, FIRST ? start : g.v[6]); g.v[7] = __dp4a(pb, k.s3, FIRST ? start : g.v[7]);
+}
+// The same pair with the four selectors of each code word prepared by the caller (Sel): several queries that share
+// a pass over the codes share them too (3 ALU-pipe operations per word that are then paid once, not once per query).
+struct Sel {
+    uint32_t w, x, wh, xh;   // word, word ^ 0x88888888, and their upper halves
+};
+__device__ __forceinline__ Sel make_sel(uint32_t w, const PipeK& k) {
+    const uint32_t x = w ^ 0x88888888u;
+    return Sel{w, x, hi16(w, k), hi16(x, k)};
+}
+template <bool FIRST>
+__device__ __forceinline__ void lut_pair_sel(const Sel& s0, const Sel& s1, const uint4& t0, const uint4& t1, GroupAcc& g,
+                                             const PipeK& k, uint32_t start) {
+    const uint32_t pa = fadd(fadd(prmt(t0.x, t0.y, s0.w), prmt(t0.z, t0.w, s0.x), k),
+                             fadd(prmt(t1.x, t1.y, s1.w), prmt(t1.z, t1.w, s1.x), k), k);
+    const uint32_t pb = fadd(fadd(prmt(t0.x, t0.y, s0.wh), prmt(t0.z, t0.w, s0.xh), k),
+                             fadd(prmt(t1.x, t1.y, s1.wh), prmt(t1.z, t1.w, s1.xh), k), k);
     g.v[0] = __dp4a(pa, k.s0, FIRST ? start : g.v[0]); g.v[1] = __dp4a(pa, k.s1, FIRST ? start : g.v[1]);
     g.v[2] = __dp4a(pa, k.s2, FIRST ? start : g.v[2]); g.v[3] = __dp4a(pa, k.s3, FIRST ? start : g.v[3]);
     g.v[4] = __dp4a(pb, k.s0, FIRST ? start : g.v[4]); g.v[5] = __dp4a(pb, k.s1, FIRST ? start : g.v[5]);

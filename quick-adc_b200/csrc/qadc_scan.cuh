@@ -318,6 +318,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
     uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty);
     pin(slot); pin(sb); pin(n_left);   // full_a / empty_a are compile-time offsets from the shared-memory base
     uint32_t stage = 0, phase = 0;
+    const uint32_t rt_zero = pk.one - 1u;   // 0 (PipeK::one is 1, a kernel argument the compiler cannot fold)
     int lbound[QB], gb[QB];   // strict local bound, shared bound (refreshed once per ring revolution)
 #pragma unroll
     for (int qi = 0; qi < QB; ++qi) {
@@ -395,8 +396,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
             uint4 w[Cfg::kQuads];
 #pragma unroll
             for (int q = 0; q < Cfg::kQuads; ++q) w[q] = lds128(src + q * 512);
+            const uint32_t landed = zero_after_loads(w[Cfg::kQuads - 1].w, rt_zero);   // 0, available once the loads have landed
             __syncwarp();
-            if (lane == 0) mbar_arrive_a(empty_a + stage * 8);   // the words are in registers: release the stage early
+            if (lane == 0) mbar_arrive_a(empty_a + stage * 8 + landed);   // the words are in registers: release the stage early
             bool reload = false;
             if (stage == 0) {
                 // the shared bound is read once per ring revolution and used one revolution later: the load
@@ -484,24 +486,34 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
 #pragma unroll
                     for (int qi = 0; qi < QB; ++qi) gb_next[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
                 }
+                const uint32_t landed = zero_after_loads(w[Cfg::kQuads - 1].w, rt_zero);   // 0, available once the loads have landed
                 __syncwarp();
-                if (lane == 0) mbar_arrive_a(empty_a + stage * 8);   // the words are in registers: release the stage early
+                if (lane == 0) mbar_arrive_a(empty_a + stage * 8 + landed);   // the words are in registers: release the stage early
+                // quad-outer, query-inner: the selectors of a quad's four code words (XOR + two shifts per word, on
+                // the ALU pipe that binds this regime) are prepared once and used by all QB queries
+                GroupAcc g[QB];
+                uint32_t bound[QB];
+#pragma unroll
+                for (int qi = 0; qi < QB; ++qi) bound[qi] = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
+                // (Early abandon — skipping the last sub-quantisers once every vector of the superblock has reached
+                // the bound — is exact but was measured 5 % slower: the vote/branch splits the unrolled lookup chain.)
+#pragma unroll
+                for (int q = 0; q < Cfg::kQuads; ++q) {
+                    const Sel s0 = make_sel(w[q].x, pk), s1 = make_sel(w[q].y, pk), s2 = make_sel(w[q].z, pk), s3 = make_sel(w[q].w, pk);
+#pragma unroll
+                    for (int qi = 0; qi < QB; ++qi) {
+                        const uint4* tq = qtab + qi * M + 4 * q;
+                        const uint4 t0 = tq[0], t1 = tq[1], t2 = tq[2], t3 = tq[3];
+                        if (q == 0) lut_pair_sel<true>(s0, s1, t0, t1, g[qi], pk, 0u - bound[qi]);
+                        else lut_pair_sel<false>(s0, s1, t0, t1, g[qi], pk, 0u);
+                        lut_pair_sel<false>(s2, s3, t2, t3, g[qi], pk, 0u);
+                    }
+                }
 #pragma unroll
                 for (int qi = 0; qi < QB; ++qi) {
-                    if (qi < nqb) {
-                        const uint32_t bound = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
-                        GroupAcc g;
-                        // (Early abandon — skipping the last sub-quantisers once every vector of the superblock
-                        // has reached the bound — is exact but was measured 5 % slower: the vote/branch splits
-                        // the unrolled lookup chain.)
-#pragma unroll
-                        for (int p = 0; p < M / 2; ++p) {   // pairs of sub-quantisers
-                            const uint4 t0 = qtab[qi * M + 2 * p], t1 = qtab[qi * M + 2 * p + 1];
-                            const uint4& wq = w[p >> 1];
-                            scan_pair(p == 0, (p & 1) ? wq.z : wq.x, (p & 1) ? wq.w : wq.y, t0, t1, g, pk, bound);
-                        }
-                        const bool mine = any_below(g);
-                        if (__any_sync(0xffffffffu, mine)) emit_group(g, mine, bound, qi, sb);   // rare
+                    if (qi < nqb) {   // (a missing query of the last group has all-127 tables: it never has a candidate)
+                        const bool mine = any_below(g[qi]);
+                        if (__any_sync(0xffffffffu, mine)) emit_group(g[qi], mine, bound[qi], qi, sb);   // rare
                     }
                 }
                 if (stage == 0) {
@@ -676,17 +688,6 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
             uint4 w[4];
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) w[qd] = lds128(src + qd * 512);
-            if (NPS == 1 || h + 1 == nsb) {
-                __syncwarp();
-                if (i < n_refill && elect_one()) {   // the unit's words are in registers: refill the slot at once
-                    const uint32_t bytes = unit_bytes(i + NSW);
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_r + slot * 8), "r"(bytes) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                     ring_w + slot * Cfg::kSlotBytes),
-                                 "l"(refill), "r"(bytes), "r"(full_r + slot * 8)
-                                 : "memory");
-                }
-            }
             // rare: some vector of the superblock is a candidate
             auto emit = [&](const GroupAcc& g, const bool mine) {
                 const uint32_t sb = first + i * (NW * NPS) + h;
@@ -742,6 +743,22 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
                 const bool mine = any_below(g);
                 if (__any_sync(0xffffffffu, mine)) emit(g, mine);
             }
+            // The slot is refilled HERE, behind the vote that consumed every code word of the superblock: instructions
+            // issue in order, so all four shared-memory loads have landed by now.  (Issued right behind the loads, as the
+            // first version did, the copy depends on nothing they produce; a load still queued in the LSU when an
+            // L2-hit TMA copy lands would then read the NEXT superblock — observed in the batched kernel, whose table
+            // loads keep the LSU busy.  Costs nothing: three slots are in flight while this one is computed.)
+            if (NPS == 1 || h + 1 == nsb) {
+                __syncwarp();
+                if (i < n_refill && elect_one()) {
+                    const uint32_t bytes = unit_bytes(i + NSW);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_r + slot * 8), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     ring_w + slot * Cfg::kSlotBytes),
+                                 "l"(refill), "r"(bytes), "r"(full_r + slot * 8)
+                                 : "memory");
+                }
+            }
             if (slot == 0 && (NPS == 1 || h == 0)) {
                 // once per ring revolution: the shared bound read one revolution ago (never waited for), the filter's
                 // pass-rate score decays, a tighter clamped table is built when the bound has moved enough
@@ -782,6 +799,212 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
     bitonic_sort_u64(scratch, n_sort, threadIdx.x, NW * 32, BlockSync());
     uint64_t* dst = a.lists + (static_cast<size_t>(q) * a.n_lists + blockIdx.x) * a.r;
     for (int i = threadIdx.x; i < a.r; i += NW * 32) dst[i] = scratch[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Flat scan, QB queries per pass (any M), PER-WARP rings: the batched regime of configs 1 and 3 (many queries over a
+// database that the L2 holds or that every pass streams).  Same ring as scan_flat_wr_kernel — warp w owns superblocks
+// sb0 + w, sb0 + w + NW, ... and keeps NSW one-superblock TMA bulk copies in flight into its own slots — around the
+// shared-selector lookup loop of scan_flat_kernel's batched path (tables of the QB queries in shared memory, selectors
+// of a quad prepared once for all of them).  ncu on config 1 with the CTA-wide ring (profiles/r02_flat_batched_*):
+// 9 % of all executed instructions were barrier spins (6 % of them the producer warp's), 10 % of the samples sat at the
+// `full` barrier: a warp that takes the rare path (candidate lists, compaction) holds back the refill of the stage for
+// the other 14.  Here nobody waits for anybody else and the 16th warp computes.
+// ------------------------------------------------------------------------------------------
+template <int M, int QB, int NW, int NSW>
+struct WarpRingBatchCfg {
+    static constexpr int kQuads = M / 4, kSbBytes = M * 128;
+    static constexpr int kRingBytes = NW * NSW * kSbBytes;
+    static constexpr int kThreads = NW * 32;
+    // rings | tables | barriers | histograms + counters | list counts/bounds, rounded to 16 bytes
+    static constexpr int kFixedBytes = ((kRingBytes + QB * M * 16 + NW * NSW * 8 + QB * (128 + 2) * 4 + NW * QB * 8) + 15) / 16 * 16;
+    static size_t smem_bytes(int cap) { return static_cast<size_t>(kFixedBytes) + static_cast<size_t>(NW) * QB * cap * 8; }
+};
+
+template <int M, int QB, int NW, int NSW>
+__global__ void __launch_bounds__(NW * 32, 1) scan_flat_wrq_kernel(const FlatScanArgs a) {
+    using Cfg = WarpRingBatchCfg<M, QB, NW, NSW>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* rings = smem;                                                                 // [NW][NSW][kSbBytes]
+    uint4* qtab = reinterpret_cast<uint4*>(rings + Cfg::kRingBytes);                       // [QB][M]
+    uint64_t* full = reinterpret_cast<uint64_t*>(qtab + QB * M);                           // [NW][NSW]
+    int* hist = reinterpret_cast<int*>(full + NW * NSW);                                   // [QB][128]
+    int* hist_total = hist + QB * 128;                                                     // [QB]
+    int* hist_next = hist_total + QB;                                                      // [QB]
+    int* cnt = hist_next + QB;                                                             // [NW][QB]
+    int* bnd = cnt + NW * QB;
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem + Cfg::kFixedBytes);                // [NW][QB][cap]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sb0 = min(blockIdx.x * a.sb_per_chunk, a.n_sb);
+    const uint32_t sb1 = min(sb0 + a.sb_per_chunk, a.n_sb);
+    const int qbase = blockIdx.y * QB;
+    const int nqb = min(QB, a.nq - qbase);
+    const PipeK pk = a.k;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NW * NSW; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < QB * M; i += blockDim.x) {
+        const int qi = i / M;
+        qtab[i] = (qi < nqb) ? reinterpret_cast<const uint4*>(a.qtabs)[static_cast<size_t>(qbase) * M + i]
+                             : make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+    }
+    for (int i = threadIdx.x; i < NW * QB * a.cap; i += blockDim.x) lists[i] = kEmptyKey;
+    for (int i = threadIdx.x; i < NW * QB; i += blockDim.x) { cnt[i] = 0; bnd[i] = 127; }
+    for (int i = threadIdx.x; i < QB * 128; i += blockDim.x) hist[i] = 0;
+    for (int i = threadIdx.x; i < QB; i += blockDim.x) { hist_total[i] = 0; hist_next[i] = a.r; }
+    __syncthreads();
+
+    // (warp, query) candidate lists; the rare path takes the query as a RUNTIME index so that it exists once in the
+    // code (inlined once per query it made the QB = 4 loop miss the instruction cache: no_instruction 3.4 stalls/issue)
+    auto list_of = [&](int qi) { return WarpList{lists + (static_cast<size_t>(warp) * QB + qi) * a.cap, cnt + warp * QB + qi, bnd + warp * QB + qi}; };
+    const int halves = (a.cap < a.r + kSbVec) ? 2 : 1;
+    const int compact_at = min(a.cap - kSbVec / halves, 2 * a.r);
+
+    // this warp's superblocks: sb0 + warp + i * NW, i < n_mine
+    const uint32_t first = sb0 + warp;
+    const uint32_t n_mine = (first < sb1) ? (sb1 - first + NW - 1) / NW : 0;
+    const uint32_t ring_a = smem_u32(rings) + warp * (NSW * Cfg::kSbBytes);
+    const uint32_t full_a = smem_u32(full) + warp * (NSW * 8);
+    const uint8_t* src0 = a.codes + static_cast<size_t>(first) * Cfg::kSbBytes;
+    if (lane == 0)
+        for (uint32_t i = 0; i < min(n_mine, static_cast<uint32_t>(NSW)); ++i) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_a + i * 8), "r"(Cfg::kSbBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             ring_a + i * Cfg::kSbBytes),
+                         "l"(src0 + static_cast<size_t>(i) * (NW * Cfg::kSbBytes)), "r"(Cfg::kSbBytes), "r"(full_a + i * 8)
+                         : "memory");
+        }
+
+    int lbound[QB], gb[QB];   // strict local bound, shared bound (refreshed once per ring revolution)
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) {
+        lbound[qi] = 127;
+        gb[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
+    }
+    // rare path of one (superblock, query): returns the shared-bound candidate in hb and the list's strict bound in lb
+    auto emit_group = [&](const GroupAcc& g, const bool mine, const uint32_t bound, const int qi, const uint32_t sb, int& hb_out, int& lb_out) {
+        WarpList wl = list_of(qi);
+        for (int half = 0; half < halves; ++half) {
+            const int before = *wl.count;
+            __syncwarp();
+            const bool my_turn = halves == 1 || (lane >> 4) == half;
+            if (mine && my_turn) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl, hist + qi * 128);
+            __syncwarp();
+            const int now = *wl.count;
+            const int hb = hist_update(hist + qi * 128, hist_total + qi, hist_next + qi, now - before, a.r, lane,
+                                       a.shared_bound + qbase + qi);
+            if (hb < hb_out) hb_out = hb;
+            if (now >= compact_at) {
+                wl.compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
+                lb_out = *wl.bound;
+            }
+        }
+    };
+
+    uint32_t phase = 0;
+    uint32_t ring_r = ring_a + lane * 16, ring_w = ring_a, full_r = full_a;
+    pin(ring_r); pin(ring_w); pin(full_r);
+    const uint8_t* refill = src0 + static_cast<size_t>(NSW) * (NW * Cfg::kSbBytes);   // source of superblock i + NSW
+    const uint32_t n_refill = n_mine > NSW ? n_mine - NSW : 0;
+    uint32_t slot = 0;
+    for (uint32_t i = 0; i < n_mine; ++i) {
+        mbar_wait_a(full_r + slot * 8, phase);
+        const uint32_t src = ring_r + slot * Cfg::kSbBytes;
+        uint4 w[Cfg::kQuads];
+#pragma unroll
+        for (int q = 0; q < Cfg::kQuads; ++q) w[q] = lds128(src + q * 512);
+        int gb_next[QB];
+        if (slot == 0) {
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) gb_next[qi] = (qi < nqb) ? load_shared_bound(a.shared_bound + qbase + qi) : 0;
+        }
+        GroupAcc g[QB];
+        uint32_t bound[QB];
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) bound[qi] = static_cast<uint32_t>(min(lbound[qi], gb[qi] + 1));
+#pragma unroll
+        for (int q = 0; q < Cfg::kQuads; ++q) {
+            const Sel s0 = make_sel(w[q].x, pk), s1 = make_sel(w[q].y, pk), s2 = make_sel(w[q].z, pk), s3 = make_sel(w[q].w, pk);
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) {
+                const uint4* tq = qtab + qi * M + 4 * q;
+                const uint4 t0 = tq[0], t1 = tq[1], t2 = tq[2], t3 = tq[3];
+                if (q == 0) lut_pair_sel<true>(s0, s1, t0, t1, g[qi], pk, 0u - bound[qi]);
+                else lut_pair_sel<false>(s0, s1, t0, t1, g[qi], pk, 0u);
+                lut_pair_sel<false>(s2, s3, t2, t3, g[qi], pk, 0u);
+            }
+        }
+        // one vote for all QB queries (a missing query of the last group has all-127 tables: it never has a candidate)
+        uint32_t mine_mask = 0;
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) mine_mask |= any_below(g[qi]) ? (1u << qi) : 0u;
+        if (__any_sync(0xffffffffu, mine_mask != 0)) {   // rare: some vector of the superblock is a candidate of some query
+            uint32_t pend = __reduce_or_sync(0xffffffffu, mine_mask);
+#pragma unroll 1
+            while (pend) {
+                const int qi = __ffs(pend) - 1;
+                pend &= pend - 1;
+                GroupAcc gs = g[0];
+                uint32_t bs = bound[0];
+#pragma unroll
+                for (int u = 1; u < QB; ++u)
+                    if (u == qi) { gs = g[u]; bs = bound[u]; }
+                int hb = 127, lb = 127;
+                emit_group(gs, (mine_mask >> qi) & 1u, bs, qi, first + i * NW, hb, lb);
+#pragma unroll
+                for (int u = 0; u < QB; ++u)
+                    if (u == qi) { gb[u] = min(gb[u], hb); lbound[u] = min(lbound[u], lb); }
+            }
+        }
+        // The slot is refilled behind the vote that consumed every code word of the superblock: instructions issue in
+        // order, so the shared-memory loads of the slot have landed.  (Issued right behind the loads, the copy depends on
+        // nothing they produce, and the table loads of the other warps can hold a code-word load in the LSU queue longer
+        // than an L2-hit TMA copy takes: the warp then read words of the NEXT superblock — caught by the variant-agreement
+        // test, ~3 % of the queries of a 4-queries-per-pass run.)
+        __syncwarp();
+        if (i < n_refill && elect_one()) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_r + slot * 8), "r"(Cfg::kSbBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             ring_w + slot * Cfg::kSbBytes),
+                         "l"(refill), "r"(Cfg::kSbBytes), "r"(full_r + slot * 8)
+                         : "memory");
+        }
+        refill += NW * Cfg::kSbBytes;
+        if (slot == 0) {
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) gb[qi] = min(gb[qi], gb_next[qi]);
+        }
+        if (++slot == NSW) { slot = 0; phase ^= 1; }
+    }
+
+    // ---- final: one sorted list per (CTA, query) when the NW warp lists fit a CTA-wide sort in the idle rings,
+    // else one list per (warp, query) ----
+    const bool cta_merge = a.n_lists == static_cast<int>(gridDim.x);
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(rings);
+#pragma unroll 1
+    for (int qi = 0; qi < nqb; ++qi)
+        list_of(qi).compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
+    if (!cta_merge) {
+#pragma unroll 1
+        for (int qi = 0; qi < nqb; ++qi)
+                store_list(list_of(qi), a.lists + (static_cast<size_t>(qbase + qi) * a.n_lists + blockIdx.x * NW + warp) * a.r, a.r, lane);
+        return;
+    }
+    int n_sort = 64;
+    while (n_sort < NW * a.r) n_sort <<= 1;
+#pragma unroll 1
+    for (int qi = 0; qi < nqb; ++qi) {   // CTA-uniform
+        __syncthreads();        // every warp has consumed its ring / the previous query is stored
+        for (int i = lane; i < a.r; i += 32) scratch[warp * a.r + i] = list_of(qi).keys[i];
+        for (int i = NW * a.r + threadIdx.x; i < n_sort; i += NW * 32) scratch[i] = kEmptyKey;
+        __syncthreads();
+        bitonic_sort_u64(scratch, n_sort, threadIdx.x, NW * 32, BlockSync());
+        uint64_t* dst = a.lists + (static_cast<size_t>(qbase + qi) * a.n_lists + blockIdx.x) * a.r;
+        for (int i = threadIdx.x; i < a.r; i += NW * 32) dst[i] = scratch[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
