@@ -530,7 +530,7 @@ def run_ours(args):
             "configs": configs,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "scan_flat_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "scan_flat_wr_kernel<16,4> (one query per pass, per-warp TMA rings)" if qb_used == 1 else "scan_flat_wrq_kernel (several queries per pass)",
                          "kernel_ms": t_scan * 1e3, "kernel_share_of_step": t_scan * 1e3 / ms_step,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": passes * n_local * CODE_BYTES},
