@@ -77,24 +77,35 @@ int mensure(qadc_multi* mm, int g, DevBuf& b, size_t bytes) {
     return QADC_OK;
 }
 
-// all-gather of `bytes` per shard: send[g] -> recv[g] laid out [G][bytes] on every device
-int multi_all_gather(qadc_multi* mm, const std::vector<const void*>& send, const std::vector<void*>& recv, size_t bytes) {
+// all-gathers of `bytes` per shard: send[g] -> recv[g] laid out [G][bytes] on every device; all jobs of one call travel
+// in ONE NCCL group (a single fused launch per device)
+struct GatherJob {
+    std::vector<const void*> send;
+    std::vector<void*> recv;
+    size_t bytes;
+};
+int multi_all_gather(qadc_multi* mm, const std::vector<GatherJob>& jobs) {
     if (mm->use_nccl) {
         MNCCL(mm->pGroupStart());
-        for (int g = 0; g < mm->G; ++g) {
-            ncclResult_t r = mm->pAllGather(send[g], recv[g], bytes, ncclUint8, mm->comms[g], mm->ctx[g]->stream);
-            if (r != ncclSuccess) { mm->pGroupEnd(); return mfail(mm, QADC_ECUDA, std::string("ncclAllGather: ") + mm->pGetErrorString(r)); }
-        }
+        for (const GatherJob& j : jobs)
+            for (int g = 0; g < mm->G; ++g) {
+                ncclResult_t r = mm->pAllGather(j.send[g], j.recv[g], j.bytes, ncclUint8, mm->comms[g], mm->ctx[g]->stream);
+                if (r != ncclSuccess) { mm->pGroupEnd(); return mfail(mm, QADC_ECUDA, std::string("ncclAllGather: ") + mm->pGetErrorString(r)); }
+            }
         MNCCL(mm->pGroupEnd());
         return QADC_OK;
     }
     // virtual shards on one device: every source stream must have produced its buffer before anyone copies it
     for (int g = 0; g < mm->G; ++g) MCK(cudaStreamSynchronize(mm->ctx[g]->stream));
-    for (int g = 0; g < mm->G; ++g)
-        for (int s = 0; s < mm->G; ++s)
-            MCK(cudaMemcpyAsync(static_cast<uint8_t*>(recv[g]) + static_cast<size_t>(s) * bytes, send[s], bytes,
-                                cudaMemcpyDeviceToDevice, mm->ctx[g]->stream));
+    for (const GatherJob& j : jobs)
+        for (int g = 0; g < mm->G; ++g)
+            for (int s = 0; s < mm->G; ++s)
+                MCK(cudaMemcpyAsync(static_cast<uint8_t*>(j.recv[g]) + static_cast<size_t>(s) * j.bytes, j.send[s], j.bytes,
+                                    cudaMemcpyDeviceToDevice, mm->ctx[g]->stream));
     return QADC_OK;
+}
+int multi_all_gather(qadc_multi* mm, const std::vector<const void*>& send, const std::vector<void*>& recv, size_t bytes) {
+    return multi_all_gather(mm, std::vector<GatherJob>{GatherJob{send, recv, bytes}});
 }
 
 }  // namespace
@@ -351,16 +362,15 @@ int qadc_multi_search(qadc_multi* mm, const float* queries, int nq, int ma, int 
     const int8_t* d_dists = mm->sh[0].dists.as<int8_t>();
     const int32_t* d_counts = mm->sh[0].counts.as<int32_t>();
     if (G > 1) {
-        std::vector<const void*> send(G);
-        std::vector<void*> recv(G);
-        for (int g = 0; g < G; ++g) { send[g] = mm->sh[g].keys.p; recv[g] = mm->sh[g].gkeys.p; }
-        int rc = multi_all_gather(mm, send, recv, nr * 8);
-        if (rc) return rc;
-        if (ivf) {   // labels travel with their keys; a flat id is the key's low 32 bits
-            for (int g = 0; g < G; ++g) { send[g] = mm->sh[g].ids.p; recv[g] = mm->sh[g].gids.p; }
-            rc = multi_all_gather(mm, send, recv, nr * 4);
-            if (rc) return rc;
+        std::vector<GatherJob> jobs(ivf ? 2 : 1);   // labels travel with their keys; a flat id is the key's low 32 bits
+        jobs[0].bytes = nr * 8;
+        if (ivf) jobs[1].bytes = nr * 4;
+        for (int g = 0; g < G; ++g) {
+            jobs[0].send.push_back(mm->sh[g].keys.p); jobs[0].recv.push_back(mm->sh[g].gkeys.p);
+            if (ivf) { jobs[1].send.push_back(mm->sh[g].ids.p); jobs[1].recv.push_back(mm->sh[g].gids.p); }
         }
+        int rc = multi_all_gather(mm, jobs);
+        if (rc) return rc;
         MCK(cudaSetDevice(mm->devices[0]));
         MCK(cudaEventRecord(mm->ev[3], mm->ctx[0]->stream));
         auto& s0 = mm->sh[0];

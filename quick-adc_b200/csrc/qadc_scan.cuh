@@ -1322,7 +1322,17 @@ __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(const MergeA
     const int total = a.L * a.r;
     const int step = kMergeCap / 2;   // inputs per round; buffer holds <= r <= cap/2 before a round
     int first_base = 0;
-    if (a.init_bound) {
+    if (a.shard_major && !a.init_bound) {
+        // Shard merge: every input list is sorted, so the r-th key of a FULL list bounds the result (that shard alone holds
+        // r keys at or below it); with the smallest such key as the filter ~r-and-a-few of the L * r keys survive and the
+        // sort shrinks from 1024 to 128-256 slots (config 5 on 8 GPUs: 0.57 ms per 10 000-query batch before).
+        for (int l = tid; l < a.L; l += kMergeThreads) {
+            const unsigned long long last = a.in_keys[(static_cast<size_t>(l) * a.nq + q) * a.r + a.r - 1];
+            if (last != kEmptyKey) atomicMin(&bound_key, last + 1);   // strict filter below: keep keys <= last
+        }
+        __syncthreads();
+    }
+    if (a.init_bound || a.shard_major) {
         // Fast path: with the scan's final shared bound as the filter only r-and-a-few keys survive, so one pass
         // without per-round barriers collects them all (148 lists x 100 keys: 15 rounds of load -> barrier -> barrier
         // cost 87 us per step of the 1e9 scan); if they do not fit the buffer the streaming rounds below start over.

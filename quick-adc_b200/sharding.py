@@ -83,8 +83,20 @@ def all_gather_topk(keys, ids, group=None):
     nq = keys.shape[0]
     gk = torch.empty((world * nq,) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
     gi = torch.empty((world * nq,) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
-    dist.all_gather_into_tensor(gk, keys.contiguous(), group=group)   # concatenation along dim 0
-    dist.all_gather_into_tensor(gi, ids.contiguous(), group=group)
+    k, i = keys.contiguous(), ids.contiguous()
+    coalesce = getattr(dist, "_coalescing_manager", None) if keys.is_cuda else None
+    done = False
+    if coalesce is not None:
+        try:   # both all-gathers in ONE NCCL group launch (ncclGroupStart/End): one kernel, one latency
+            with coalesce(group=group, device=keys.device, async_ops=False):
+                dist.all_gather_into_tensor(gk, k, group=group)   # concatenation along dim 0
+                dist.all_gather_into_tensor(gi, i, group=group)
+            done = True
+        except (TypeError, RuntimeError, AssertionError):
+            done = False
+    if not done:
+        dist.all_gather_into_tensor(gk, k, group=group)
+        dist.all_gather_into_tensor(gi, i, group=group)
     return gk.view((world,) + tuple(keys.shape)), gi.view((world,) + tuple(ids.shape))
 
 
