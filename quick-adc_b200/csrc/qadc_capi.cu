@@ -395,7 +395,7 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
     const size_t fused_smem = ivf_prep_smem_bytes(M, ma, dim);
     // (two CTAs per SM or it loses to the separate kernels: measured 6.3 vs 5.7 ms on config 5, nprobe 128, where the
     // tables of one query take 128 KB; opt_ivf_fused = 2 forces it whenever it fits)
-    const size_t fused_limit = ctx->opt_ivf_fused >= 2 ? static_cast<size_t>(kMaxSmem) - 2048 : 100 * 1024;
+    const size_t fused_limit = ctx->opt_ivf_fused >= 2 ? static_cast<size_t>(kMaxSmem) - 2048 : 112 * 1024;
     const bool fused = !flat && ctx->opt_ivf_fused && fused_smem <= fused_limit &&
                        static_cast<uint64_t>(ma) * ctx->max_start <= (1u << 16);
     ENSURE(ctx->b_assign, nqa * 4);

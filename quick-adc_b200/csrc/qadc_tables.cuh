@@ -591,6 +591,7 @@ __host__ __device__ inline size_t ivf_prep_smem_bytes(int m, int ma, int dim) {
     b += static_cast<size_t>(8) * 2 * dim * 4;                // per-warp residual + rotated copy
     b += static_cast<size_t>(ma + 1) * 4 + static_cast<size_t>(ma) * 8;   // prefix offsets, first prefix vector of each probe
     b += 2 * kSelCap * 4;                                     // value buffers of the radix select
+    b += static_cast<size_t>(ma) * m * 16;                    // int8 tables (kept for the shared-bound seed)
     return b + 64;
 }
 
@@ -604,6 +605,7 @@ __global__ void __launch_bounds__(256) ivf_prepare_kernel(const IvfPrepArgs a) {
     int* poff = reinterpret_cast<int*>(pfirst + a.ma);                           // [ma + 1]
     uint32_t* vb0 = reinterpret_cast<uint32_t*>(poff + a.ma + 1);
     uint32_t* vb1 = vb0 + kSelCap;
+    int8_t* itab = reinterpret_cast<int8_t*>((reinterpret_cast<uintptr_t>(vb1 + kSelCap) + 15) & ~static_cast<uintptr_t>(15));   // [ma][TE]
     __shared__ int count, hist[256], state[2];
     __shared__ unsigned int bound;
     __shared__ float red[8];
@@ -682,10 +684,18 @@ __global__ void __launch_bounds__(256) ivf_prepare_kernel(const IvfPrepArgs a) {
                 float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int bl = 0; bl < blocks; ++bl) {
+                    float av[8];
+                    if ((dsq & 3) == 0) {   // 16-byte aligned sub-vectors: two 128-bit shared-memory loads (same values, same order)
+                        const float4 a0 = *reinterpret_cast<const float4*>(xa + bl * 8), a1 = *reinterpret_cast<const float4*>(xa + bl * 8 + 4);
+                        av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < 8; ++l) av[l] = xa[bl * 8 + l];
+                    }
 #pragma unroll
                     for (int l = 0; l < 8; ++l) {
                         const float bv = kRegCb ? cbr[kRegCb ? k : 0][(bl * 8 + l) % CBR] : __ldg(b + bl * 8 + l);
-                        const float diff = __fsub_rn(xa[bl * 8 + l], bv);
+                        const float diff = __fsub_rn(av[l], bv);
                         acc[l] = __fmaf_rn(diff, diff, acc[l]);
                     }
                 }
@@ -777,28 +787,20 @@ __global__ void __launch_bounds__(256) ivf_prepare_kernel(const IvfPrepArgs a) {
     }
     const float delta = __fdiv_rn(__fsub_rn(qmax, qmin), 127.0f);
     const float inv_delta = __fdiv_rn(1.0f, delta);
-    int8_t* itab = reinterpret_cast<int8_t*>(tab);   // the int8 tables take over the first quarter of the float tables
     const int entries = ma * TE;
     int8_t* gq = a.qtables + static_cast<size_t>(q) * entries;
-    for (int base = 0; base < entries; base += 4 * kSelThreads) {   // a chunk's bytes land below the floats still to be read
-        const int e = base + 4 * tid;
-        char4 out = make_char4(0, 0, 0, 0);
-        if (e < entries) {
-            const float4 v = *reinterpret_cast<const float4*>(tab + e);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-            int8_t qv[4];
+    for (int e = 4 * tid; e < entries; e += 4 * kSelThreads) {   // own shared-memory region: no barrier per chunk
+        const float4 v = *reinterpret_cast<const float4*>(tab + e);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        int8_t qv[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float x = vv[i] < 0.f ? 0.f : vv[i];
-                qv[i] = (x >= qmax) ? static_cast<int8_t>(127) : static_cast<int8_t>(quantize_entry(__fsub_rn(x, qmin), delta, inv_delta));
-            }
-            out = make_char4(qv[0], qv[1], qv[2], qv[3]);
+        for (int i = 0; i < 4; ++i) {
+            const float x = vv[i] < 0.f ? 0.f : vv[i];
+            qv[i] = (x >= qmax) ? static_cast<int8_t>(127) : static_cast<int8_t>(quantize_entry(__fsub_rn(x, qmin), delta, inv_delta));
         }
-        __syncthreads();
-        if (e < entries) {
-            *reinterpret_cast<char4*>(itab + e) = out;
-            *reinterpret_cast<char4*>(gq + e) = out;
-        }
+        const char4 out = make_char4(qv[0], qv[1], qv[2], qv[3]);
+        *reinterpret_cast<char4*>(itab + e) = out;
+        *reinterpret_cast<char4*>(gq + e) = out;
     }
     // ---- 5. the query's shared bound: r-th smallest int8 distance among the same prefix vectors ----
     hist[tid] = 0;
