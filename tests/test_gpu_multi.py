@@ -80,3 +80,36 @@ def test_multi_reports_errors(qadc):
         mi.search(synth.make_queries(rng, 2, 128), 1, 10)
     assert e.value.code == qadc.QADC_EBOUND
     mi.close()
+
+
+def test_multi_ivf_more_than_one_sub_batch_and_bound_error(qadc):
+    """The owner-computes exchange of qadc_multi_search runs in sub-batches of 32768 queries: 33000 queries (the first 200
+    repeated) return the single-GPU result for every copy; a keep so small that the probed prefixes hold fewer than r
+    vectors reports the reference's "Max quantization bound too high" (QADC_EBOUND) through the sharded bounds too."""
+    rng = np.random.default_rng(91)
+    dim, m, n, K, ma, r, keep = 64, 16, 40000, 40, 6, 20, 0.05
+    cb = synth.make_pq(rng, dim, m)
+    cents = (2 * rng.standard_normal((K, dim))).astype(np.float32)
+    codes, labels, offsets = synth.make_ivf(rng, n, K, m, empty=(3,))
+    base_q = synth.make_queries(rng, 200, dim)
+    q = np.tile(base_q, (165, 1))          # 33000 queries
+    one = qadc.Index(0)
+    one.set_pq(dim, m, cb); one.set_coarse(cents)
+    one.load_ivf(codes, labels, offsets, keep)
+    exp = one.search(base_q, ma, r)
+    one.close()
+    devs, _ = _devices()
+    mi = qadc.MultiIndex(devs)
+    mi.set_pq(dim, m, cb); mi.set_coarse(cents)
+    mi.load_ivf(codes, labels, offsets, keep)
+    ids, d, cnt = mi.search(q, ma, r)
+    for name, got, want in (("ids", ids, exp[0]), ("d", d, exp[1]), ("cnt", cnt, exp[2])):
+        assert np.array_equal(got.reshape((165, 200) + got.shape[1:]), np.broadcast_to(want, (165,) + want.shape)), name
+    mi.close()
+    mi = qadc.MultiIndex(devs)
+    mi.set_pq(dim, m, cb); mi.set_coarse(cents)
+    mi.load_ivf(codes, labels, offsets, 0.0001)     # one prefix vector per list: 6 probes x 1 < r
+    with pytest.raises(qadc.QadcError) as e:
+        mi.search(base_q[:4], ma, r)
+    assert e.value.code == qadc.QADC_EBOUND
+    mi.close()

@@ -1,4 +1,4 @@
-"""Debug helper: every flat-scan variant against the one-query-per-pass kernel on one database (also a racecheck target)."""
+"""Every flat-scan variant (queries per pass, chunking, ring type) against the one-query-per-pass kernel on one database (also a racecheck target)."""
 import os, sys, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
