@@ -77,7 +77,7 @@ struct qadc_ctx {
     int* d_err = nullptr;
     int* h_err = nullptr;   // pinned
     // options / accounting
-    long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1, opt_ivf_fused = 1, opt_flat_ring = 1;
+    long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1, opt_ivf_fused = 1, opt_flat_ring = 1, opt_flat_seed = 1;
     bool sbound_seeded = false;   // the fused inverted-list table kernel already wrote the shared bounds of this batch
     int ivf_sb_per_item = 8;   // superblocks per work item of the IVF scan (option "ivf_sb_per_item")
     int launches = 0;
@@ -289,10 +289,13 @@ int seed_shared_bound(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qt
     pa.hist = ctx->b_hist.as<unsigned int>();
     pa.owned_size = ctx->local_mode ? ctx->d_owned : nullptr;
     dim3 grid(pa.nsplit, nq);
-    if (ctx->m == 16) prefix_hist_kernel<16><<<grid, 256, 0, ctx->stream>>>(pa);
-    else prefix_hist_kernel<32><<<grid, 256, 0, ctx->stream>>>(pa);
-    ctx->launches++;
-    QCK(cudaGetLastError());
+    // flat_seed = 0 (flat databases): no histogram pass, the bound starts at 126 and the scan's own candidates tighten it
+    if (ctx->K != 0 || ctx->opt_flat_seed) {
+        if (ctx->m == 16) prefix_hist_kernel<16><<<grid, 256, 0, ctx->stream>>>(pa);
+        else prefix_hist_kernel<32><<<grid, 256, 0, ctx->stream>>>(pa);
+        ctx->launches++;
+        QCK(cudaGetLastError());
+    }
     prefix_bound_kernel<<<nq, 128, 0, ctx->stream>>>(pa.hist, r, ctx->b_sbound.as<int>());
     ctx->launches++;
     QCK(cudaGetLastError());
@@ -492,6 +495,8 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
     pa.starts = ctx->d_starts; pa.start_off = ctx->d_start_off; pa.start_size = ctx->d_start_size;
     pa.assign = d_assign; pa.tables = ctx->b_tables.as<float>(); pa.ma = ma; pa.r = r; pa.M = M;
     pa.qmax = ctx->b_qmax.as<float>();
+    const uint32_t* sel_lists = nullptr;
+    int sel_n = 0;
     if (!flat && ctx->max_start <= 128) {
         // inverted lists with short prefixes: one warp per probe
         pa.nsplit = 1; pa.lists = nullptr;
@@ -509,16 +514,13 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         else prefix_scan_kernel<32><<<pgrid, kSelThreads, 0, ctx->stream>>>(pa);
         ctx->launches++;
         QCK(cudaGetLastError());
-        if (nsplit > 1) {
-            prefix_select_kernel<<<nq, kSelThreads, 0, ctx->stream>>>(pa.lists, nsplit * r, r, ctx->b_qmax.as<float>());
-            ctx->launches++;
-            QCK(cudaGetLastError());
-        }
+        if (nsplit > 1) { sel_lists = pa.lists; sel_n = nsplit * r; }   // selected inside quantize_kernel
     }
     // 5. bounds + int8 tables
     quantize_kernel<<<nq, 256, 0, ctx->stream>>>(
         ctx->b_tables.as<float>(), ctx->b_tmin.as<float>(), ctx->b_qmax.as<float>(), ma, M,
-        ctx->b_qtables.as<int8_t>(), ctx->b_qmin.as<float>(), ctx->d_err);
+        ctx->b_qtables.as<int8_t>(), ctx->b_qmin.as<float>(), ctx->d_err, nullptr, nullptr, nullptr,
+        sel_lists, sel_n, r, ctx->b_qmax.as<float>());
     ctx->launches++;
     QCK(cudaGetLastError());
     return QADC_OK;
@@ -1487,6 +1489,7 @@ int qadc_set_option(qadc_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "flat_filter")) ctx->opt_flat_filter = value != 0;
     else if (!strcmp(key, "ivf_fused")) ctx->opt_ivf_fused = value;
     else if (!strcmp(key, "flat_ring")) ctx->opt_flat_ring = value != 0;
+    else if (!strcmp(key, "flat_seed")) ctx->opt_flat_seed = value != 0;
     else if (!strcmp(key, "ivf_sb_per_item")) {
         if (value < 1 || value > (1 << 20)) return fail(ctx, QADC_EINVAL, "ivf_sb_per_item out of range");
         ctx->ivf_sb_per_item = static_cast<int>(value);

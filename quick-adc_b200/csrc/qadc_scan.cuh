@@ -1213,19 +1213,33 @@ __global__ void __launch_bounds__(256) prefix_hist_kernel(const PrefixBoundArgs 
         for (int i = lane; i < M; i += 32) reinterpret_cast<uint4*>(tab[warp])[i] = __ldg(tsrc + i);
         __syncwarp();
         const uint8_t* codes = a.starts + a.start_off[p] * CS;
-        for (uint32_t v = v0 + vfirst; v < v1; v += vstep) {
-            uint32_t w[CS / 4];   // one 8- / 16-byte load per vector instead of CS byte loads
-            if constexpr (CS == 8) {
-                const uint2 c = *reinterpret_cast<const uint2*>(codes + static_cast<size_t>(v) * CS);
-                w[0] = c.x; w[1] = c.y;
-            } else {
-                const uint4 c = *reinterpret_cast<const uint4*>(codes + static_cast<size_t>(v) * CS);
-                w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w;
-            }
-            int sum = 0;
+        // four vectors per thread and turn, loads first (the prefix streams from L2 / HBM: one dependent load per turn was
+        // latency-bound).  Distances of 127 and more are not counted: bin 127 is never read, and nearly every prefix
+        // vector lands there (qmax is the r-th smallest prefix distance), i.e. a same-address atomic per vector.
+        for (uint64_t v = v0 + vfirst; v < v1; v += 4ull * vstep) {
+            uint32_t w[4][CS / 4];
 #pragma unroll
-            for (int j = 0; j < M; ++j) sum += tab[warp][j * 16 + ((w[j >> 3] >> (4 * (j & 7))) & 15u)];
-            atomicAdd(&hist[min(sum, 127)], 1u);
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t vv = v + static_cast<uint64_t>(u) * vstep;
+                if (vv < v1) {
+                    if constexpr (CS == 8) {
+                        const uint2 c = *reinterpret_cast<const uint2*>(codes + vv * CS);
+                        w[u][0] = c.x; w[u][1] = c.y;
+                    } else {
+                        const uint4 c = *reinterpret_cast<const uint4*>(codes + vv * CS);
+                        w[u][0] = c.x; w[u][1] = c.y; w[u][2] = c.z; w[u][3] = c.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (v + static_cast<uint64_t>(u) * vstep < v1) {
+                    int sum = 0;
+#pragma unroll
+                    for (int j = 0; j < M; ++j) sum += tab[warp][j * 16 + ((w[u][j >> 3] >> (4 * (j & 7))) & 15u)];
+                    if (sum < 127) atomicAdd(&hist[sum], 1u);
+                }
+            }
         }
     }
     __syncthreads();
@@ -1329,6 +1343,45 @@ __global__ void __launch_bounds__(kMergeThreads) merge_lists_kernel(const MergeA
         for (int l = tid; l < a.L; l += kMergeThreads) {
             const unsigned long long last = a.in_keys[(static_cast<size_t>(l) * a.nq + q) * a.r + a.r - 1];
             if (last != kEmptyKey) atomicMin(&bound_key, last + 1);   // strict filter below: keep keys <= last
+        }
+        __syncthreads();
+    }
+    if (a.init_bound && !a.shard_major && total > kMergeCap) {
+        // Pre-pass (int8-distance keys, more input than the buffer holds): the scan's shared bound is the r-th distance of
+        // ONE CTA's share of the vectors, so nearly every key of every list passes it (148 lists x 100 keys at the 1e9
+        // scan: the fast path below overflowed and the streaming rounds cost 73 us per step).  The r-th smallest distance
+        // of the union is exact and cheap: a 128-bin histogram of the keys' distances (one shared-memory atomic per
+        // distinct value and warp), its scan, and the bound drops to "r keys and the ties of the last distance".
+        __shared__ unsigned int dh[129];
+        for (int i = tid; i < 129; i += kMergeThreads) dh[i] = 0;
+        __syncthreads();
+        const unsigned long long bk0 = bound_key;
+        constexpr int U = 8;
+        for (int base = tid; base - tid < total; base += kMergeThreads * U) {   // warp-uniform trip count (match_any below)
+            uint64_t k[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kMergeThreads;
+                k[u] = i < total ? a.in_keys[(static_cast<size_t>(q) * a.L) * a.r + i] : kEmptyKey;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned d = k[u] < bk0 ? static_cast<unsigned>(k[u] >> 48) & 127u : 128u;
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if ((tid & 31) == __ffs(peers) - 1) atomicAdd(&dh[d], static_cast<unsigned>(__popc(peers)));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned cum = 0;
+            for (int d = 0; d < 128; ++d) {
+                cum += dh[d];
+                if (cum >= static_cast<unsigned>(a.r)) {
+                    const unsigned long long nb = static_cast<unsigned long long>(d + 1) << 48;
+                    if (nb < bound_key) bound_key = nb;
+                    break;
+                }
+            }
         }
         __syncthreads();
     }

@@ -96,19 +96,19 @@ __device__ __forceinline__ uint32_t block_radix_select(const uint32_t* vals, int
 // Streaming "r smallest float values" over a shared buffer of 2048 value slots (ping-pong halves of kSelCap),
 // compacted with block_radix_select: only the multiset of values matters (ties are interchangeable).
 struct BlockMinValues {
-    uint32_t* buf[2];       // kSelCap/2 ... each kSelCap uint32
-    int* count;             // entries in buf[cur]
+    uint32_t* cur;          // kSelCap uint32: the buffer being filled
+    uint32_t* other;        // kSelCap uint32: where a compaction writes (the two swap; no runtime-indexed pointer array,
+                            // which the compiler put on the stack)
+    int* count;             // entries in cur
     int* hist;              // 256
     int* state;             // 2
     unsigned int* bound;    // pass iff bits < *bound
-    int cur;
     __device__ __forceinline__ void init(int tid) {
         if (tid == 0) { *count = 0; *bound = 0xffffffffu; }
-        cur = 0;
         __syncthreads();
     }
     __device__ __forceinline__ void push(uint32_t bits) {
-        if (bits < *bound) buf[cur][atomicAdd(count, 1)] = bits;
+        if (bits < *bound) cur[atomicAdd(count, 1)] = bits;
     }
     // call after every round of <= kSelCap/2 pushes (all threads); force = last round
     __device__ __forceinline__ void maybe_compact(int r, int tid, bool force) {
@@ -117,20 +117,21 @@ struct BlockMinValues {
         __syncthreads();
         if ((c > kSelCap / 2 || force) && c >= r) {
             int n_less;
-            const uint32_t b = block_radix_select(buf[cur], c, r, hist, state, tid, n_less);
+            const uint32_t b = block_radix_select(cur, c, r, hist, state, tid, n_less);
             __syncthreads();
             if (tid == 0) *count = 0;
             __syncthreads();
-            uint32_t* dst = buf[cur ^ 1];
+            uint32_t* dst = other;
             for (int i = tid; i < c; i += kSelThreads) {
-                const uint32_t v = buf[cur][i];
+                const uint32_t v = cur[i];
                 if (v < b) dst[atomicAdd(count, 1)] = v;
             }
             __syncthreads();
             for (int i = n_less + tid; i < r; i += kSelThreads) dst[i] = b;   // the r-th value and its ties
             __syncthreads();
             if (tid == 0) { *count = r; *bound = b; }
-            cur ^= 1;
+            other = cur;
+            cur = dst;
             __syncthreads();
         }
     }
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixAr
     __shared__ int count, hist[256], state[2];
     __shared__ unsigned int bound;
     const int split = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
-    BlockMinValues top{{vbuf[0], vbuf[1]}, &count, hist, state, &bound, 0};
+    BlockMinValues top{vbuf[0], vbuf[1], &count, hist, state, &bound};
     top.init(tid);
     for (int ar = 0; ar < a.ma; ++ar) {
         const int p = a.assign[static_cast<size_t>(q) * a.ma + ar];
@@ -437,20 +438,32 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixAr
             tab[i] = a.tables[(static_cast<size_t>(q) * a.ma + ar) * M * 16 + i];
         __syncthreads();
         const uint8_t* codes = a.starts + a.start_off[p] * CS;
+        static_assert(kSelCap / 2 % kSelThreads == 0, "a round is a whole number of vectors per thread");
+        constexpr int VPT = kSelCap / 2 / kSelThreads;   // vectors per thread and round; loads first: the prefix streams from L2 / HBM
         for (uint32_t base = v0; base < v1; base += kSelCap / 2) {
-            for (uint32_t v = base + tid; v < min(base + kSelCap / 2, v1); v += kSelThreads) {
-                uint32_t w[CS / 4];
-                if constexpr (CS == 8) {
-                    const uint2 c = *reinterpret_cast<const uint2*>(codes + static_cast<size_t>(v) * CS);
-                    w[0] = c.x; w[1] = c.y;
-                } else {
-                    const uint4 c = *reinterpret_cast<const uint4*>(codes + static_cast<size_t>(v) * CS);
-                    w[0] = c.x; w[1] = c.y; w[2] = c.z; w[3] = c.w;
-                }
-                float s = 0.f;
+            const uint32_t vend = min(base + kSelCap / 2, v1);
+            uint32_t w[VPT][CS / 4];
 #pragma unroll
-                for (int j = 0; j < M; ++j) s = __fadd_rn(s, tab[j * 16 + ((w[j >> 3] >> (4 * (j & 7))) & 15u)]);
-                top.push(__float_as_uint(s));   // sums of non-negative entries: the bit patterns order like the values
+            for (int u = 0; u < VPT; ++u) {
+                const uint32_t v = base + tid + u * kSelThreads;
+                if (v < vend) {
+                    if constexpr (CS == 8) {
+                        const uint2 c = *reinterpret_cast<const uint2*>(codes + static_cast<size_t>(v) * CS);
+                        w[u][0] = c.x; w[u][1] = c.y;
+                    } else {
+                        const uint4 c = *reinterpret_cast<const uint4*>(codes + static_cast<size_t>(v) * CS);
+                        w[u][0] = c.x; w[u][1] = c.y; w[u][2] = c.z; w[u][3] = c.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < VPT; ++u) {
+                if (base + tid + u * kSelThreads < vend) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < M; ++j) s = __fadd_rn(s, tab[j * 16 + ((w[u][j >> 3] >> (4 * (j & 7))) & 15u)]);
+                    top.push(__float_as_uint(s));   // sums of non-negative entries: the bit patterns order like the values
+                }
             }
             top.maybe_compact(a.r, tid, false);
         }
@@ -459,7 +472,7 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixAr
     // r smallest values of this split (FLT_MAX-padded); a single split needs no merge: the r-th value is qmax
     // (FLT_MAX when the prefix is too short)
     const int c = count;
-    const uint32_t* res = top.buf[top.cur];
+    const uint32_t* res = top.cur;
     if (a.local_out) {
         float* dst = a.local_out + static_cast<size_t>(q) * (a.r + 1) + 1;
         for (int i = tid; i < a.r; i += kSelThreads) dst[i] = (i < c) ? __uint_as_float(res[i]) : 3.402823466e+38f;
@@ -470,16 +483,6 @@ __global__ void __launch_bounds__(kSelThreads) prefix_scan_kernel(const PrefixAr
         uint32_t* dst = a.lists + (static_cast<size_t>(q) * a.nsplit + split) * a.r;
         for (int i = tid; i < a.r; i += kSelThreads) dst[i] = (i < c) ? res[i] : 0x7f7fffffu;
     }
-}
-
-// The r-th smallest of the nsplit * r values the splits of one query left (grid = queries) -> qmax.
-__global__ void __launch_bounds__(kSelThreads) prefix_select_kernel(const uint32_t* __restrict__ lists, int n_per_query, int r,
-                                                                   float* __restrict__ qmax) {
-    __shared__ int hist[256], state[2];
-    const int q = blockIdx.x, tid = threadIdx.x;
-    int n_less;
-    const uint32_t b = block_radix_select(lists + static_cast<size_t>(q) * n_per_query, n_per_query, r, hist, state, tid, n_less);
-    if (tid == 0) qmax[q] = __uint_as_float(b);   // FLT_MAX (the padding) when fewer than r prefix vectors exist
 }
 
 // Short prefixes (inverted lists): one warp per probe, lanes over the few prefix vectors; the
@@ -740,7 +743,7 @@ __global__ void __launch_bounds__(256) ivf_prepare_kernel(const IvfPrepArgs a) {
         }
         if (lane == 0) poff[0] = 0;
     }
-    BlockMinValues top{{vb0, vb1}, &count, hist, state, &bound, 0};
+    BlockMinValues top{vb0, vb1, &count, hist, state, &bound};
     top.init(tid);   // (a block barrier: tables, red[], poff[] are visible from here on)
     const int total = poff[ma];
     auto locate = [&](int item, int& probe, uint32_t (&w)[CS / 4]) {   // probe of a flattened item and its code words
@@ -891,11 +894,23 @@ __global__ void __launch_bounds__(256) quantize_kernel(float* __restrict__ table
                                                        int8_t* __restrict__ qtables, float* __restrict__ qmin_out,
                                                        int* __restrict__ err, const float* __restrict__ qmin_in = nullptr,
                                                        const int32_t* __restrict__ assign = nullptr,
-                                                       const uint32_t* __restrict__ part_size = nullptr) {
+                                                       const uint32_t* __restrict__ part_size = nullptr,
+                                                       const uint32_t* __restrict__ sel_lists = nullptr, int sel_n = 0,
+                                                       int sel_r = 0, float* qmax_out = nullptr) {
     // qmin_in / assign / part_size ("owner computes"): the query's minimum comes from bounds_combine_kernel and only the
-    // tables of probes whose list lives on this device exist
+    // tables of probes whose list lives on this device exist.
+    // sel_lists (flat databases, split prefix scan): qmax is selected here — the sel_r-th smallest of the sel_n values
+    // the splits left (a launch of its own before) — and stored to qmax_out.
     __shared__ float red[8];
+    __shared__ int sel_hist[256], sel_state[2];
     const int q = blockIdx.x, tid = threadIdx.x;
+    float qmax_sel = 0.f;
+    if (sel_lists) {
+        int n_less;
+        qmax_sel = __uint_as_float(block_radix_select(sel_lists + static_cast<size_t>(q) * sel_n, sel_n, sel_r, sel_hist,
+                                                      sel_state, tid, n_less));
+        if (tid == 0) qmax_out[q] = qmax_sel;   // FLT_MAX (the padding) when fewer than sel_r prefix vectors exist
+    }
     float mn = qmin_in ? qmin_in[q] : 3.402823466e+38f;
     if (!qmin_in)
         for (int a = tid; a < ma; a += 256) mn = fminf(mn, tmin[static_cast<size_t>(q) * ma + a]);
@@ -906,7 +921,7 @@ __global__ void __launch_bounds__(256) quantize_kernel(float* __restrict__ table
     for (int w = 1; w < 8; ++w) qmin = fminf(qmin, red[w]);
     const bool clamp = qmin < 0.f;
     if (clamp) qmin = 0.f;
-    const float qmax = qmax_in[q];
+    const float qmax = sel_lists ? qmax_sel : qmax_in[q];
     if (tid == 0) {
         qmin_out[q] = qmin;
         if (qmax > 1e30f) atomicExch(err, 1);

@@ -176,6 +176,30 @@ def test_flat_scan_degenerate_ties(qadc, oracle):
     ix.close()
 
 
+@pytest.mark.parametrize("n_distinct", [1, 2, 40])
+def test_flat_merge_of_many_full_lists(qadc, oracle, n_distinct):
+    """More per-CTA lists than the merge buffer holds (31 chunks x r = 100 keys > 2048 slots), every list full: the merge
+    first narrows its bound to the r-th distance of the union (128-bin histogram of the keys' distances).  One distinct
+    distance = every key ties with the r-th (the narrowed bound keeps them all and the streaming rounds take over), two =
+    the answer straddles the two classes, 40 = a few dozen classes."""
+    rng = np.random.default_rng(500 + n_distinct)
+    n, m, r, nq = 123457, 16, 100, 4
+    codes = np.zeros((n, m // 2), np.uint8)
+    codes[:, 0] = rng.integers(0, min(n_distinct, 16), n)                    # low nibble of byte 0 = sub-quantiser 0
+    codes[:, 1] = rng.integers(0, max(1, n_distinct // 16), n)               # low nibble of byte 1 = sub-quantiser 2
+    ix = flat_index(qadc, 128, m, synth.make_pq(rng, 128, m), codes, 1.0)
+    ix.set_option("flat_qb", 1)
+    ix.set_option("flat_chunks", 64)
+    qt = np.zeros((nq, 1, m, 16), np.int8)
+    qt[:, 0, 0, :] = rng.integers(0, 60, (nq, 16))
+    qt[:, 0, 2, :] = rng.integers(0, 60, (nq, 16))
+    ids, d, cnt = ix.scan_with_tables(np.zeros((nq, 1), np.int32), qt, r)
+    for q in range(nq):
+        e_ids, e_d, e_cnt, _ = oracle.scan_with_tables(codes, None, np.array([0, n], np.int64), np.zeros(1, np.int32), qt[q], r)
+        assert cnt[q] == e_cnt and np.array_equal(d[q], e_d) and np.array_equal(ids[q], e_ids)
+    ix.close()
+
+
 @pytest.mark.parametrize("name", IVF + OPQ)
 def test_ivf_scan_with_reference_tables(qadc, oracle, name):
     """Injected assign + the reference's own int8 tables: canonical result bit-exact vs the
