@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "qadc_capi.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("qadc_capi.cu", "qadc_device.cuh", "qadc_scan.cuh", "qadc_tables.cuh", "qadc_adc.cuh", "qadc_multi.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("qadc_capi.cu", "qadc_device.cuh", "qadc_scan.cuh", "qadc_tables.cuh", "qadc_adc.cuh", "qadc_multi.cuh", "qadc_flatprep.cuh")]
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "qadc_b200.h"))
 OUT = os.path.join(HERE, "libqadc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -11,6 +11,7 @@
 #include "qadc_scan.cuh"
 #include "qadc_tables.cuh"
 #include "qadc_adc.cuh"
+#include "qadc_flatprep.cuh"
 
 using namespace qadc;
 
@@ -62,6 +63,7 @@ struct qadc_ctx {
     uint32_t *d_size = nullptr, *d_pos_base = nullptr, *d_start_size = nullptr;
     uint32_t* d_owned = nullptr;   // [parts] 1 = this shard answers for the partition ("owner computes"); default: size > 0
     uint8_t* d_starts = nullptr;
+    uint8_t* d_starts_native = nullptr;   // flat database, long prefix: the prefix as nibble-plane superblocks (qadc_flatprep.cuh)
     uint32_t max_start = 0;
     // plain-ADC database (db_query path): row-major codes, independent of the Quick ADC layout above
     int adc_parts = 0;
@@ -71,13 +73,13 @@ struct qadc_ctx {
     DevBuf b_adc_dists;
     // scratch
     DevBuf staging, b_queries, b_assign, b_tables, b_tmin, b_qmax, b_qmin, b_qtables, b_lists, b_plists, b_ids,
-        b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound, b_cdist, b_qmin_raw;
+        b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound, b_cdist, b_qmin_raw, b_prov, b_fprep, b_cand, b_ghist;
     int local_nq = 0, local_ma = 0, local_r = 0;   // batch whose tables qadc_tables_local_device left in the scratch
     bool local_mode = false;                        // scan_device runs for qadc_search_bounded_device: only owned probes have tables
     int* d_err = nullptr;
     int* h_err = nullptr;   // pinned
     // options / accounting
-    long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1, opt_ivf_fused = 1, opt_flat_ring = 1, opt_flat_seed = 1;
+    long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1, opt_ivf_fused = 1, opt_flat_ring = 1, opt_flat_seed = 1, opt_flat_prep = 1, opt_seed_minus = 0, opt_flat_share = 1;
     bool sbound_seeded = false;   // the fused inverted-list table kernel already wrote the shared bounds of this batch
     int ivf_sb_per_item = 8;   // superblocks per work item of the IVF scan (option "ivf_sb_per_item")
     int launches = 0;
@@ -127,7 +129,7 @@ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 void free_db(qadc_ctx* c) {
     cudaFree(c->d_codes); cudaFree(c->d_labels); cudaFree(c->d_sb_off); cudaFree(c->d_label_off);
     cudaFree(c->d_start_off); cudaFree(c->d_owned); cudaFree(c->d_size); cudaFree(c->d_pos_base); cudaFree(c->d_start_size);
-    cudaFree(c->d_starts);
+    cudaFree(c->d_starts); cudaFree(c->d_starts_native); c->d_starts_native = nullptr;
     for (auto p : c->h_explicit_prefix)
         if (p && !c->d_prefix_block) cudaFree(p);
     cudaFree(c->d_prefix_block); c->d_prefix_block = nullptr;
@@ -160,6 +162,14 @@ __global__ void extract_prefix_kernel(const uint8_t* __restrict__ native, const 
         }
     }
 }
+
+#ifdef QADC_EXPERIMENT
+// tools/exp_seed.py (build with QADC_NVCC_EXTRA=-DQADC_EXPERIMENT): how much would a tighter shared-bound seed be worth
+__global__ void seed_minus_kernel(int* sbound, int nq, int k) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) sbound[q] = max(0, sbound[q] - k);
+}
+#endif
 
 // ---- flat scan dispatch ---------------------------------------------------------------------
 template <int M, int QB, int NW, int NS>
@@ -277,16 +287,41 @@ int plan_flat(qadc_ctx* ctx, int nq, int r, FlatPlan& pl) {
     return QADC_OK;
 }
 
+// grid.x of the int8 passes over a flat prefix: about eight CTAs (64 warps) per SM over all queries, so that a warp has
+// only a few superblocks to fetch one after the other (at two CTAs per SM the pass was latency-bound: 22 us for the
+// 500 000-vector prefix of the 1e9 bench and 16 queries)
+unsigned flat_prep_splits(const qadc_ctx* ctx, uint32_t n_sb, int nq) {
+    const unsigned want = static_cast<unsigned>((8 * ctx->sm_count + nq - 1) / nq);
+    return std::max(1u, std::min(want, (n_sb + 7) / 8));
+}
+
 // Seeds the per-query shared bound from the keep-prefixes (prefix_hist + prefix_bound kernels).
 int seed_shared_bound(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables, int nq, int ma, int r) {
-    ENSURE(ctx->b_hist, static_cast<size_t>(nq) * 128 * 4);
+    ENSURE(ctx->b_hist, static_cast<size_t>(nq) * 129 * 4);   // 128 bins per query + one ticket per query
     ENSURE(ctx->b_sbound, static_cast<size_t>(nq) * 4);
-    QCK(cudaMemsetAsync(ctx->b_hist.p, 0, static_cast<size_t>(nq) * 128 * 4, ctx->stream));
+    QCK(cudaMemsetAsync(ctx->b_hist.p, 0, static_cast<size_t>(nq) * 129 * 4, ctx->stream));
+    unsigned int* hist = ctx->b_hist.as<unsigned int>();
+    if (ctx->K == 0 && ctx->d_starts_native && ctx->opt_flat_prep && ctx->opt_flat_seed) {
+        // long flat prefix: the same histogram from the nibble-plane copy of the prefix with the PRMT core, its scan by the
+        // last CTA of each query (qadc_flatprep.cuh): one launch
+        const uint32_t n_prefix = ctx->h_start_size[0], n_sb = (n_prefix + kSbVec - 1) / kSbVec;
+        dim3 pgrid(flat_prep_splits(ctx, n_sb, nq), nq);
+        unsigned int* done = hist + static_cast<size_t>(nq) * 128;
+        if (ctx->m == 16)
+            flat_prefix_pass_kernel<16, 0><<<pgrid, 256, 0, ctx->stream>>>(ctx->d_starts_native, n_prefix, d_qtables, hist, done,
+                                                                          ctx->b_sbound.as<int>(), 126, r, 0, nullptr, nullptr, make_pipek());
+        else
+            flat_prefix_pass_kernel<32, 0><<<pgrid, 256, 0, ctx->stream>>>(ctx->d_starts_native, n_prefix, d_qtables, hist, done,
+                                                                          ctx->b_sbound.as<int>(), 126, r, 0, nullptr, nullptr, make_pipek());
+        ctx->launches++;
+        QCK(cudaGetLastError());
+        return QADC_OK;
+    }
     PrefixBoundArgs pa;
     pa.starts = ctx->d_starts; pa.start_off = ctx->d_start_off; pa.start_size = ctx->d_start_size;
     pa.assign = d_assign; pa.qtabs = d_qtables; pa.ma = ma;
     pa.nsplit = (ctx->K == 0) ? static_cast<int>(std::min<uint32_t>(64, std::max<uint32_t>(1, ctx->max_start / 8192))) : 1;
-    pa.hist = ctx->b_hist.as<unsigned int>();
+    pa.hist = hist;
     pa.owned_size = ctx->local_mode ? ctx->d_owned : nullptr;
     dim3 grid(pa.nsplit, nq);
     // flat_seed = 0 (flat databases): no histogram pass, the bound starts at 126 and the scan's own candidates tighten it
@@ -320,7 +355,12 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
     if (ctx->sbound_seeded) ctx->sbound_seeded = false;   // seeded by ivf_prepare_kernel for exactly this batch
     else rc = seed_shared_bound(ctx, d_assign, d_qtables, nq, ma, r);
     if (rc) return rc;
-    if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0[ctx->scan_seq % qadc_ctx::kScanRing], ctx->stream));
+#ifdef QADC_EXPERIMENT
+    if (ctx->opt_seed_minus) {
+        seed_minus_kernel<<<(nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->b_sbound.as<int>(), nq, static_cast<int>(ctx->opt_seed_minus));
+        QCK(cudaGetLastError());
+    }
+#endif
     if (flat) {
         FlatPlan pl;
         rc = plan_flat(ctx, nq, r, pl);
@@ -335,6 +375,14 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         a.pos_base = ctx->h_pos_base[0]; a.sb_per_chunk = pl.sb_per_chunk; a.qtabs = d_qtables; a.nq = nq;
         a.r = r; a.cap = pl.cap; a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
         a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk; a.use_filter = static_cast<int>(ctx->opt_flat_filter);
+        a.ghist = nullptr;
+        if (ctx->opt_flat_share && pl.chunks > 1) {
+            // the chunks of a query pool their candidates in a global histogram (hist_publish)
+            ENSURE(ctx->b_ghist, static_cast<size_t>(nq) * 128 * 4);
+            QCK(cudaMemsetAsync(ctx->b_ghist.p, 0, static_cast<size_t>(nq) * 128 * 4, ctx->stream));
+            a.ghist = ctx->b_ghist.as<int>();
+        }
+        if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0[ctx->scan_seq % qadc_ctx::kScanRing], ctx->stream));
         rc = pl.v->launch(ctx, a, pl.chunks);
         if (rc) return rc == QADC_ENOMEM ? fail(ctx, rc, "scan kernel shared memory exceeds 227 KB") : rc;
     } else {
@@ -353,6 +401,7 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         a.lists = ctx->b_lists.as<uint64_t>(); a.n_lists = n_lists;
         a.shared_bound = ctx->b_sbound.as<int>(); a.k = pk;
         dim3 grid(chunks, nq);
+        if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0[ctx->scan_seq % qadc_ctx::kScanRing], ctx->stream));
         if (M == 16) {
             QCK(cudaFuncSetAttribute(scan_ivf_kernel<16, kNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
@@ -490,6 +539,45 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         QCK(cudaGetLastError());
     }
     if (record_events) QCK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    // 4'. flat database with a long prefix: int8 lower bounds exclude all but a few thousand prefix vectors per query
+    //     from the float scan (qadc_flatprep.cuh); qmax and the int8 tables are bit-identical to the plain path below
+    if (flat && ctx->d_starts_native && ctx->opt_flat_prep && r <= kPrefMaxR) {
+        const uint32_t n_prefix = ctx->h_start_size[0];
+        const size_t te = static_cast<size_t>(M) * 16;
+        const int nsplit = static_cast<int>(std::min(n_prefix, kPrefSampleMax) / kPrefSplit);
+        ENSURE(ctx->b_prov, static_cast<size_t>(nq) * te);
+        ENSURE(ctx->b_fprep, static_cast<size_t>(nq) * 4);
+        ENSURE(ctx->b_cand, static_cast<size_t>(nq) * kPrefCandCap * 4);
+        ENSURE(ctx->b_plists, static_cast<size_t>(nq) * nsplit * r * 4);
+        ENSURE(ctx->b_sbound, static_cast<size_t>(nq) * 4);
+        QCK(cudaMemsetAsync(ctx->b_fprep.p, 0, static_cast<size_t>(nq) * 4, ctx->stream));
+        FlatPrepArgs fa;
+        fa.starts = ctx->d_starts; fa.native = ctx->d_starts_native; fa.n_prefix = n_prefix;
+        fa.tables = ctx->b_tables.as<float>(); fa.r = r; fa.nsplit = nsplit; fa.sample_lists = ctx->b_plists.as<uint32_t>();
+        fa.prov_qt = ctx->b_prov.as<int8_t>(); fa.cand_count = ctx->b_fprep.as<unsigned int>();
+        fa.cand = ctx->b_cand.as<uint32_t>(); fa.seed_out = ctx->b_sbound.as<int>();
+        const uint32_t n_sb = (n_prefix + kSbVec - 1) / kSbVec;
+        dim3 sgrid(nsplit, nq), pgrid(flat_prep_splits(ctx, n_sb, nq), nq);
+        const PipeK pk = make_pipek();
+        float* tabs = ctx->b_tables.as<float>();
+        if (M == 16) {
+            flat_prefix_sample_kernel<16><<<sgrid, kSelThreads, 0, ctx->stream>>>(fa);
+            flat_prefix_bound_kernel<16><<<nq, kSelThreads, 0, ctx->stream>>>(fa);
+            flat_prefix_pass_kernel<16, 1><<<pgrid, 256, 0, ctx->stream>>>(fa.native, n_prefix, fa.prov_qt, nullptr, nullptr, nullptr, 127, r, 0, fa.cand_count, fa.cand, pk);
+            flat_bounds_final_kernel<16><<<nq, kSelThreads, 0, ctx->stream>>>(fa, tabs, ctx->b_tmin.as<float>(), ctx->b_qtables.as<int8_t>(),
+                                                                             ctx->b_qmin.as<float>(), ctx->b_qmax.as<float>(), ctx->d_err);
+        } else {
+            flat_prefix_sample_kernel<32><<<sgrid, kSelThreads, 0, ctx->stream>>>(fa);
+            flat_prefix_bound_kernel<32><<<nq, kSelThreads, 0, ctx->stream>>>(fa);
+            flat_prefix_pass_kernel<32, 1><<<pgrid, 256, 0, ctx->stream>>>(fa.native, n_prefix, fa.prov_qt, nullptr, nullptr, nullptr, 127, r, 0, fa.cand_count, fa.cand, pk);
+            flat_bounds_final_kernel<32><<<nq, kSelThreads, 0, ctx->stream>>>(fa, tabs, ctx->b_tmin.as<float>(), ctx->b_qtables.as<int8_t>(),
+                                                                             ctx->b_qmin.as<float>(), ctx->b_qmax.as<float>(), ctx->d_err);
+        }
+        ctx->launches += 4;
+        QCK(cudaGetLastError());
+        ctx->sbound_seeded = ctx->opt_flat_seed != 0;   // the final kernel left the scan's shared-bound seed of this batch
+        return QADC_OK;
+    }
     // 4. keep-prefix float scan -> qmax
     PrefixArgs pa;
     pa.starts = ctx->d_starts; pa.start_off = ctx->d_start_off; pa.start_size = ctx->d_start_size;
@@ -945,6 +1033,17 @@ int qadc_finalize(qadc_ctx* ctx, float keep) {
             if (ctx->h_explicit_prefix[p])
                 QCK(cudaMemcpyAsync(ctx->d_starts + ctx->h_start_off[p] * CS, ctx->h_explicit_prefix[p],
                                     static_cast<size_t>(ctx->h_explicit_count[p]) * CS, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    cudaFree(ctx->d_starts_native); ctx->d_starts_native = nullptr;
+    if (ctx->K == 0 && ctx->h_start_size[0] >= kPrefMinNative) {
+        // flat database with a long keep-prefix: a nibble-plane copy of the prefix for the int8 passes of qadc_flatprep.cuh
+        const uint32_t n = ctx->h_start_size[0];
+        const size_t n_sb = (static_cast<size_t>(n) + kSbVec - 1) / kSbVec;
+        QCK(cudaMalloc(&ctx->d_starts_native, n_sb * sb_bytes(M)));
+        const unsigned blocks = static_cast<unsigned>((n_sb * 32 + 255) / 256);
+        if (M == 16) transpose_codes_kernel<16><<<blocks, 256, 0, ctx->stream>>>(ctx->d_starts, n, ctx->d_starts_native, 0);
+        else transpose_codes_kernel<32><<<blocks, 256, 0, ctx->stream>>>(ctx->d_starts, n, ctx->d_starts_native, 0);
+        QCK(cudaGetLastError());
     }
     QCK(cudaStreamSynchronize(ctx->stream));
     ctx->finalized = true;
@@ -1490,6 +1589,11 @@ int qadc_set_option(qadc_ctx* ctx, const char* key, long value) {
     else if (!strcmp(key, "ivf_fused")) ctx->opt_ivf_fused = value;
     else if (!strcmp(key, "flat_ring")) ctx->opt_flat_ring = value != 0;
     else if (!strcmp(key, "flat_seed")) ctx->opt_flat_seed = value != 0;
+    else if (!strcmp(key, "flat_prep")) ctx->opt_flat_prep = value != 0;
+    else if (!strcmp(key, "flat_share")) ctx->opt_flat_share = value != 0;
+#ifdef QADC_EXPERIMENT
+    else if (!strcmp(key, "seed_minus")) ctx->opt_seed_minus = value;   // tools/exp_seed.py only: a seed below the true bound loses results
+#endif
     else if (!strcmp(key, "ivf_sb_per_item")) {
         if (value < 1 || value > (1 << 20)) return fail(ctx, QADC_EINVAL, "ivf_sb_per_item out of range");
         ctx->ivf_sb_per_item = static_cast<int>(value);

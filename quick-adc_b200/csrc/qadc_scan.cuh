@@ -185,8 +185,10 @@ __device__ __forceinline__ void load_shared_bound_now(int& v, const int* p) {
 // After a warp pushed `added` candidates: count them CTA-wide and, when the count passes the next
 // threshold, re-derive the query's shared bound from the CTA histogram.  Whole warp calls it;
 // returns the new bound (or 127 when nothing changed).
+// (global_too: the CTA shares a query with other CTAs — the threshold then starts at r / 4 instead of r and passing it
+// returns -1: the caller publishes to the query's global histogram, hist_publish, which yields the bound.)
 __device__ __forceinline__ int hist_update(int* hist, int* hist_total, int* hist_next, int added, int r, int lane,
-                                           int* shared_bound) {
+                                           int* shared_bound, bool global_too = false) {
     int total = 0;
     if (lane == 0) {
         total = atomicAdd(hist_total, added) + added;
@@ -196,12 +198,66 @@ __device__ __forceinline__ int hist_update(int* hist, int* hist_total, int* hist
     }
     total = __shfl_sync(0xffffffffu, total, 0);
     if (total < 0) return 127;
+    if (global_too) {
+        if (lane == 0) atomicMax(hist_next, total + max(r / 4, 8));
+        return -1;
+    }
     const int hb = hist_bound(hist, r, lane);
     if (lane == 0) {
         atomicMax(hist_next, total + max(r / 4, 8));
         if (hb < 127) atomicMin(shared_bound, hb);
     }
     return hb;
+}
+
+// The same across the CTAs of a query (flat scans cut a database into up to 148 x 16 chunks per query): the CTA histogram
+// only knows the CTA's share of the vectors, so its r-th distance is that of 1/chunks of the database — on rank 0 of an
+// 8-way sharded 1e9 scan the bound stayed 10-20 above the final one for most of a CTA's life, the pre-filter passed too
+// many superblocks to the exact core and the scan took 2.78 ms where a perfect seed gave 2.565 (tools/exp_seed.py).
+// Whenever a CTA re-derives its own bound it therefore also PUBLISHES the candidates it has counted since the last time
+// to the query's histogram in global memory (ghist, zeroed per launch; non-negative deltas under a CTA-wide lock, so the
+// global counts never exceed the number of scanned vectors at each distance) and takes the bound of the union: the
+// smallest distance whose global cumulative count reaches r.  A whole warp calls it; returns that bound or 127.
+__device__ __forceinline__ int hist_publish(const int* hist, int* hpub, int* publock, int* ghist, int r, int lane,
+                                            int* shared_bound) {
+    int got = 0;
+    if (lane == 0) got = atomicCAS(publock, 0, 1) == 0;
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (!got) return 127;   // another warp of the CTA is publishing
+    __syncwarp();
+    const int4 cur = *reinterpret_cast<const int4*>(hist + lane * 4);   // counts only grow
+    const int4 pub = *reinterpret_cast<const int4*>(hpub + lane * 4);
+    int* g = ghist + lane * 4;
+    if (cur.x > pub.x) atomicAdd(g, cur.x - pub.x);
+    if (cur.y > pub.y) atomicAdd(g + 1, cur.y - pub.y);
+    if (cur.z > pub.z) atomicAdd(g + 2, cur.z - pub.z);
+    if (cur.w > pub.w) atomicAdd(g + 3, cur.w - pub.w);
+    *reinterpret_cast<int4*>(hpub + lane * 4) = cur;
+    const int4 c = __ldcg(reinterpret_cast<const int4*>(g));   // the other CTAs' counts (own additions may be missing: fine)
+    const int mine = c.x + c.y + c.z + c.w;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const unsigned reached = __ballot_sync(0xffffffffu, incl >= r);
+    int b = 127;
+    if (reached) {
+        const int src = __ffs(reached) - 1;
+        if (lane == src) {
+            const int c0 = incl - mine + c.x, c1 = c0 + c.y, c2 = c1 + c.z;
+            b = lane * 4 + (c0 >= r ? 0 : (c1 >= r ? 1 : (c2 >= r ? 2 : 3)));
+            if (b < 127) atomicMin(shared_bound, b);
+        }
+        b = __shfl_sync(0xffffffffu, b, src);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();   // hpub is written before the lock opens
+        atomicExch(publock, 0);
+    }
+    return b;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -223,6 +279,7 @@ struct FlatScanArgs {
     int* shared_bound;      // [nq]
     PipeK k;                // {1, -1}
     int use_filter;         // register-table variant: clamped byte-lane pre-filter before the exact core
+    int* ghist;             // [nq][128] the queries' global candidate histograms (zeroed per launch) or null
 };
 
 template <int M, int QB, int NW, int NS>
@@ -578,8 +635,8 @@ struct WarpRingCfg {
     static constexpr int kSlotBytes = NPS * kSbBytes;   // a ring slot holds NPS consecutive superblocks (one TMA copy, one barrier)
     static constexpr int kRingBytes = NW * NSW * kSlotBytes;
     static constexpr int kThreads = NW * 32;
-    // rings | table | per-warp filter tables | barriers | histogram + counters | list counts/bounds, rounded to 16 bytes
-    static constexpr int kFixedBytes = ((kRingBytes + M * 16 + NW * M * 16 + NW * NSW * 8 + (128 + 2) * 4 + NW * 8) + 15) / 16 * 16;
+    // rings | table | per-warp filter tables | barriers | histogram + published copy + counters | list counts/bounds, rounded to 16 bytes
+    static constexpr int kFixedBytes = ((kRingBytes + M * 16 + NW * M * 16 + NW * NSW * 8 + (2 * 128 + 4) * 4 + NW * 8) + 15) / 16 * 16;
     static size_t smem_bytes(int cap) { return static_cast<size_t>(kFixedBytes) + static_cast<size_t>(NW) * cap * 8; }
 };
 
@@ -593,9 +650,11 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
     uint4* ftab = qtab + M;                                                                // [NW][M]
     uint64_t* full = reinterpret_cast<uint64_t*>(ftab + NW * M);                           // [NW][NSW]
     int* hist = reinterpret_cast<int*>(full + NW * NSW);                                   // [128]
-    int* hist_total = hist + 128;
+    int* hpub = hist + 128;                                                                // [128] counts already in a.ghist
+    int* hist_total = hpub + 128;
     int* hist_next = hist_total + 1;
-    int* cnt = hist_next + 1;                                                              // [NW]
+    int* publock = hist_next + 1;
+    int* cnt = publock + 2;                                                                // [NW]
     int* bnd = cnt + NW;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + Cfg::kFixedBytes);                // [NW][cap]
 
@@ -612,8 +671,9 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
     for (int i = threadIdx.x; i < M; i += blockDim.x) qtab[i] = reinterpret_cast<const uint4*>(a.qtabs)[static_cast<size_t>(q) * M + i];
     for (int i = threadIdx.x; i < NW * a.cap; i += blockDim.x) lists[i] = kEmptyKey;
     for (int i = threadIdx.x; i < NW; i += blockDim.x) { cnt[i] = 0; bnd[i] = 127; }
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) hist[i] = 0;
-    if (threadIdx.x == 0) { *hist_total = 0; *hist_next = a.r; }
+    int* ghist = (a.ghist && gridDim.x > 1) ? a.ghist + static_cast<size_t>(q) * 128 : nullptr;   // one chunk: the CTA sees everything
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;   // hist + hpub
+    if (threadIdx.x == 0) { *hist_total = 0; *hist_next = ghist ? max(a.r / 4, 8) : a.r; *publock = 0; }
     __syncthreads();
 
     WarpList wl{lists + static_cast<size_t>(warp) * a.cap, cnt + warp, bnd + warp};
@@ -699,7 +759,8 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
                     if (mine && my_turn) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl, hist);
                     __syncwarp();
                     const int now = *wl.count;
-                    const int hb = hist_update(hist, hist_total, hist_next, now - before, a.r, lane, sbound);
+                    int hb = hist_update(hist, hist_total, hist_next, now - before, a.r, lane, sbound, ghist != nullptr);
+                    if (hb == -1) hb = hist_publish(hist, hpub, publock, ghist, a.r, lane, sbound);   // threshold passed: share
                     if (hb < gb) gb = hb;
                     if (now >= compact_at) {
                         wl.compact(a.cap, a.r, lane, sbound);
@@ -816,8 +877,8 @@ struct WarpRingBatchCfg {
     static constexpr int kQuads = M / 4, kSbBytes = M * 128;
     static constexpr int kRingBytes = NW * NSW * kSbBytes;
     static constexpr int kThreads = NW * 32;
-    // rings | tables | barriers | histograms + counters | list counts/bounds, rounded to 16 bytes
-    static constexpr int kFixedBytes = ((kRingBytes + QB * M * 16 + NW * NSW * 8 + QB * (128 + 2) * 4 + NW * QB * 8) + 15) / 16 * 16;
+    // rings | tables | barriers | histograms + published copies + counters | list counts/bounds, rounded to 16 bytes
+    static constexpr int kFixedBytes = ((kRingBytes + QB * M * 16 + NW * NSW * 8 + QB * (2 * 128 + 4) * 4 + NW * QB * 8) + 15) / 16 * 16;
     static size_t smem_bytes(int cap) { return static_cast<size_t>(kFixedBytes) + static_cast<size_t>(NW) * QB * cap * 8; }
 };
 
@@ -829,9 +890,11 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wrq_kernel(const FlatSca
     uint4* qtab = reinterpret_cast<uint4*>(rings + Cfg::kRingBytes);                       // [QB][M]
     uint64_t* full = reinterpret_cast<uint64_t*>(qtab + QB * M);                           // [NW][NSW]
     int* hist = reinterpret_cast<int*>(full + NW * NSW);                                   // [QB][128]
-    int* hist_total = hist + QB * 128;                                                     // [QB]
+    int* hpub = hist + QB * 128;                                                           // [QB][128] counts already in a.ghist
+    int* hist_total = hpub + QB * 128;                                                     // [QB]
     int* hist_next = hist_total + QB;                                                      // [QB]
-    int* cnt = hist_next + QB;                                                             // [NW][QB]
+    int* publock = hist_next + QB;                                                         // [QB] (+ QB pad)
+    int* cnt = publock + 2 * QB;                                                           // [NW][QB]
     int* bnd = cnt + NW * QB;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + Cfg::kFixedBytes);                // [NW][QB][cap]
 
@@ -853,8 +916,9 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wrq_kernel(const FlatSca
     }
     for (int i = threadIdx.x; i < NW * QB * a.cap; i += blockDim.x) lists[i] = kEmptyKey;
     for (int i = threadIdx.x; i < NW * QB; i += blockDim.x) { cnt[i] = 0; bnd[i] = 127; }
-    for (int i = threadIdx.x; i < QB * 128; i += blockDim.x) hist[i] = 0;
-    for (int i = threadIdx.x; i < QB; i += blockDim.x) { hist_total[i] = 0; hist_next[i] = a.r; }
+    int* const ghist0 = (a.ghist && gridDim.x > 1) ? a.ghist + static_cast<size_t>(qbase) * 128 : nullptr;   // one chunk: nothing to share
+    for (int i = threadIdx.x; i < 2 * QB * 128; i += blockDim.x) hist[i] = 0;   // hist + hpub
+    for (int i = threadIdx.x; i < QB; i += blockDim.x) { hist_total[i] = 0; hist_next[i] = ghist0 ? max(a.r / 4, 8) : a.r; publock[i] = 0; }
     __syncthreads();
 
     // (warp, query) candidate lists; the rare path takes the query as a RUNTIME index so that it exists once in the
@@ -894,8 +958,10 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wrq_kernel(const FlatSca
             if (mine && my_turn) emit_candidates(g, bound, sb * kSbVec + lane * 8, a.size, a.pos_base, 0, wl, hist + qi * 128);
             __syncwarp();
             const int now = *wl.count;
-            const int hb = hist_update(hist + qi * 128, hist_total + qi, hist_next + qi, now - before, a.r, lane,
-                                       a.shared_bound + qbase + qi);
+            int hb = hist_update(hist + qi * 128, hist_total + qi, hist_next + qi, now - before, a.r, lane,
+                                 a.shared_bound + qbase + qi, ghist0 != nullptr);
+            if (hb == -1)   // threshold passed: pool the candidates of the query's chunks (hist_publish)
+                hb = hist_publish(hist + qi * 128, hpub + qi * 128, publock + qi, ghist0 + qi * 128, a.r, lane, a.shared_bound + qbase + qi);
             if (hb < hb_out) hb_out = hb;
             if (now >= compact_at) {
                 wl.compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);

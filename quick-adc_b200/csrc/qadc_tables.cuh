@@ -889,28 +889,12 @@ __global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ v
 // qmin = min over all ma tables (negatives clamped to 0, also in `tables`), qmax from the
 // prefix scan; q(v) = 127 if v >= qmax else (int8) trunc((v - qmin) / delta),
 // delta = (qmax - qmin) / 127.  err[0] is set when qmax > 1e30 (db_query_4.cpp:271-274).
-__global__ void __launch_bounds__(256) quantize_kernel(float* __restrict__ tables, const float* __restrict__ tmin,
-                                                       const float* __restrict__ qmax_in, int ma, int M,
-                                                       int8_t* __restrict__ qtables, float* __restrict__ qmin_out,
-                                                       int* __restrict__ err, const float* __restrict__ qmin_in = nullptr,
-                                                       const int32_t* __restrict__ assign = nullptr,
-                                                       const uint32_t* __restrict__ part_size = nullptr,
-                                                       const uint32_t* __restrict__ sel_lists = nullptr, int sel_n = 0,
-                                                       int sel_r = 0, float* qmax_out = nullptr) {
-    // qmin_in / assign / part_size ("owner computes"): the query's minimum comes from bounds_combine_kernel and only the
-    // tables of probes whose list lives on this device exist.
-    // sel_lists (flat databases, split prefix scan): qmax is selected here — the sel_r-th smallest of the sel_n values
-    // the splits left (a launch of its own before) — and stored to qmax_out.
-    __shared__ float red[8];
-    __shared__ int sel_hist[256], sel_state[2];
-    const int q = blockIdx.x, tid = threadIdx.x;
-    float qmax_sel = 0.f;
-    if (sel_lists) {
-        int n_less;
-        qmax_sel = __uint_as_float(block_radix_select(sel_lists + static_cast<size_t>(q) * sel_n, sel_n, sel_r, sel_hist,
-                                                      sel_state, tid, n_less));
-        if (tid == 0) qmax_out[q] = qmax_sel;   // FLT_MAX (the padding) when fewer than sel_r prefix vectors exist
-    }
+// One query's share (all 256 threads of its CTA call it): `red` = 8 floats of shared memory.
+__device__ __forceinline__ void quantize_query(float* __restrict__ tables, const float* __restrict__ tmin, const float qmax,
+                                               int ma, int M, int8_t* __restrict__ qtables, float* __restrict__ qmin_out,
+                                               int* __restrict__ err, const float* __restrict__ qmin_in,
+                                               const int32_t* __restrict__ assign, const uint32_t* __restrict__ part_size,
+                                               const int q, const int tid, float* red) {
     float mn = qmin_in ? qmin_in[q] : 3.402823466e+38f;
     if (!qmin_in)
         for (int a = tid; a < ma; a += 256) mn = fminf(mn, tmin[static_cast<size_t>(q) * ma + a]);
@@ -921,7 +905,6 @@ __global__ void __launch_bounds__(256) quantize_kernel(float* __restrict__ table
     for (int w = 1; w < 8; ++w) qmin = fminf(qmin, red[w]);
     const bool clamp = qmin < 0.f;
     if (clamp) qmin = 0.f;
-    const float qmax = sel_lists ? qmax_sel : qmax_in[q];
     if (tid == 0) {
         qmin_out[q] = qmin;
         if (qmax > 1e30f) atomicExch(err, 1);
@@ -946,6 +929,33 @@ __global__ void __launch_bounds__(256) quantize_kernel(float* __restrict__ table
         out.x = qv[0]; out.y = qv[1]; out.z = qv[2]; out.w = qv[3];
         *reinterpret_cast<char4*>(qtables + base + e) = out;
     }
+}
+
+__global__ void __launch_bounds__(256) quantize_kernel(float* __restrict__ tables, const float* __restrict__ tmin,
+                                                       const float* __restrict__ qmax_in, int ma, int M,
+                                                       int8_t* __restrict__ qtables, float* __restrict__ qmin_out,
+                                                       int* __restrict__ err, const float* __restrict__ qmin_in = nullptr,
+                                                       const int32_t* __restrict__ assign = nullptr,
+                                                       const uint32_t* __restrict__ part_size = nullptr,
+                                                       const uint32_t* __restrict__ sel_lists = nullptr, int sel_n = 0,
+                                                       int sel_r = 0, float* qmax_out = nullptr) {
+    // qmin_in / assign / part_size ("owner computes"): the query's minimum comes from bounds_combine_kernel and only the
+    // tables of probes whose list lives on this device exist.
+    // sel_lists (flat databases, split prefix scan): qmax is selected here — the sel_r-th smallest of the sel_n values
+    // the splits left (a launch of its own before) — and stored to qmax_out.
+    __shared__ float red[8];
+    __shared__ int sel_hist[256], sel_state[2];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    float qmax;
+    if (sel_lists) {
+        int n_less;
+        qmax = __uint_as_float(block_radix_select(sel_lists + static_cast<size_t>(q) * sel_n, sel_n, sel_r, sel_hist,
+                                                  sel_state, tid, n_less));
+        if (tid == 0) qmax_out[q] = qmax;   // FLT_MAX (the padding) when fewer than sel_r prefix vectors exist
+    } else {
+        qmax = qmax_in[q];
+    }
+    quantize_query(tables, tmin, qmax, ma, M, qtables, qmin_out, err, qmin_in, assign, part_size, q, tid, red);
 }
 
 }  // namespace qadc

@@ -253,6 +253,66 @@ def test_ivf_random_large(qadc, oracle):
     ix.close()
 
 
+# ---- long flat keep-prefixes: int8 lower bounds in front of the float prefix scan (qadc_flatprep.cuh) ------------
+def _flat_prefix_case(rng, kind, n, m):
+    codes = synth.make_codes(rng, n, m)
+    if kind == "identical":            # every prefix vector ties: more candidates than slots, every vector evaluated
+        codes[:] = codes[0]
+    elif kind == "two_values":         # two distinct vectors: the r-th smallest sits inside one huge tie class
+        codes[:] = codes[rng.integers(0, 2, n)]
+    elif kind == "sample_unlike_rest": # the first 65 536 vectors (the provisional bound's sample) are all the same vector
+        codes[:65536] = codes[0]
+    return codes
+
+
+@pytest.mark.parametrize("kind,m,dim,n,keep,r", [
+    ("random", 16, 128, 300000, 0.5, 100), ("random", 32, 96, 280000, 0.5, 16), ("random", 16, 64, 270000, 0.5, 512),
+    ("random", 16, 128, 270000, 0.5, 513), ("random", 16, 128, 300000, 0.45, 1), ("identical", 16, 128, 270000, 0.5, 100),
+    ("two_values", 32, 128, 270000, 0.5, 50), ("sample_unlike_rest", 16, 128, 300000, 0.5, 100),
+    ("random", 16, 128, 60000, 0.5, 100)])
+def test_flat_long_prefix_bounds_bit_exact(qadc, oracle, kind, m, dim, n, keep, r):
+    """qmax / qmin / int8 tables of a flat database whose keep-prefix is long enough for the int8 pre-selection
+    (>= 131 072 vectors): bit-identical to the plain float prefix scan (option flat_prep = 0) and to the oracle, and so
+    are the search results; r = 513 is past the pre-selection's limit and the 30 000-vector prefix below its minimum
+    (plain path either way)."""
+    rng = np.random.default_rng(len(kind) * 1000 + m + r)
+    cb = synth.make_pq(rng, dim, m)
+    codes = _flat_prefix_case(rng, kind, n, m)
+    q = synth.make_queries(rng, 6, dim)
+    ix = flat_index(qadc, dim, m, cb, codes, keep)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=keep, offsets=np.array([0, n], np.int64)), q, 1, r)
+    outs = {}
+    for prep in (1, 0):
+        ix.set_option("flat_prep", prep)
+        out = ix.build_tables(q, 1, r)
+        assert out["rc"] == 0
+        for k in ("qmin", "qmax", "qtables"):
+            assert np.array_equal(out[k], exp[k]), (prep, k)
+        ids, d, cnt = ix.search(q, 1, r)
+        assert np.array_equal(ids, exp["ids"]) and np.array_equal(d, exp["d"]) and np.array_equal(cnt, exp["count"]), prep
+        outs[prep] = out
+    ix.close()
+
+
+def test_flat_long_prefix_degenerate_scale(qadc, oracle):
+    """Sub-quantiser tables that are almost constant next to their sum (every centroid of a sub-quantiser at nearly the
+    same large distance from the query): the provisional scale is rejected and the pre-selection keeps every vector."""
+    rng = np.random.default_rng(4242)
+    dim, m, n, r = 64, 16, 280000, 100
+    cb = (synth.make_pq(rng, dim, m) * 1e-3).astype(np.float32)
+    q = (synth.make_queries(rng, 4, dim) + 50.0).astype(np.float32)
+    codes = synth.make_codes(rng, n, m)
+    ix = flat_index(qadc, dim, m, cb, codes, 0.5)
+    exp = oracle.search(dict(dim=dim, m=m, codebooks=cb, codes=codes, keep=0.5, offsets=np.array([0, n], np.int64)), q, 1, r)
+    out = ix.build_tables(q, 1, r)
+    assert out["rc"] == 0
+    for k in ("qmin", "qmax", "qtables"):
+        assert np.array_equal(out[k], exp[k]), k
+    ids, d, cnt = ix.search(q, 1, r)
+    assert np.array_equal(ids, exp["ids"]) and np.array_equal(d, exp["d"]) and np.array_equal(cnt, exp["count"])
+    ix.close()
+
+
 # ---- Stage T: tables, bounds, int8 tables ---------------------------------------------------
 @pytest.mark.parametrize("name", FLAT + IVF + OPQ)
 def test_table_pipeline_vs_oracle_and_reference(qadc, oracle, name):

@@ -4,8 +4,8 @@ rank 0's contiguous shard of the 1e9 x 16x4 bench database with the replicated k
 per step, one query per pass.  The scan shrinks with G, the table / keep-prefix / bound / merge stages do not: at G = 8
 they are what separates the measured scaling from linear.
 
-usage: [G=8] [STEPS=40] [QADC_LIB=build_ab/x.so] python tools/bench_fixed.py [out.npz]
-Prints one line per setting of the `flat_seed` option (skipped for libraries that do not know it) and, when a path is
+usage: [G=8] [STEPS=40] [OPT=flat_prep] [QADC_LIB=build_ab/x.so] python tools/bench_fixed.py [out.npz]
+Prints one line per setting (1, 0, 1, 0) of the option OPT (skipped for libraries that do not know it) and, when a path is
 given, stores the result arrays so that two builds can be compared bit for bit (tools/bench_fixed.py a.npz b.npz = compare)."""
 import os
 import sys
@@ -67,9 +67,10 @@ def step():
 
 
 out = {}
+OPT = os.environ.get("OPT", "flat_prep")
 for seed in (1, 0, 1, 0):
     try:
-        ix.set_option("flat_seed", seed)
+        ix.set_option(OPT, seed)
     except qadc_b200.QadcError:
         if seed == 0:
             continue
@@ -84,14 +85,14 @@ for seed in (1, 0, 1, 0):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / STEPS
     scan = float(np.mean(ix.scan_ms_history(min(STEPS, 64))))
-    print(f"G={G} n_local={n_local} prefix={n_prefix} flat_seed={seed}: step {ms:.4f} ms, scan kernel {scan:.4f} ms, "
+    print(f"G={G} n_local={n_local} prefix={n_prefix} {OPT}={seed}: step {ms:.4f} ms, scan kernel {scan:.4f} ms, "
           f"fixed {1e3 * (ms - scan):.1f} us, launches/step {ix.last_launch_count()}", flush=True)
     out[f"ids_seed{seed}"] = d_ids.cpu().numpy()
     out[f"d_seed{seed}"] = d_d.cpu().numpy()
     out[f"cnt_seed{seed}"] = d_cnt.cpu().numpy()
 if "ids_seed0" in out:
     same = all(np.array_equal(out[f"{k}_seed0"], out[f"{k}_seed1"]) for k in ("ids", "d", "cnt"))
-    print("flat_seed 0 == flat_seed 1:", same, flush=True)
+    print(f"{OPT} 0 == {OPT} 1:", same, flush=True)
 if len(sys.argv) == 2:
     np.savez(sys.argv[1], ids=out["ids_seed1"], d=out["d_seed1"], cnt=out["cnt_seed1"])
 ix.close()
