@@ -410,6 +410,15 @@ def run_ours(args):
             ms = float(t.item())
         return ms / steps
 
+    def per_rank(x):
+        """[x of rank 0, ..., x of rank world-1] (diagnostic: skew between the GPUs of a box)"""
+        if world == 1:
+            return [float(x)]
+        t = torch.zeros(world, device=dev)
+        t[rank] = float(x)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
     for _ in range(args.warmup):
         step_device()
     ix.synchronize()
@@ -424,6 +433,7 @@ def run_ours(args):
     ms_step = timed(step_device, args.steps)
     # CUDA events recorded on the launching stream around every scan launch of the timed steps
     scan_ms = ix.scan_ms_history(min(args.steps, 64))
+    scan_ms_ranks = per_rank(np.mean(scan_ms))
     if prof:
         torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
@@ -432,6 +442,25 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     ix.synchronize()
+    # diagnostic (N > 1): where a step's time goes on every rank — the local search vs the top-r exchange (NCCL all-gather
+    # + shard merge; a rank that finishes its scan early waits here for the slowest GPU of the box)
+    exchange = None
+    if world > 1:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        acc = [0.0, 0.0]
+        for _ in range(5):
+            barrier()
+            ev[0].record(stream)
+            ix.search_device(d_q.data_ptr(), nq, 1, R, d_ids.data_ptr(), d_d.data_ptr(), d_cnt.data_ptr(), d_keys.data_ptr())
+            ev[1].record(stream)
+            dist.all_gather_into_tensor(g_keys.view(world * nq, R), d_keys)
+            ix.merge_shards_device(g_keys.data_ptr(), None, world, nq, R, o_ids.data_ptr(), o_d.data_ptr(), o_cnt.data_ptr())
+            ev[2].record(stream)
+            stream.synchronize()
+            acc[0] += ev[0].elapsed_time(ev[1]) / 5
+            acc[1] += ev[1].elapsed_time(ev[2]) / 5
+        exchange = {"search_ms_per_rank": per_rank(acc[0]), "allgather_and_merge_ms_per_rank": per_rank(acc[1]),
+                    "note": "5 untimed steps after the timed region; the exchange includes waiting for the slowest rank"}
     # informational: the same step with 4 queries sharing every pass over the codes.  A quarter of
     # the HBM traffic, so the scan is bound by integer issue instead of HBM (and draws less power);
     # not the configuration `value` / `roofline` are quoted on.
@@ -527,11 +556,12 @@ def run_ours(args):
                 "queries_per_pass": 4, "value": N * nq / (ms_batched * 1e-3), "unit": "vectors/s", "ms_per_step": ms_batched,
                 "note": "informational: same step, 4 queries share each pass over the codes (integer-issue bound)"},
             "verify": verify,
+            "exchange": exchange,
             "configs": configs,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "scan_flat_wr_kernel<16,4> (one query per pass, per-warp TMA rings)" if qb_used == 1 else "scan_flat_wrq_kernel (several queries per pass)",
-                         "kernel_ms": t_scan * 1e3, "kernel_share_of_step": t_scan * 1e3 / ms_step,
+                         "kernel_ms": t_scan * 1e3, "kernel_ms_per_rank": scan_ms_ranks, "kernel_share_of_step": t_scan * 1e3 / ms_step,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": passes * n_local * CODE_BYTES},
         }

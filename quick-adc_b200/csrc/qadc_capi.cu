@@ -73,7 +73,7 @@ struct qadc_ctx {
     DevBuf b_adc_dists;
     // scratch
     DevBuf staging, b_queries, b_assign, b_tables, b_tmin, b_qmax, b_qmin, b_qtables, b_lists, b_plists, b_ids,
-        b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound, b_cdist, b_qmin_raw, b_prov, b_fprep, b_cand, b_ghist;
+        b_dists, b_counts, b_keys, b_dump, b_hist, b_sbound, b_cdist, b_qmin_raw, b_prov, b_cand, b_ghist;
     int local_nq = 0, local_ma = 0, local_r = 0;   // batch whose tables qadc_tables_local_device left in the scratch
     bool local_mode = false;                        // scan_device runs for qadc_search_bounded_device: only owned probes have tables
     int* d_err = nullptr;
@@ -81,6 +81,7 @@ struct qadc_ctx {
     // options / accounting
     long opt_flat_qb = 0, opt_flat_chunks = 0, opt_flat_filter = 1, opt_ivf_fused = 1, opt_flat_ring = 1, opt_flat_seed = 1, opt_flat_prep = 1, opt_seed_minus = 0, opt_flat_share = 1;
     bool sbound_seeded = false;   // the fused inverted-list table kernel already wrote the shared bounds of this batch
+    bool ghist_zeroed = false;    // the table pipeline of this batch already zeroed b_ghist for the scan that follows
     int ivf_sb_per_item = 8;   // superblocks per work item of the IVF scan (option "ivf_sb_per_item")
     int launches = 0;
     cudaEvent_t ev[8] = {};
@@ -378,10 +379,13 @@ int scan_device(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qtables,
         a.ghist = nullptr;
         if (ctx->opt_flat_share && pl.chunks > 1) {
             // the chunks of a query pool their candidates in a global histogram (hist_publish)
-            ENSURE(ctx->b_ghist, static_cast<size_t>(nq) * 128 * 4);
-            QCK(cudaMemsetAsync(ctx->b_ghist.p, 0, static_cast<size_t>(nq) * 128 * 4, ctx->stream));
+            if (!ctx->ghist_zeroed) {   // (the long-prefix table pipeline zeroes it together with its own counters)
+                ENSURE(ctx->b_ghist, static_cast<size_t>(nq) * 129 * 4);
+                QCK(cudaMemsetAsync(ctx->b_ghist.p, 0, static_cast<size_t>(nq) * 128 * 4, ctx->stream));
+            }
             a.ghist = ctx->b_ghist.as<int>();
         }
+        ctx->ghist_zeroed = false;
         if (ctx->scan_timed) QCK(cudaEventRecord(ctx->ev_scan0[ctx->scan_seq % qadc_ctx::kScanRing], ctx->stream));
         rc = pl.v->launch(ctx, a, pl.chunks);
         if (rc) return rc == QADC_ENOMEM ? fail(ctx, rc, "scan kernel shared memory exceeds 227 KB") : rc;
@@ -546,15 +550,16 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         const size_t te = static_cast<size_t>(M) * 16;
         const int nsplit = static_cast<int>(std::min(n_prefix, kPrefSampleMax) / kPrefSplit);
         ENSURE(ctx->b_prov, static_cast<size_t>(nq) * te);
-        ENSURE(ctx->b_fprep, static_cast<size_t>(nq) * 4);
+        ENSURE(ctx->b_ghist, static_cast<size_t>(nq) * 129 * 4);   // [nq][128] the scan's global histograms | [nq] candidate counts
         ENSURE(ctx->b_cand, static_cast<size_t>(nq) * kPrefCandCap * 4);
         ENSURE(ctx->b_plists, static_cast<size_t>(nq) * nsplit * r * 4);
         ENSURE(ctx->b_sbound, static_cast<size_t>(nq) * 4);
-        QCK(cudaMemsetAsync(ctx->b_fprep.p, 0, static_cast<size_t>(nq) * 4, ctx->stream));
+        QCK(cudaMemsetAsync(ctx->b_ghist.p, 0, static_cast<size_t>(nq) * 129 * 4, ctx->stream));   // one memset for both
+        ctx->ghist_zeroed = true;
         FlatPrepArgs fa;
         fa.starts = ctx->d_starts; fa.native = ctx->d_starts_native; fa.n_prefix = n_prefix;
         fa.tables = ctx->b_tables.as<float>(); fa.r = r; fa.nsplit = nsplit; fa.sample_lists = ctx->b_plists.as<uint32_t>();
-        fa.prov_qt = ctx->b_prov.as<int8_t>(); fa.cand_count = ctx->b_fprep.as<unsigned int>();
+        fa.prov_qt = ctx->b_prov.as<int8_t>(); fa.cand_count = ctx->b_ghist.as<unsigned int>() + static_cast<size_t>(nq) * 128;
         fa.cand = ctx->b_cand.as<uint32_t>(); fa.seed_out = ctx->b_sbound.as<int>();
         const uint32_t n_sb = (n_prefix + kSbVec - 1) / kSbVec;
         dim3 sgrid(nsplit, nq), pgrid(flat_prep_splits(ctx, n_sb, nq), nq);
@@ -1312,7 +1317,7 @@ int qadc_build_tables(qadc_ctx* ctx, const float* queries, int nq, int ma, int r
     ctx->launches = 0;
     rc = tables_device(ctx, ctx->b_queries.as<float>(), nq, ma, r, d_ain, false, out_tables != nullptr);
     if (rc) return rc;
-    ctx->sbound_seeded = false;   // no scan follows this call
+    ctx->sbound_seeded = false; ctx->ghist_zeroed = false;   // no scan follows this call
     QCK(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_assign) QCK(cudaMemcpyAsync(out_assign, ctx->b_assign.p, nqa * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_tables) QCK(cudaMemcpyAsync(out_tables, ctx->b_tables.p, nqa * td * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -214,26 +214,20 @@ __device__ __forceinline__ int hist_update(int* hist, int* hist_total, int* hist
 // only knows the CTA's share of the vectors, so its r-th distance is that of 1/chunks of the database — on rank 0 of an
 // 8-way sharded 1e9 scan the bound stayed 10-20 above the final one for most of a CTA's life, the pre-filter passed too
 // many superblocks to the exact core and the scan took 2.78 ms where a perfect seed gave 2.565 (tools/exp_seed.py).
-// Whenever a CTA re-derives its own bound it therefore also PUBLISHES the candidates it has counted since the last time
-// to the query's histogram in global memory (ghist, zeroed per launch; non-negative deltas under a CTA-wide lock, so the
-// global counts never exceed the number of scanned vectors at each distance) and takes the bound of the union: the
-// smallest distance whose global cumulative count reaches r.  A whole warp calls it; returns that bound or 127.
-__device__ __forceinline__ int hist_publish(const int* hist, int* hpub, int* publock, int* ghist, int r, int lane,
-                                            int* shared_bound) {
-    int got = 0;
-    if (lane == 0) got = atomicCAS(publock, 0, 1) == 0;
-    got = __shfl_sync(0xffffffffu, got, 0);
-    if (!got) return 127;   // another warp of the CTA is publishing
-    __syncwarp();
-    const int4 cur = *reinterpret_cast<const int4*>(hist + lane * 4);   // counts only grow
-    const int4 pub = *reinterpret_cast<const int4*>(hpub + lane * 4);
+// When a query has several CTAs its candidates are therefore counted in a PENDING histogram (`pend`, the only one the
+// CTA keeps then), and every r/4 candidates a warp moves what is pending — atomicExch per bin, so every candidate is
+// handed over exactly once whichever warps publish concurrently — into the query's histogram in global memory (ghist,
+// zeroed per launch: its counts never exceed the number of scanned vectors at each distance) and takes the bound of the
+// union: the smallest distance whose global cumulative count reaches r.  A whole warp calls it; returns that bound or 127.
+__device__ __forceinline__ int hist_publish(int* pend, int* ghist, int r, int lane, int* shared_bound) {
+    int* p = pend + lane * 4;
     int* g = ghist + lane * 4;
-    if (cur.x > pub.x) atomicAdd(g, cur.x - pub.x);
-    if (cur.y > pub.y) atomicAdd(g + 1, cur.y - pub.y);
-    if (cur.z > pub.z) atomicAdd(g + 2, cur.z - pub.z);
-    if (cur.w > pub.w) atomicAdd(g + 3, cur.w - pub.w);
-    *reinterpret_cast<int4*>(hpub + lane * 4) = cur;
-    const int4 c = __ldcg(reinterpret_cast<const int4*>(g));   // the other CTAs' counts (own additions may be missing: fine)
+    const int d0 = atomicExch(p, 0), d1 = atomicExch(p + 1, 0), d2 = atomicExch(p + 2, 0), d3 = atomicExch(p + 3, 0);
+    if (d0) atomicAdd(g, d0);
+    if (d1) atomicAdd(g + 1, d1);
+    if (d2) atomicAdd(g + 2, d2);
+    if (d3) atomicAdd(g + 3, d3);
+    const int4 c = __ldcg(reinterpret_cast<const int4*>(g));   // the other CTAs' counts (own additions may still be on their way: fine)
     const int mine = c.x + c.y + c.z + c.w;
     int incl = mine;
 #pragma unroll
@@ -242,22 +236,15 @@ __device__ __forceinline__ int hist_publish(const int* hist, int* hpub, int* pub
         if (lane >= o) incl += up;
     }
     const unsigned reached = __ballot_sync(0xffffffffu, incl >= r);
+    if (!reached) return 127;
+    const int src = __ffs(reached) - 1;
     int b = 127;
-    if (reached) {
-        const int src = __ffs(reached) - 1;
-        if (lane == src) {
-            const int c0 = incl - mine + c.x, c1 = c0 + c.y, c2 = c1 + c.z;
-            b = lane * 4 + (c0 >= r ? 0 : (c1 >= r ? 1 : (c2 >= r ? 2 : 3)));
-            if (b < 127) atomicMin(shared_bound, b);
-        }
-        b = __shfl_sync(0xffffffffu, b, src);
+    if (lane == src) {
+        const int c0 = incl - mine + c.x, c1 = c0 + c.y, c2 = c1 + c.z;
+        b = lane * 4 + (c0 >= r ? 0 : (c1 >= r ? 1 : (c2 >= r ? 2 : 3)));
+        if (b < 127) atomicMin(shared_bound, b);
     }
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();   // hpub is written before the lock opens
-        atomicExch(publock, 0);
-    }
-    return b;
+    return __shfl_sync(0xffffffffu, b, src);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -635,8 +622,8 @@ struct WarpRingCfg {
     static constexpr int kSlotBytes = NPS * kSbBytes;   // a ring slot holds NPS consecutive superblocks (one TMA copy, one barrier)
     static constexpr int kRingBytes = NW * NSW * kSlotBytes;
     static constexpr int kThreads = NW * 32;
-    // rings | table | per-warp filter tables | barriers | histogram + published copy + counters | list counts/bounds, rounded to 16 bytes
-    static constexpr int kFixedBytes = ((kRingBytes + M * 16 + NW * M * 16 + NW * NSW * 8 + (2 * 128 + 4) * 4 + NW * 8) + 15) / 16 * 16;
+    // rings | table | per-warp filter tables | barriers | histogram + counters | list counts/bounds, rounded to 16 bytes
+    static constexpr int kFixedBytes = ((kRingBytes + M * 16 + NW * M * 16 + NW * NSW * 8 + (128 + 4) * 4 + NW * 8) + 15) / 16 * 16;
     static size_t smem_bytes(int cap) { return static_cast<size_t>(kFixedBytes) + static_cast<size_t>(NW) * cap * 8; }
 };
 
@@ -650,11 +637,9 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
     uint4* ftab = qtab + M;                                                                // [NW][M]
     uint64_t* full = reinterpret_cast<uint64_t*>(ftab + NW * M);                           // [NW][NSW]
     int* hist = reinterpret_cast<int*>(full + NW * NSW);                                   // [128]
-    int* hpub = hist + 128;                                                                // [128] counts already in a.ghist
-    int* hist_total = hpub + 128;
+    int* hist_total = hist + 128;
     int* hist_next = hist_total + 1;
-    int* publock = hist_next + 1;
-    int* cnt = publock + 2;                                                                // [NW]
+    int* cnt = hist_next + 3;                                                              // [NW]
     int* bnd = cnt + NW;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + Cfg::kFixedBytes);                // [NW][cap]
 
@@ -672,8 +657,8 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
     for (int i = threadIdx.x; i < NW * a.cap; i += blockDim.x) lists[i] = kEmptyKey;
     for (int i = threadIdx.x; i < NW; i += blockDim.x) { cnt[i] = 0; bnd[i] = 127; }
     int* ghist = (a.ghist && gridDim.x > 1) ? a.ghist + static_cast<size_t>(q) * 128 : nullptr;   // one chunk: the CTA sees everything
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;   // hist + hpub
-    if (threadIdx.x == 0) { *hist_total = 0; *hist_next = ghist ? max(a.r / 4, 8) : a.r; *publock = 0; }
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) hist[i] = 0;   // (the pending counts when the query has several CTAs)
+    if (threadIdx.x == 0) { *hist_total = 0; *hist_next = ghist ? max(a.r / 4, 8) : a.r; }
     __syncthreads();
 
     WarpList wl{lists + static_cast<size_t>(warp) * a.cap, cnt + warp, bnd + warp};
@@ -760,7 +745,7 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
                     __syncwarp();
                     const int now = *wl.count;
                     int hb = hist_update(hist, hist_total, hist_next, now - before, a.r, lane, sbound, ghist != nullptr);
-                    if (hb == -1) hb = hist_publish(hist, hpub, publock, ghist, a.r, lane, sbound);   // threshold passed: share
+                    if (hb == -1) hb = hist_publish(hist, ghist, a.r, lane, sbound);   // threshold passed: share
                     if (hb < gb) gb = hb;
                     if (now >= compact_at) {
                         wl.compact(a.cap, a.r, lane, sbound);
@@ -877,8 +862,8 @@ struct WarpRingBatchCfg {
     static constexpr int kQuads = M / 4, kSbBytes = M * 128;
     static constexpr int kRingBytes = NW * NSW * kSbBytes;
     static constexpr int kThreads = NW * 32;
-    // rings | tables | barriers | histograms + published copies + counters | list counts/bounds, rounded to 16 bytes
-    static constexpr int kFixedBytes = ((kRingBytes + QB * M * 16 + NW * NSW * 8 + QB * (2 * 128 + 4) * 4 + NW * QB * 8) + 15) / 16 * 16;
+    // rings | tables | barriers | histograms + counters | list counts/bounds, rounded to 16 bytes
+    static constexpr int kFixedBytes = ((kRingBytes + QB * M * 16 + NW * NSW * 8 + QB * (128 + 2) * 4 + NW * QB * 8) + 15) / 16 * 16;
     static size_t smem_bytes(int cap) { return static_cast<size_t>(kFixedBytes) + static_cast<size_t>(NW) * QB * cap * 8; }
 };
 
@@ -890,11 +875,9 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wrq_kernel(const FlatSca
     uint4* qtab = reinterpret_cast<uint4*>(rings + Cfg::kRingBytes);                       // [QB][M]
     uint64_t* full = reinterpret_cast<uint64_t*>(qtab + QB * M);                           // [NW][NSW]
     int* hist = reinterpret_cast<int*>(full + NW * NSW);                                   // [QB][128]
-    int* hpub = hist + QB * 128;                                                           // [QB][128] counts already in a.ghist
-    int* hist_total = hpub + QB * 128;                                                     // [QB]
+    int* hist_total = hist + QB * 128;                                                     // [QB]
     int* hist_next = hist_total + QB;                                                      // [QB]
-    int* publock = hist_next + QB;                                                         // [QB] (+ QB pad)
-    int* cnt = publock + 2 * QB;                                                           // [NW][QB]
+    int* cnt = hist_next + QB;                                                             // [NW][QB]
     int* bnd = cnt + NW * QB;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + Cfg::kFixedBytes);                // [NW][QB][cap]
 
@@ -917,8 +900,8 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wrq_kernel(const FlatSca
     for (int i = threadIdx.x; i < NW * QB * a.cap; i += blockDim.x) lists[i] = kEmptyKey;
     for (int i = threadIdx.x; i < NW * QB; i += blockDim.x) { cnt[i] = 0; bnd[i] = 127; }
     int* const ghist0 = (a.ghist && gridDim.x > 1) ? a.ghist + static_cast<size_t>(qbase) * 128 : nullptr;   // one chunk: nothing to share
-    for (int i = threadIdx.x; i < 2 * QB * 128; i += blockDim.x) hist[i] = 0;   // hist + hpub
-    for (int i = threadIdx.x; i < QB; i += blockDim.x) { hist_total[i] = 0; hist_next[i] = ghist0 ? max(a.r / 4, 8) : a.r; publock[i] = 0; }
+    for (int i = threadIdx.x; i < QB * 128; i += blockDim.x) hist[i] = 0;   // (the pending counts when the queries have several CTAs)
+    for (int i = threadIdx.x; i < QB; i += blockDim.x) { hist_total[i] = 0; hist_next[i] = ghist0 ? max(a.r / 4, 8) : a.r; }
     __syncthreads();
 
     // (warp, query) candidate lists; the rare path takes the query as a RUNTIME index so that it exists once in the
@@ -961,7 +944,7 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wrq_kernel(const FlatSca
             int hb = hist_update(hist + qi * 128, hist_total + qi, hist_next + qi, now - before, a.r, lane,
                                  a.shared_bound + qbase + qi, ghist0 != nullptr);
             if (hb == -1)   // threshold passed: pool the candidates of the query's chunks (hist_publish)
-                hb = hist_publish(hist + qi * 128, hpub + qi * 128, publock + qi, ghist0 + qi * 128, a.r, lane, a.shared_bound + qbase + qi);
+                hb = hist_publish(hist + qi * 128, ghist0 + qi * 128, a.r, lane, a.shared_bound + qbase + qi);
             if (hb < hb_out) hb_out = hb;
             if (now >= compact_at) {
                 wl.compact(a.cap, a.r, lane, a.shared_bound + qbase + qi);
