@@ -138,7 +138,7 @@ def ncu_traffic_per_launch(n_local, nq, qb):
     (1e9 local vectors, 16 queries per step, 1 query per pass); (None, None) for any other configuration."""
     if (n_local, nq, qb) != (10 ** 9, 16, 1):
         return None, None
-    for name in ("r02b_scan_flat_16x4_1B_ncu_full.txt", "r02_scan_flat_16x4_1B_ncu_full.txt", "r01_scan_flat_16x4_1B_ncu_full.txt"):
+    for name in ("r02c_scan_flat_16x4_1B_ncu_full.txt", "r02b_scan_flat_16x4_1B_ncu_full.txt", "r02_scan_flat_16x4_1B_ncu_full.txt", "r01_scan_flat_16x4_1B_ncu_full.txt"):
         p = os.path.join(ROOT, "profiles", name)
         try:
             vals = {}

@@ -263,8 +263,15 @@ int qadc_adc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, 
  * lookup core of the one-query-per-pass flat scan, 0 = exact core only; same results), "ivf_fused" (1 = default:
  * one kernel per query batch builds the float tables of an inverted-list search in shared memory, bounds and
  * quantises them there; 0 = the separate table / prefix / quantise kernels; same results), "ivf_sb_per_item" (256-vector blocks per work item of the inverted-list
- * scan, default 8), "time_scan" (1: record CUDA events around the scan kernel for
- * qadc_last_scan_ms).  Unknown key -> QADC_EINVAL. */
+ * scan, default 8), "flat_ring" (1 = default: per-warp TMA rings; 0 = the CTA-wide ring of round 1), "flat_share"
+ * (1 = default: the CTAs that scan different chunks of a flat database for the same query pool their candidates in a
+ * global histogram, so that the query's bound is that of everything scanned so far; 0 = every CTA derives it from its
+ * own chunk; same results), "flat_prep" (1 = default: flat databases whose keep-prefix has at least 131 072 vectors
+ * select the candidates of the float prefix scan with int8 lower bounds; 0 = the plain float scan of the whole prefix;
+ * same qmax, tables and results), "flat_seed" (1 = default: the scan's bound starts at a value derived from the
+ * keep-prefix; 0 = at 126; same results), "time_scan" (1: record CUDA events around the scan kernel for
+ * qadc_last_scan_ms).  Every setting returns the same results; the knobs exist for A/B timing and for the parity
+ * tests that compare the paths.  Unknown key -> QADC_EINVAL. */
 int qadc_set_option(qadc_ctx* ctx, const char* key, long value);
 
 #ifdef __cplusplus

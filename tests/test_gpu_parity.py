@@ -290,6 +290,10 @@ def test_flat_long_prefix_bounds_bit_exact(qadc, oracle, kind, m, dim, n, keep, 
             assert np.array_equal(out[k], exp[k]), (prep, k)
         ids, d, cnt = ix.search(q, 1, r)
         assert np.array_equal(ids, exp["ids"]) and np.array_equal(d, exp["d"]) and np.array_equal(cnt, exp["count"]), prep
+        # injected int8 tables: the bound is then seeded by the histogram pass over the nibble-plane prefix (its r-th
+        # smallest sum found by the last CTA to finish) instead of the table pipeline's candidates
+        ids, d, cnt = ix.scan_with_tables(out["assign"], out["qtables"], r)
+        assert np.array_equal(ids, exp["ids"]) and np.array_equal(d, exp["d"]) and np.array_equal(cnt, exp["count"]), prep
         outs[prep] = out
     ix.close()
 
