@@ -72,9 +72,10 @@ void qadc_destroy(qadc_ctx* ctx);
 const char* qadc_last_error(const qadc_ctx* ctx);
 
 /* ---- quantisers ----------------------------------------------------------------------- */
-/* Replaces base_pq / opq state (quantizers.hpp:96-168, :248-301).  bits must be 4 and m in
- * {16, 32} (get_simd_scan_func_epi8, db_query_4.cpp:23-35).  rotation: dim*dim row-major
- * (opq::rotation) or NULL for a plain PQ.  Host pointers. */
+/* Replaces base_pq / opq state (quantizers.hpp:96-168, :248-301).  The Quick ADC database needs bits = 4 and m in
+ * {16, 32} (get_simd_scan_func_epi8, db_query_4.cpp:23-35); the plain ADC entry points (qadc_adc_load / qadc_adc_search)
+ * and qadc_encode also take (4,8) (8,8) (16,8) (2,16) (4,16) (8,16) (get_scan_func, query_common.hpp:122-147).
+ * codebooks: m x 2^bits x dim/m floats.  rotation: dim*dim row-major (opq::rotation) or NULL for a plain PQ.  Host pointers. */
 int qadc_set_pq(qadc_ctx* ctx, int dim, int m, int bits, const float* codebooks,
                 const float* rotation);
 /* Replaces index_db::centroids (databases.hpp:176-189): K*dim floats. K == 0 / never
@@ -232,8 +233,8 @@ int qadc_download_codes(qadc_ctx* ctx, int part_i, uint8_t* out_codes);
 /* Replaces base_pq::encode_multiple_vectors + multiple_set_bits_4 (quantizers.hpp:49-68,
  * :222-245) and, with a coarse quantiser set, index_db::assign_single_compute_residuals
  * (databases.hpp:252-268): rotates (OPQ; with inverted lists the residual is what is rotated) and encodes `count` host vectors
- * (count*dim floats) into row-major codes (count*m*bits/8 bytes; 8-bit quantisers: one byte per
- * sub-quantiser, multiple_set_bits_native<uint8_t>, quantizers.hpp:36-47).  out_assign (count, may be
+ * (count*dim floats) into row-major codes (count*m*bits/8 bytes; 8- / 16-bit quantisers: one byte / one little-endian uint16
+ * per sub-quantiser, multiple_set_bits_native<T>, quantizers.hpp:36-47).  out_assign (count, may be
  * NULL) receives the coarse cell of every vector when the context has a coarse quantiser; the
  * code is then that of the residual.  Nearest centroid by direct squared distance, first minimum
  * on ties. */
@@ -246,7 +247,8 @@ int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* ou
  * [offsets[p], offsets[p+1]) (partition_count + 1 offsets; 1 partition for a flat database, K for
  * inverted lists, which also need `labels`).  Code size m*bits/8 bytes; 4-bit codes two per byte,
  * low nibble first (quantizers.hpp:49-68).  Works for every quantiser qadc_set_pq accepts:
- * (16,4) (32,4) (4,8) (8,8) (16,8); the 16-bit configurations of db_query are not supported.
+ * (16,4) (32,4) (4,8) (8,8) (16,8) (2,16) (4,16) (8,16) — every pair of get_scan_func (query_common.hpp:122-147);
+ * 16-bit codes are one little-endian uint16 per sub-quantiser.
  * Independent of the Quick ADC database (qadc_begin_database .. qadc_finalize). */
 int qadc_adc_load(qadc_ctx* ctx, int partition_count, const uint64_t* offsets, const uint8_t* codes,
                   const uint32_t* labels);

@@ -1,6 +1,7 @@
 // qadc_adc.cuh — the plain ADC scan of the reference's db_query tool ("next" row N4):
 // scanner_simple + scan_standard<uint8_t,NSQ> / scan_4<NSQ> (db_query.cpp:17-46,
-// query_common.hpp:59-118) over row-major codes with float tables of 2^bits entries.
+// query_common.hpp:59-118) over row-major codes with float tables of 2^bits entries (4-, 8- and 16-bit
+// sub-quantisers: every (nsq, bits) pair get_scan_func accepts, query_common.hpp:122-147).
 // Selection rule: the r smallest under (distance, probe rank, position) — what the reference's
 // strict heap test yields when partitions are visited in probe order.  Distances are summed in
 // sub-quantiser order with __fadd_rn (bit-identical to the oracle; the reference's -ffast-math
@@ -23,8 +24,9 @@ struct AdcScanArgs {
 template <int BITS, int NSQ>
 __global__ void __launch_bounds__(kSelThreads) adc_scan_kernel(const AdcScanArgs a) {
     constexpr int CS = NSQ * BITS / 8, NC = 1 << BITS, W = (CS + 3) / 4;
+    constexpr bool kSmemTable = BITS <= 8;   // 16-bit quantisers: 65 536 floats per sub-quantiser stay in global memory (L2)
     __shared__ uint64_t keys[kSelCap];
-    __shared__ float tab[NSQ * NC];
+    __shared__ float tab[kSmemTable ? NSQ * NC : 1];
     __shared__ int count;
     __shared__ unsigned long long bound_key;
     const int split = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
@@ -37,10 +39,12 @@ __global__ void __launch_bounds__(kSelThreads) adc_scan_kernel(const AdcScanArgs
         const uint32_t v0 = static_cast<uint32_t>(static_cast<uint64_t>(n) * split / a.nsplit);
         const uint32_t v1 = static_cast<uint32_t>(static_cast<uint64_t>(n) * (split + 1) / a.nsplit);
         if (v1 > v0) {   // block-uniform
-            __syncthreads();
-            for (int i = tid; i < NSQ * NC; i += kSelThreads)
-                tab[i] = a.tables[(static_cast<size_t>(q) * a.ma + ar) * (NSQ * NC) + i];
-            __syncthreads();
+            const float* gtab = a.tables + (static_cast<size_t>(q) * a.ma + ar) * (NSQ * NC);
+            if constexpr (kSmemTable) {
+                __syncthreads();
+                for (int i = tid; i < NSQ * NC; i += kSelThreads) tab[i] = gtab[i];
+                __syncthreads();
+            }
             const uint8_t* codes = a.rows + a.row_off[p] * CS;
             for (uint32_t base = v0; base < v1; base += kSelCap / 2) {
                 for (uint32_t v = base + tid; v < min(base + kSelCap / 2, v1); v += kSelThreads) {
@@ -58,8 +62,10 @@ __global__ void __launch_bounds__(kSelThreads) adc_scan_kernel(const AdcScanArgs
                     float s = 0.f;
 #pragma unroll
                     for (int j = 0; j < NSQ; ++j) {
-                        const uint32_t idx = BITS == 4 ? (w[j >> 3] >> (4 * (j & 7))) & 15u : (w[j >> 2] >> (8 * (j & 3))) & 255u;
-                        s = __fadd_rn(s, tab[j * NC + idx]);
+                        const uint32_t idx = BITS == 4 ? (w[j >> 3] >> (4 * (j & 7))) & 15u
+                                           : BITS == 8 ? (w[j >> 2] >> (8 * (j & 3))) & 255u
+                                                       : (w[j >> 1] >> (16 * (j & 1))) & 65535u;
+                        s = __fadd_rn(s, kSmemTable ? tab[j * NC + idx] : __ldg(gtab + j * NC + idx));
                     }
                     top.push((static_cast<uint64_t>(__float_as_uint(s)) << 32) | (seq0 + v));
                 }

@@ -716,12 +716,13 @@ const char* qadc_last_error(const qadc_ctx* c) { return c ? c->err.c_str() : g_c
 int qadc_set_pq(qadc_ctx* ctx, int dim, int m, int bits, const float* codebooks, const float* rotation) {
     if (!ctx || !codebooks) return fail(ctx, QADC_EINVAL, "null argument");
     // get_simd_scan_func_epi8 (db_query_4.cpp:23-35), load_database_check (:393-402)
-    // plus the 8-bit configurations of the plain ADC tool (get_scan_func, query_common.hpp:122-147); those
-    // contexts only serve qadc_adc_load / qadc_adc_search
+    // plus the 8- and 16-bit configurations of the plain ADC tool (get_scan_func, query_common.hpp:122-147); those
+    // contexts only serve qadc_adc_load / qadc_adc_search (and qadc_encode)
     const bool quick = bits == 4 && (m == 16 || m == 32);
     const bool adc8 = bits == 8 && (m == 4 || m == 8 || m == 16);
-    if (!quick && !adc8)
-        return fail(ctx, QADC_EINVAL, "Unsupported (nsq,nsq_bits) configuration. Supported: (16,4) (32,4); plain ADC also (4,8) (8,8) (16,8).");
+    const bool adc16 = bits == 16 && (m == 2 || m == 4 || m == 8);
+    if (!quick && !adc8 && !adc16)
+        return fail(ctx, QADC_EINVAL, "Unsupported (nsq,nsq_bits) configuration. Supported: (16,4) (32,4); plain ADC also (4,8) (8,8) (16,8) (2,16) (4,16) (8,16).");
     if (dim <= 0 || dim % m != 0) return fail(ctx, QADC_EINVAL, "dim must be a positive multiple of m");
     if (static_cast<size_t>(dim) * 64 > static_cast<size_t>(kMaxSmem))
         return fail(ctx, QADC_EINVAL, "dim > 3632 is not supported (the table kernel keeps 8 x 2 x dim floats in shared memory)");
@@ -1439,7 +1440,8 @@ int qadc_encode(qadc_ctx* ctx, const float* vectors, uint32_t count, int32_t* ou
             d_in = ctx->b_tables.as<float>();
             residual_done = ivf;
         }
-        const size_t threads = static_cast<size_t>(n) * CS;
+        // one thread per (vector, code byte); 16-bit codes: per (vector, sub-quantiser), two bytes each
+        const size_t threads = ctx->bits == 16 ? static_cast<size_t>(n) * M : static_cast<size_t>(n) * CS;
         encode_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(
             d_in, n, dim, M, ctx->bits, ctx->d_codebooks, (ivf && !residual_done) ? ctx->d_centroids : nullptr, d_assign,
             ctx->b_dump.as<uint8_t>());
@@ -1562,7 +1564,10 @@ int qadc_adc_search(qadc_ctx* ctx, const float* queries, int nq, int ma, int r, 
         else if (bits == 4 && M == 32) adc_scan_kernel<4, 32><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
         else if (bits == 8 && M == 4) adc_scan_kernel<8, 4><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
         else if (bits == 8 && M == 8) adc_scan_kernel<8, 8><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
-        else adc_scan_kernel<8, 16><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
+        else if (bits == 8) adc_scan_kernel<8, 16><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
+        else if (M == 2) adc_scan_kernel<16, 2><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
+        else if (M == 4) adc_scan_kernel<16, 4><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
+        else adc_scan_kernel<16, 8><<<sgrid, kSelThreads, 0, ctx->stream>>>(a);
         ctx->launches++;
         QCK(cudaGetLastError());
         MergeArgs mg{};

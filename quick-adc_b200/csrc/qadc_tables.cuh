@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(256) ivf_prepare_kernel(const IvfPrepArgs a) {
 // base_pq::encode_multiple_vectors + multiple_set_bits_4 / _native<uint8_t> (quantizers.hpp:36-68,
 // :222-245): one thread per (vector, code byte) finds the nearest of the 2^bits centroids (direct
 // squared distance, first minimum wins like the k=1 heap) for the sub-quantisers of that byte:
-// 4-bit codes hold idx[2b] | idx[2b+1]<<4, 8-bit codes idx[b].
+// 4-bit codes hold idx[2b] | idx[2b+1]<<4, 8-bit codes idx[b], 16-bit codes idx[j] as two bytes.
 // `centroids`/`assign` given: encode the residual x - centroid[assign[v]] (index_db::add_vectors).
 __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ vectors, uint32_t count, int dim, int M,
                                                      int bits, const float* __restrict__ codebooks,
@@ -841,6 +841,30 @@ __global__ void __launch_bounds__(256) encode_kernel(const float* __restrict__ v
                                                      const int32_t* __restrict__ assign, uint8_t* __restrict__ codes) {
     const int CS = M * bits / 8, dsq = dim / M, per = 8 / bits, ncent = 1 << bits;
     const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (bits == 16) {
+        // one thread per (vector, sub-quantiser): the nearest of 65 536 centroids, stored as a little-endian uint16
+        // (multiple_set_bits_native<std::uint16_t>)
+        if (t >= static_cast<size_t>(count) * M) return;
+        const uint32_t v = static_cast<uint32_t>(t / M);
+        const int j = static_cast<int>(t % M);
+        const float* x = vectors + static_cast<size_t>(v) * dim;
+        const float* cent = centroids ? centroids + static_cast<size_t>(assign[v]) * dim : nullptr;
+        int best = 0;
+        float bd = 0.f;
+        for (int c = 0; c < ncent; ++c) {
+            const float* cb = codebooks + (static_cast<size_t>(j) * ncent + c) * dsq;
+            float s = 0.f;
+            for (int i = 0; i < dsq; ++i) {
+                const float xi = cent ? __fsub_rn(x[j * dsq + i], __ldg(cent + j * dsq + i)) : x[j * dsq + i];
+                const float diff = __fsub_rn(xi, __ldg(cb + i));
+                s = __fmaf_rn(diff, diff, s);
+            }
+            if (c == 0 || s < bd) { bd = s; best = c; }
+        }
+        codes[static_cast<size_t>(v) * CS + 2 * j] = static_cast<uint8_t>(best & 255);
+        codes[static_cast<size_t>(v) * CS + 2 * j + 1] = static_cast<uint8_t>(best >> 8);
+        return;
+    }
     if (t >= static_cast<size_t>(count) * CS) return;
     const uint32_t v = static_cast<uint32_t>(t / CS);
     const int b = static_cast<int>(t % CS);

@@ -149,7 +149,7 @@ inline std::unique_ptr<base_db> load_qdb(std::istream& in, const char* filename,
     const int kind = h[0], pq_kind = h[1], dim = h[2], m = h[3], bits = h[4], K = h[5];
     // every header field is checked before it sizes an allocation (a corrupt file must say so, not crash):
     // geometry like get_pq below, every array bounded by the file length
-    const bool geometry_ok = (kind == 0 || kind == 1) && (pq_kind == 0 || pq_kind == 1) && m > 0 && (bits == 4 || bits == 8) &&
+    const bool geometry_ok = (kind == 0 || kind == 1) && (pq_kind == 0 || pq_kind == 1) && m > 0 && (bits == 4 || bits == 8 || bits == 16) &&
                              dim > 0 && dim <= (1 << 20) && dim % m == 0 && (m * bits) % 8 == 0 && K > 0 && (kind == 1 || K == 1);
     const std::uint64_t fixed_bytes = geometry_ok ? ((static_cast<std::uint64_t>(dim) << bits) + (pq_kind ? static_cast<std::uint64_t>(dim) * dim : 0) +
                                                      (kind ? static_cast<std::uint64_t>(K) * dim : 0)) * 4 + static_cast<std::uint64_t>(K) * 8

@@ -2,8 +2,8 @@
 // the B200 float scan:  db_query [-r R] [-m MA] [-b BATCH_SIZE] [-g GPU] [-o results.bin]
 //                                db_file query_file groundtruth_file
 // Same defaults (r=100, ma=1; batch=1 -> here "all queries in one batch") and the same CSV on
-// stdout.  Quantisers: (16,4) (32,4) (4,8) (8,8) (16,8); the 16-bit ones of get_scan_func
-// (query_common.hpp:122-147) are refused.  -o dumps per query r uint32 ids then r float32
+// stdout.  Quantisers: every pair of get_scan_func (query_common.hpp:122-147): (16,4) (32,4) (4,8) (8,8) (16,8)
+// (2,16) (4,16) (8,16).  -o dumps per query r uint32 ids then r float32
 // distances, ascending by distance, for tests.
 #include <unistd.h>
 

@@ -138,11 +138,13 @@ def archive_case(ref, name, seed, dim, m, n, K):
 
 
 def adc_case(name, seed, dim, m, bits, n, nq, r, K=0, ma=1, opq=False):
-    """db_query (plain ADC, "next" row N4): scanner_simple over 8-bit or 4-bit codes, flat or IVF."""
+    """db_query (plain ADC, "next" row N4): scanner_simple over 4-, 8- or 16-bit codes, flat or IVF."""
     rng = np.random.default_rng(seed)
     cs = m * bits // 8
-    out = dict(dim=dim, m=m, bits=bits, r=r, ma=ma, codebooks=rng.standard_normal((m, 1 << bits, dim // m)).astype(np.float32),
-               queries=synth.make_queries(rng, nq, dim))
+    # 16-bit quantisers: the codebooks (m x 65536 x 2 floats) are the lattice of synth.lattice_codebook16, regenerated by
+    # the tests instead of being stored (test_oracle.adc_db)
+    cb = synth.lattice_codebook16(m) if bits == 16 else rng.standard_normal((m, 1 << bits, dim // m)).astype(np.float32)
+    out = dict(dim=dim, m=m, bits=bits, r=r, ma=ma, codebooks=cb, queries=synth.make_queries(rng, nq, dim) * (2.0 if bits == 16 else 1.0))
     if opq:
         out["rotation"] = np.ascontiguousarray(np.linalg.qr(rng.standard_normal((dim, dim)))[0].astype(np.float32))
     if K:
@@ -156,6 +158,8 @@ def adc_case(name, seed, dim, m, bits, n, nq, r, K=0, ma=1, opq=False):
         out["offsets"] = np.array([0, n], np.int64)
     out["codes"] = rng.integers(0, 256, (n, cs), dtype=np.uint8)
     out["ref_ids"], out["ref_dists"] = RefAdc().search(out, out["queries"], ma, r)
+    if bits == 16:
+        del out["codebooks"]
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, "first distances", out["ref_dists"][0, :3])
 
@@ -192,6 +196,10 @@ def main():
         adc_case("adc_ivf_16x8", seed=110, dim=128, m=16, bits=8, n=6000, nq=8, r=20, K=16, ma=5)
     if want("adc_ivf_opq_32x4"):
         adc_case("adc_ivf_opq_32x4", seed=111, dim=96, m=32, bits=4, n=5000, nq=6, r=16, K=12, ma=4, opq=True)
+    if want("adc_flat_2x16"):
+        adc_case("adc_flat_2x16", seed=113, dim=4, m=2, bits=16, n=4000, nq=8, r=20)
+    if want("adc_ivf_8x16"):
+        adc_case("adc_ivf_8x16", seed=114, dim=16, m=8, bits=16, n=6000, nq=8, r=20, K=16, ma=5)
     if want("archives"):
         archive_case(ref, "archives", seed=108, dim=32, m=16, n=300, K=6)
     # OPQ: the rotation sits between the residuals and the tables

@@ -7,6 +7,18 @@ def make_pq(rng, dim, m):
     return rng.standard_normal((m, 16, dim // m)).astype(np.float32)
 
 
+def lattice_codebook16(m):
+    """A 16-bit product quantiser whose codebooks need no storage: sub-quantiser j (2-d sub-vectors) has the 65 536
+    centroids of a 256 x 256 lattice, centroid c = ((c & 255) - 127.5) / 32 + j / 64, ((c >> 8) - 127.5) / 32 - j / 64
+    (exactly representable in float32).  Shape m x 65536 x 2."""
+    c = np.arange(65536)
+    cb = np.empty((m, 65536, 2), np.float32)
+    for j in range(m):
+        cb[j, :, 0] = ((c & 255) - 127.5) / 32 + j / 64
+        cb[j, :, 1] = ((c >> 8) - 127.5) / 32 - j / 64
+    return cb
+
+
 def make_codes(rng, n, m):
     """i.i.d. uniform nibbles, generated directly as bytes (row-major n x m/2)."""
     return rng.integers(0, 256, (n, m // 2), dtype=np.uint8)

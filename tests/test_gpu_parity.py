@@ -1010,9 +1010,11 @@ def test_adc_search_golden(qadc, oracle, name):
     ix.close()
 
 
-@pytest.mark.parametrize("m,bits,ivf", [(8, 8, False), (16, 8, False), (4, 8, True), (16, 4, False), (32, 4, True)])
+@pytest.mark.parametrize("m,bits,ivf", [(8, 8, False), (16, 8, False), (4, 8, True), (16, 4, False), (32, 4, True),
+                                        (2, 16, False), (4, 16, True), (8, 16, False)])
 def test_adc_search_larger(qadc, oracle, m, bits, ivf):
-    """Splits, compaction rounds, duplicate codes (distance ties broken by scan order), r = 100."""
+    """Splits, compaction rounds, duplicate codes (distance ties broken by scan order), r = 100; every (nsq, bits) pair
+    of get_scan_func (query_common.hpp:122-147), the 16-bit ones with their 65 536-entry tables in global memory."""
     rng = np.random.default_rng(200 + m + bits)
     dim, n, nq, r = 8 * m, 150000, 9, 100
     db = dict(dim=dim, m=m, bits=bits, codebooks=rng.standard_normal((m, 1 << bits, dim // m)).astype(np.float32))
@@ -1058,4 +1060,25 @@ def test_adc_short_database_and_errors(qadc, oracle):
         ix.adc_search(q, 2, 8)                           # flat database: ma must be 1
     ix.close()
     with pytest.raises(qadc.QadcError):
-        qadc.Index(0).set_pq(32, 2, rng.standard_normal((2, 65536, 16)).astype(np.float32), bits=16)   # 16-bit: unsupported
+        qadc.Index(0).set_pq(24, 3, rng.standard_normal((3, 256, 8)).astype(np.float32), bits=8)   # (3,8): not a get_scan_func pair
+
+
+def test_gpu_encoder_16bit_matches_oracle(qadc, oracle):
+    """16-bit sub-quantisers: nearest of 65 536 centroids per sub-vector, codes as little-endian uint16
+    (multiple_set_bits_native<std::uint16_t>, quantizers.hpp:36-47) == the oracle's encoder, then searched as a plain-ADC
+    database == the oracle.  (The reference's own encoder goes through find_k_neighbors, whose stride is wrong for more
+    than 256 centroids, neighbors.cpp:64 — no golden codes exist for this case.)"""
+    rng = np.random.default_rng(1616)
+    m, dim, n, nq, r = 4, 8, 3000, 6, 30
+    cb = synth.lattice_codebook16(m)
+    base = (3.0 * rng.standard_normal((n, dim))).astype(np.float32)
+    ix = qadc.Index(0)
+    ix.set_pq(dim, m, cb, bits=16)
+    codes = ix.encode(base)
+    assert codes.shape == (n, 2 * m) and np.array_equal(codes, oracle.encode(base, m, cb, 16))
+    ix.adc_load(codes)
+    q = (3.0 * synth.make_queries(rng, nq, dim)).astype(np.float32)
+    ids, d, cnt = ix.adc_search(q, 1, r)
+    exp = oracle.adc_search(dict(dim=dim, m=m, bits=16, codebooks=cb, codes=codes, offsets=np.array([0, n], np.int64)), q, 1, r)
+    assert np.array_equal(cnt, exp["count"]) and np.array_equal(ids, exp["ids"]) and np.array_equal(d, exp["d"])
+    ix.close()

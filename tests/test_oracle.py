@@ -221,11 +221,13 @@ def test_full_pipeline_self_consistent(oracle, name):
         assert np.array_equal(ids, res["ids"][q]) and np.array_equal(d, res["d"][q]) and cnt == res["count"][q]
 
 
-ADC = ["adc_flat_8x8", "adc_ivf_16x8", "adc_ivf_opq_32x4"]   # db_query (plain ADC): 8-bit flat / IVF, 4-bit IVF + OPQ
+# db_query (plain ADC): 8-bit flat / IVF, 4-bit IVF + OPQ, 16-bit flat / IVF (lattice codebooks, synth.lattice_codebook16)
+ADC = ["adc_flat_8x8", "adc_ivf_16x8", "adc_ivf_opq_32x4", "adc_flat_2x16", "adc_ivf_8x16"]
 
 
 def adc_db(g):
-    db = dict(dim=int(g["dim"]), m=int(g["m"]), bits=int(g["bits"]), codebooks=g["codebooks"], codes=g["codes"],
+    cb = g["codebooks"] if "codebooks" in g else synth.lattice_codebook16(int(g["m"]))
+    db = dict(dim=int(g["dim"]), m=int(g["m"]), bits=int(g["bits"]), codebooks=cb, codes=g["codes"],
               offsets=g["offsets"])
     if "centroids" in g:
         db.update(centroids=g["centroids"], labels=g["labels"])
