@@ -310,10 +310,10 @@ int seed_shared_bound(qadc_ctx* ctx, const int32_t* d_assign, const int8_t* d_qt
         unsigned int* done = hist + static_cast<size_t>(nq) * 128;
         if (ctx->m == 16)
             flat_prefix_pass_kernel<16, 0><<<pgrid, 256, 0, ctx->stream>>>(ctx->d_starts_native, n_prefix, d_qtables, hist, done,
-                                                                          ctx->b_sbound.as<int>(), 126, r, 0, nullptr, nullptr, make_pipek());
+                                                                          ctx->b_sbound.as<int>(), 126, r, 0, nullptr, nullptr, 0u, make_pipek());
         else
             flat_prefix_pass_kernel<32, 0><<<pgrid, 256, 0, ctx->stream>>>(ctx->d_starts_native, n_prefix, d_qtables, hist, done,
-                                                                          ctx->b_sbound.as<int>(), 126, r, 0, nullptr, nullptr, make_pipek());
+                                                                          ctx->b_sbound.as<int>(), 126, r, 0, nullptr, nullptr, 0u, make_pipek());
         ctx->launches++;
         QCK(cudaGetLastError());
         return QADC_OK;
@@ -551,7 +551,10 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         const int nsplit = static_cast<int>(std::min(n_prefix, kPrefSampleMax) / kPrefSplit);
         ENSURE(ctx->b_prov, static_cast<size_t>(nq) * te);
         ENSURE(ctx->b_ghist, static_cast<size_t>(nq) * 129 * 4);   // [nq][128] the scan's global histograms | [nq] candidate counts
-        ENSURE(ctx->b_cand, static_cast<size_t>(nq) * kPrefCandCap * 4);
+        // candidate slots per query: 16 384, fewer for large batches (256 MB in all, never below the 4096 the one-buffer
+        // path of the final kernel takes; a query with more candidates than slots evaluates its whole prefix)
+        const uint32_t cand_cap = static_cast<uint32_t>(std::max<size_t>(kPrefFastCap, std::min<size_t>(kPrefCandCap, (size_t(64) << 20) / nq)));
+        ENSURE(ctx->b_cand, static_cast<size_t>(nq) * cand_cap * 4);
         ENSURE(ctx->b_plists, static_cast<size_t>(nq) * nsplit * r * 4);
         ENSURE(ctx->b_sbound, static_cast<size_t>(nq) * 4);
         QCK(cudaMemsetAsync(ctx->b_ghist.p, 0, static_cast<size_t>(nq) * 129 * 4, ctx->stream));   // one memset for both
@@ -560,7 +563,7 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         fa.starts = ctx->d_starts; fa.native = ctx->d_starts_native; fa.n_prefix = n_prefix;
         fa.tables = ctx->b_tables.as<float>(); fa.r = r; fa.nsplit = nsplit; fa.sample_lists = ctx->b_plists.as<uint32_t>();
         fa.prov_qt = ctx->b_prov.as<int8_t>(); fa.cand_count = ctx->b_ghist.as<unsigned int>() + static_cast<size_t>(nq) * 128;
-        fa.cand = ctx->b_cand.as<uint32_t>(); fa.seed_out = ctx->b_sbound.as<int>();
+        fa.cand = ctx->b_cand.as<uint32_t>(); fa.cand_cap = cand_cap; fa.seed_out = ctx->b_sbound.as<int>();
         const uint32_t n_sb = (n_prefix + kSbVec - 1) / kSbVec;
         dim3 sgrid(nsplit, nq), pgrid(flat_prep_splits(ctx, n_sb, nq), nq);
         const PipeK pk = make_pipek();
@@ -568,13 +571,13 @@ int tables_device(qadc_ctx* ctx, const float* d_queries, int nq, int ma, int r, 
         if (M == 16) {
             flat_prefix_sample_kernel<16><<<sgrid, kSelThreads, 0, ctx->stream>>>(fa);
             flat_prefix_bound_kernel<16><<<nq, kSelThreads, 0, ctx->stream>>>(fa);
-            flat_prefix_pass_kernel<16, 1><<<pgrid, 256, 0, ctx->stream>>>(fa.native, n_prefix, fa.prov_qt, nullptr, nullptr, nullptr, 127, r, 0, fa.cand_count, fa.cand, pk);
+            flat_prefix_pass_kernel<16, 1><<<pgrid, 256, 0, ctx->stream>>>(fa.native, n_prefix, fa.prov_qt, nullptr, nullptr, nullptr, 127, r, 0, fa.cand_count, fa.cand, cand_cap, pk);
             flat_bounds_final_kernel<16><<<nq, kSelThreads, 0, ctx->stream>>>(fa, tabs, ctx->b_tmin.as<float>(), ctx->b_qtables.as<int8_t>(),
                                                                              ctx->b_qmin.as<float>(), ctx->b_qmax.as<float>(), ctx->d_err);
         } else {
             flat_prefix_sample_kernel<32><<<sgrid, kSelThreads, 0, ctx->stream>>>(fa);
             flat_prefix_bound_kernel<32><<<nq, kSelThreads, 0, ctx->stream>>>(fa);
-            flat_prefix_pass_kernel<32, 1><<<pgrid, 256, 0, ctx->stream>>>(fa.native, n_prefix, fa.prov_qt, nullptr, nullptr, nullptr, 127, r, 0, fa.cand_count, fa.cand, pk);
+            flat_prefix_pass_kernel<32, 1><<<pgrid, 256, 0, ctx->stream>>>(fa.native, n_prefix, fa.prov_qt, nullptr, nullptr, nullptr, 127, r, 0, fa.cand_count, fa.cand, cand_cap, pk);
             flat_bounds_final_kernel<32><<<nq, kSelThreads, 0, ctx->stream>>>(fa, tabs, ctx->b_tmin.as<float>(), ctx->b_qtables.as<int8_t>(),
                                                                              ctx->b_qmin.as<float>(), ctx->b_qmax.as<float>(), ctx->d_err);
         }

@@ -37,7 +37,7 @@ constexpr int kPrefSplit = 2048;              // sample vectors per CTA of the s
 constexpr uint32_t kPrefSampleMax = 65536;    // sample = the first min(n_prefix, 65 536) prefix vectors, whole splits
 constexpr uint32_t kPrefMinNative = 131072;   // shorter prefixes keep the plain float scan
 constexpr int kPrefMaxR = 512;                // r <= a quarter of a split
-constexpr int kPrefCandCap = 16384;           // candidate slots per query
+constexpr int kPrefCandCap = 16384;           // candidate slots per query (fewer for large batches: FlatPrepArgs::cand_cap)
 constexpr int kPrefFastCap = 2 * kSelCap;     // candidates whose distances fit one shared-memory buffer
 
 struct FlatPrepArgs {
@@ -49,7 +49,8 @@ struct FlatPrepArgs {
     uint32_t* sample_lists;       // [nq][nsplit][r] float bits: the r smallest distances of every sample split
     int8_t* prov_qt;              // [nq][M*16] provisional lower-bound tables
     unsigned int* cand_count;     // [nq] (zeroed by the caller)
-    uint32_t* cand;               // [nq][kPrefCandCap] prefix positions
+    uint32_t* cand;               // [nq][cand_cap] prefix positions
+    uint32_t cand_cap;            // candidate slots per query
     int* seed_out;                // [nq] the scan's shared bound
 };
 
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) flat_prefix_pass_kernel(const uint8_t* __
                                                                const int8_t* __restrict__ qt, unsigned int* hist,
                                                                unsigned int* done, int* rth, int rth_cap, int r, int margin,
                                                                unsigned int* __restrict__ cand_count,
-                                                               uint32_t* __restrict__ cand, const PipeK pk) {
+                                                               uint32_t* __restrict__ cand, uint32_t cand_cap, const PipeK pk) {
     constexpr int kQuads = M / 4, kSbBytes = M * 128;
     __shared__ uint4 tab[M];
     __shared__ unsigned int h[128];
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) flat_prefix_pass_kernel(const uint8_t* __
                     atomicAdd(&h[s], 1u);
                 } else {
                     const unsigned int slot = atomicAdd(&cand_count[q], 1u);
-                    if (slot < static_cast<unsigned int>(kPrefCandCap)) cand[static_cast<size_t>(q) * kPrefCandCap + slot] = pos;
+                    if (slot < cand_cap) cand[static_cast<size_t>(q) * cand_cap + slot] = pos;
                 }
             }
         }
@@ -244,9 +245,9 @@ __global__ void __launch_bounds__(kSelThreads) flat_bounds_final_kernel(const Fl
     for (int i = tid; i < TE; i += kSelThreads) tab[i] = a.tables[static_cast<size_t>(q) * TE + i];
     if (tid == 0) s_seed = 0;
     const unsigned int n_found = a.cand_count[q];
-    const bool all = n_found > static_cast<unsigned int>(kPrefCandCap);   // more candidates than slots: evaluate every prefix vector
+    const bool all = n_found > a.cand_cap;   // more candidates than slots: evaluate every prefix vector
     const uint32_t n = all ? a.n_prefix : n_found;
-    const uint32_t* cand = a.cand + static_cast<size_t>(q) * kPrefCandCap;
+    const uint32_t* cand = a.cand + static_cast<size_t>(q) * a.cand_cap;
     const bool fast = !all && n <= static_cast<uint32_t>(kPrefFastCap);
     uint32_t* vals = &vbuf[0][0];
     float qmax;
