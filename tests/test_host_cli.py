@@ -402,22 +402,28 @@ def test_file_formats_random_shapes(cli, qadc, tmp_path):
 
 
 @pytest.mark.gpu
-def test_db_build_8bit_then_db_query(cli, oracle, tmp_path):
-    """8-bit quantiser: floats -> db_build (GPU encoder; flat database in the reference's archive layout)
+@pytest.mark.parametrize("dim,m,bits,n", [(64, 8, 8, 15000), (8, 4, 16, 3000)])
+def test_db_build_8bit_then_db_query(cli, oracle, tmp_path, dim, m, bits, n):
+    """8- and 16-bit quantisers: floats -> db_build (GPU encoder; flat database in the reference's archive layout)
     -> db_query == the oracle's encoder + plain ADC on the same inputs."""
     from qadc_b200 import dbfile
     rng = np.random.default_rng(71)
-    dim, m, bits, n, nq, r = 64, 8, 8, 15000, 8, 20
-    cb = rng.standard_normal((m, 256, dim // m)).astype(np.float32)
-    base = rng.standard_normal((n, dim)).astype(np.float32)
-    q = synth.make_queries(rng, nq, dim)
+    nq, r = 8, 20
+    if bits == 16:
+        cb = synth.lattice_codebook16(m)
+        base = (3.0 * rng.standard_normal((n, dim))).astype(np.float32)
+        q = (3.0 * synth.make_queries(rng, nq, dim)).astype(np.float32)
+    else:
+        cb = rng.standard_normal((m, 256, dim // m)).astype(np.float32)
+        base = rng.standard_normal((n, dim)).astype(np.float32)
+        q = synth.make_queries(rng, nq, dim)
     dbfile.write_pq_data(tmp_path / "q.pq.data", dim, m, cb, bits=bits)
     dbfile.write_vecs(tmp_path / "base.fvecs", base)
     dbfile.write_vecs(tmp_path / "q.fvecs", q)
     p = subprocess.run([os.path.join(HOST, "db_build"), str(tmp_path / "q.pq.data"), str(tmp_path / "base.fvecs"),
                         str(tmp_path / "db.flat")], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
-    assert "pq (dim=64, sq=8x8)" in p.stderr
+    assert f"pq (dim={dim}, sq={m}x{bits})" in p.stderr
     codes = oracle.encode(base, m, cb, bits)
     assert np.array_equal(dbfile.read_db(tmp_path / "db.flat")["codes"], codes)
     exp = oracle.adc_search(dict(dim=dim, m=m, bits=bits, codebooks=cb, codes=codes, offsets=np.array([0, n], np.int64)), q, 1, r)
