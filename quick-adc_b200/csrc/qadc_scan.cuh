@@ -605,6 +605,39 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1) scan_flat_kernel(const FlatS
     }
 }
 
+// Final merge of a CTA's NW sorted warp lists into one sorted list of r keys (kEmptyKey-padded) in global memory.
+// Only keys at or below the query's shared bound can be in its top r (at least r scanned vectors are at or below it), and
+// the warp lists are sorted: each warp contributes that prefix of its list and the CTA sorts the next power of two above
+// their total.  With one bound per query (hist_publish) that is a handful of keys per CTA instead of the 2048 slots of NW
+// full lists — a 66-stage block-wide sort at the end of each of the up to 16 CTAs an SM runs per launch.  Every thread of
+// the CTA calls it; `wcount` = NW ints of shared memory, `scratch` = max(r, total keys) u64 of shared memory that no warp
+// uses any more.  Not inlined: its registers must not compete with the scan loop's (inlined, ptxas spilled a loop-carried
+// address of the 128-register kernel).
+template <int NW>
+__device__ __noinline__ void cta_merge_bounded(const uint64_t* keys, uint64_t* scratch, int* wcount, const int* sbound,
+                                               uint64_t* dst, int r) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();      // every warp has consumed its ring and left the candidate path
+    const int vmax = load_shared_bound(sbound);
+    int mine = 0;
+    for (int base = 0; base < r; base += 32) {
+        const int i = base + lane;
+        const bool keep = i < r && keys[i] != kEmptyKey && static_cast<int>(keys[i] >> 48) <= vmax;
+        mine += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (lane == 0) wcount[warp] = mine;
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w2 = 0; w2 < NW; ++w2) { const int c = wcount[w2]; if (w2 < warp) off += c; total += c; }
+    int n_sort = 64;
+    while (n_sort < total) n_sort <<= 1;
+    for (int i = lane; i < mine; i += 32) scratch[off + i] = keys[i];
+    for (int i = total + threadIdx.x; i < max(n_sort, r); i += NW * 32) scratch[i] = kEmptyKey;
+    __syncthreads();
+    bitonic_sort_u64(scratch, n_sort, threadIdx.x, NW * 32, BlockSync());
+    for (int i = threadIdx.x; i < r; i += NW * 32) dst[i] = scratch[i];
+}
+
 // ------------------------------------------------------------------------------------------
 // Flat scan, one query per pass, 16x4 codes, PER-WARP rings: grid = (chunks, queries), NW warps per CTA, no producer
 // warp.  Warp w owns superblocks sb0 + w, sb0 + w + NW, ... of the CTA's chunk (the CTA still sweeps its chunk
@@ -835,16 +868,8 @@ __global__ void __launch_bounds__(NW * 32, 1) scan_flat_wr_kernel(const FlatScan
         store_list(wl, a.lists + (static_cast<size_t>(q) * a.n_lists + blockIdx.x * NW + warp) * a.r, a.r, lane);
         return;
     }
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(rings);
-    int n_sort = 64;
-    while (n_sort < NW * a.r) n_sort <<= 1;
-    __syncthreads();   // every warp has consumed its ring
-    for (int i = lane; i < a.r; i += 32) scratch[warp * a.r + i] = wl.keys[i];
-    for (int i = NW * a.r + threadIdx.x; i < n_sort; i += NW * 32) scratch[i] = kEmptyKey;
-    __syncthreads();
-    bitonic_sort_u64(scratch, n_sort, threadIdx.x, NW * 32, BlockSync());
-    uint64_t* dst = a.lists + (static_cast<size_t>(q) * a.n_lists + blockIdx.x) * a.r;
-    for (int i = threadIdx.x; i < a.r; i += NW * 32) dst[i] = scratch[i];
+    cta_merge_bounded<NW>(wl.keys, reinterpret_cast<uint64_t*>(rings), hist, sbound,
+                          a.lists + (static_cast<size_t>(q) * a.n_lists + blockIdx.x) * a.r, a.r);
 }
 
 // ------------------------------------------------------------------------------------------
