@@ -460,7 +460,9 @@ def run_ours(args):
             acc[0] += ev[0].elapsed_time(ev[1]) / 5
             acc[1] += ev[1].elapsed_time(ev[2]) / 5
         exchange = {"search_ms_per_rank": per_rank(acc[0]), "allgather_and_merge_ms_per_rank": per_rank(acc[1]),
-                    "note": "5 untimed steps after the timed region; the exchange includes waiting for the slowest rank"}
+                    "note": "5 untimed steps after the timed region, each behind a barrier + synchronize: the search time here includes "
+                            "the host's launch latency of its short kernels (in the timed loop the launches of step i+1 are queued "
+                            "while step i scans), the exchange includes waiting for the slowest rank"}
     # informational: the same step with 4 queries sharing every pass over the codes.  A quarter of
     # the HBM traffic, so the scan is bound by integer issue instead of HBM (and draws less power);
     # not the configuration `value` / `roofline` are quoted on.
