@@ -702,7 +702,8 @@ void qadc_destroy(qadc_ctx* c) {
     cudaFree(c->d_codebooks); cudaFree(c->d_rotation); cudaFree(c->d_centroids);
     for (DevBuf* b : {&c->staging, &c->b_queries, &c->b_assign, &c->b_tables, &c->b_tmin, &c->b_qmax, &c->b_qmin,
                       &c->b_qtables, &c->b_lists, &c->b_plists, &c->b_ids, &c->b_dists, &c->b_counts, &c->b_keys,
-                      &c->b_dump, &c->b_hist, &c->b_sbound, &c->b_cdist, &c->b_adc_dists})
+                      &c->b_dump, &c->b_hist, &c->b_sbound, &c->b_cdist, &c->b_adc_dists, &c->b_qmin_raw, &c->b_prov,
+                      &c->b_cand, &c->b_ghist})
         cudaFree(b->p);
     cudaFree(c->d_rows); cudaFree(c->d_row_off); cudaFree(c->d_adc_labels);
     cudaFree(c->d_err);
